@@ -1,0 +1,219 @@
+/* sgnn_b200.h -- C ABI of libsgnn_b200.so (hand-written sm_100a kernels).
+ *
+ * Drop-in boundary for the sparse-convolution + generative-upsampling hot path that
+ * SG-NN's torch/model.py reaches through `import sparseconvnet as scn` (reference
+ * torch/model.py:7).  The reference binds that path through scn's pybind module
+ * (upstream sparseconvnet/SCN/pybind.cpp -- NOT present under /root/reference); each
+ * entry point below names the reference call site(s) in torch/model.py it serves and
+ * the upstream scn function whose role it takes.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - every pointer marked "dev" is a CUDA device pointer owned by the caller;
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it
+ *     (no host synchronisation, no allocation, no global state) and is re-entrant for
+ *     distinct (buffers, stream) pairs;
+ *   - return value: SGNN_OK or a negative SGNN_E_* code; nothing throws across the ABI;
+ *   - features are row-major [n_rows, ld] with `ld` (elements) >= channels;
+ *   - coordinates are int32 [n,4] = (z, y, x, batch)  (model.py:321, scene_dataloader.py:17,30);
+ *   - filter offsets are numbered row-major over (dz,dy,dx), last fastest:
+ *       3^3 submanifold: k = (dz+1)*9 + (dy+1)*3 + (dx+1);   2^3 stride 2: k = (z&1)*4 + (y&1)*2 + (x&1);
+ *   - weights are [K, Cin, Cout] exactly as scn stores them (App. A.4);
+ *   - rulebooks are OUTPUT-STATIONARY neighbour tables nbr[k][row] (k-major, -1 = absent),
+ *     the transpose of scn's per-offset (in,out) pair lists: pair list k == {(nbr[k][j], j) : nbr[k][j] >= 0}.
+ */
+#ifndef SGNN_B200_H
+#define SGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGNN_VERSION 100
+
+enum {
+  SGNN_OK = 0,
+  SGNN_E_INVALID = -1,     /* bad argument (null pointer, negative size, unsupported channel count) */
+  SGNN_E_CUDA = -2,        /* a CUDA runtime call failed; sgnn_last_cuda_error() has the code */
+  SGNN_E_TOO_LARGE = -3,   /* extent or row count exceeds the 2^31-1 indexing of this build */
+  SGNN_E_UNSUPPORTED = -4, /* valid in scn, not implemented here (e.g. filter size other than 3 / 2) */
+  SGNN_E_ALIGN = -5        /* pointer / leading dimension breaks an alignment rule stated below */
+};
+
+enum { SGNN_F32 = 0, SGNN_BF16 = 1 };
+
+/* Conv tile height: rows per CTA of sgnn_conv_forward. */
+#define SGNN_CONV_TILE 128
+
+/* Active-site set at one resolution: a bitmask over the (batch, z, y, x) extent, 64 x-cells per
+ * word, plus an exclusive popcount prefix (raster rank) and an optional rank->row permutation.
+ * Plays the role of scn's Metadata SparseGrid hash maps.  The struct lives on
+ * the host; the three arrays are device memory supplied by the caller:
+ *   mask        [n_words]      uint64
+ *   prefix      [n_words + 1]  int32   prefix[n_words] == number of active cells
+ *   row_of_rank [n_rows]       int32   or NULL when row id == raster rank                        */
+typedef struct SgnnGrid {
+  int32_t nb, d0, d1, d2;  /* batch count and extent in cells along z, y, x */
+  int32_t wx;              /* words per x-row = (d2 + 63) / 64 */
+  int32_t reserved;
+  int64_t n_words;         /* nb * d0 * d1 * wx */
+  uint64_t* mask;
+  int32_t* prefix;
+  int32_t* row_of_rank;
+} SgnnGrid;
+
+/* Bytes of scratch the grid/scan/compaction calls need for `n_items` scanned items. */
+size_t sgnn_scan_scratch_bytes(int64_t n_items);
+/* Scratch for the compaction calls (sgnn_dense_to_sparse, sgnn_heads_compact) over n_items candidates. */
+size_t sgnn_compact_scratch_bytes(int64_t n_items);
+
+/* ---- a1: scn.InputLayer(3, size, mode=0)  (model.py:51,216,224,265; upstream InputLayer_updateOutput)
+ * Builds mask/prefix/row_of_rank from caller-ordered coordinates.  coords: dev [n,4], int64 when
+ * coords_i64 != 0 (the LongTensor the reference passes) else int32.  coords_i32_out: dev [n,4] int32 copy
+ * or NULL.  A coordinate outside the extent sets *status (dev int32, may be NULL) to 1 and is ignored.
+ * Duplicate coordinates: the highest row id owns the cell (scn: later insert overwrites, App. A.2). */
+int sgnn_grid_build(const SgnnGrid* g, const void* coords, int coords_i64, int64_t n,
+                    int32_t* coords_i32_out, int32_t* status, void* scratch, size_t scratch_bytes,
+                    void* stream);
+
+/* ---- a4 (site set): scn.Convolution(3,C,C,2,2) output sites (model.py:44; upstream
+ * Convolution_InputSgsToRulesAndOutputSgs).  coarse cell = fine cell >> 1; coarse rows are numbered in
+ * raster order (upstream order is implementation defined), so coarse->row_of_rank is
+ * unused.  coarse extent <= ceil(fine extent / 2) per axis; fine cells whose parent falls outside the coarse
+ * extent are dropped, as scn drops parents >= its (S-2)/2+1 output size. */
+int sgnn_grid_coarsen(const SgnnGrid* fine, const SgnnGrid* coarse, void* scratch,
+                      size_t scratch_bytes, void* stream);
+
+/* ---- a7: metadata.getSpatialLocations (model.py:380).  Coordinates of a raster-ordered grid. */
+int sgnn_grid_enumerate(const SgnnGrid* g, int32_t* coords_out, void* stream);
+
+/* Row lookup: rows_out[i] = row of (coords[i].zyx >> shift, batch) or -1. */
+int sgnn_grid_lookup(const SgnnGrid* g, const int32_t* coords, int64_t n, int shift,
+                     int32_t* rows_out, void* stream);
+
+/* ---- a2: submanifold 3^3 rulebook (first SubmanifoldConvolution per resolution, model.py:53,217,225,266;
+ * upstream Metadata::getSubmanifoldRuleBook).  nbr: dev [27][n] int32. */
+int sgnn_rulebook_submanifold(const SgnnGrid* g, const int32_t* coords, int64_t n, int32_t* nbr,
+                              void* stream);
+
+/* ---- a4 (rules): filter 2 stride 2 rulebook (upstream Metadata::getRuleBook).
+ *   parent   dev [n_fine]        coarse_row * 8 + k, or -1 if the fine site has no coarse parent
+ *   children dev [8][n_coarse]   fine row at offset k of coarse row, or -1                       */
+int sgnn_rulebook_strided(const SgnnGrid* coarse, const int32_t* fine_coords, int64_t n_fine,
+                          int32_t* parent, int32_t* children, int64_t n_coarse, void* stream);
+
+/* Epilogue slot of a convolution: y = acc (+ residual); if scale: y = y*scale[c] + shift[c]
+ * (one fused multiply-add); if relu: y = max(y, 0).  out == NULL disables the slot. */
+typedef struct SgnnEpilogue {
+  void* out;           /* dev [n_out, ld] */
+  int32_t ld;
+  int32_t relu;
+  const float* scale;  /* dev [cout] or NULL */
+  const float* shift;  /* dev [cout] or NULL */
+} SgnnEpilogue;
+
+/* ---- a3 / a4 / a9: sparse convolution forward, gather -> K x (Cin x Cout) contraction, no scatter
+ * (model.py:32,38,40,44,179,186,254; upstream SubmanifoldConvolution_updateOutput / Convolution_updateOutput).
+ *   out[j] = sum_{k ascending} in[nbr[k][j] >> gather_shift] @ W[k]    over nbr[k][j] >= 0
+ * fp32 path: accumulation is one fmaf chain per output element, k ascending then ci ascending, from +0
+ * (bit-reproducible; oracle/o3.c restates it).  Cout in {4,8,12,16}; Cin <= 64.
+ * child_mode = 1 evaluates the convolution on the 8 children of every row of a parent set straight from the
+ * PARENT rulebook (generative upsampling, model.py:192-207,224-225): output row 8*p+c (c = z-major child
+ * index), offset (dz,dy,dx) of child c reads parent neighbour floor((c_a+d_a)/2) per axis; the x8 replicated
+ * features of model.py:202 never exist in memory.
+ * Alignment: when ld_in % 4 == 0 and `in` is 16-byte aligned the gather moves 16-byte chunks, otherwise
+ * 4-byte elements; outputs/residual need ld % 4 == 0 and 16-byte alignment (else SGNN_E_ALIGN). */
+typedef struct SgnnConvArgs {
+  const void* in;         /* dev [n_in, ld_in] */
+  int32_t ld_in;
+  int32_t dtype;          /* SGNN_F32 | SGNN_BF16 (features and weights) */
+  const int32_t* nbr;     /* dev [K][nbr_stride] */
+  int64_t nbr_stride;
+  int32_t K;              /* 27 or 8 */
+  int32_t child_mode;     /* 0: plain; 1: outputs are the 8 children of each nbr row (K must be 27) */
+  const void* weight;     /* dev [K][cin][cout] */
+  int32_t cin, cout;
+  int64_t n_out;          /* output rows (8 * parent rows in child mode) */
+  const void* residual;   /* dev [n_out, ld_res] or NULL */
+  int32_t ld_res;
+  int32_t reserved;
+  SgnnEpilogue a, b;
+} SgnnConvArgs;
+int sgnn_conv_forward(const SgnnConvArgs* args, void* stream);
+
+/* ---- scn.Deconvolution(3,Cin,Cout,2,2) (north_star operator surface; upstream Deconvolution_updateOutput)
+ *   out[i] = in[parent[i] >> 3] @ W[parent[i] & 7]          (rows with parent < 0 get zeros) */
+int sgnn_deconv_forward(const void* in, int32_t ld_in, int32_t dtype, const int32_t* parent,
+                        const void* weight, int32_t cin, int32_t cout, int64_t n_fine,
+                        const SgnnEpilogue* ep, void* stream);
+
+/* ---- a6: scn.UnPooling(3,2,2) (inside FullyConvolutionalNet, model.py:180,255; upstream UnPooling_updateOutput)
+ *   out[i][0:c] = in[parent[i] >> 3][0:c], optional per-channel affine + relu (folds the trailing BatchNormReLU) */
+int sgnn_unpool(const float* in, int32_t ld_in, const int32_t* parent, int32_t c, int64_t n_fine,
+                const SgnnEpilogue* ep, void* stream);
+
+/* ---- a5: scn.BatchNormReLU eval mode (model.py:37,39,42,45,181,187,256; upstream BatchNormalization_updateOutput)
+ *   y = max(fma(x, scale[c], shift[c]), 0)   scale = gamma * rsqrt(var + 1e-4), shift = beta - mean*scale
+ * (host folds; relu optional).  x and y may alias. */
+int sgnn_affine_relu(const float* x, int32_t ld_x, float* y, int32_t ld_y, int64_t n, int32_t c,
+                     const float* scale, const float* shift, int32_t relu, void* stream);
+
+/* ---- a6: AddTable / JoinTable helpers (row-wise add; column-slot copy) */
+int sgnn_add_rows(const float* a, int32_t ld_a, const float* b, int32_t ld_b, float* y,
+                  int32_t ld_y, int64_t n, int32_t c, void* stream);
+int sgnn_copy_cols(const float* src, int32_t ld_src, float* dst, int32_t ld_dst, int64_t n,
+                   int32_t c, void* stream);
+
+/* nn.Linear heads (model.py:189-190,230-231,258,271): y[i][o] = (sum_c ascending fma(x[i][c], w[o][c])) + b[o] */
+int sgnn_linear(const float* x, int32_t ld_x, const float* w, const float* b, float* y,
+                int32_t ld_y, int64_t n, int32_t cin, int32_t cout, void* stream);
+
+/* ---- a7: scn.SparseToDense (model.py:47,65; upstream SparseToDense_updateOutput).
+ * dense: dev [nb, c, d0, d1, d2] fp32, fully overwritten (zeros + scatter). */
+int sgnn_sparse_to_dense(const float* feats, int32_t ld, const int32_t* coords, int64_t n,
+                         int32_t c, float* dense, int32_t nb, int32_t d0, int32_t d1, int32_t d2,
+                         void* stream);
+
+/* ---- a8: GenModel.dense_coarse_to_sparse (model.py:315-336).
+ * dense_feats dev [nb,c,d0,d1,d2]; dense_out dev [nb,2,d0,d1,d2] (occ logit, sdf).
+ * keep = sigmoid(occ) > 0.5 evaluated literally in fp32.  Kept cells are compacted in raster order:
+ *   locs dev [cap,4] int32, feats dev [cap, ld_feats] = [occ, sdf, feats(c)], *count dev int32.
+ *   cand_out dev [nb*d0*d1*d2, 2] = (occ, sdf) of every cell (model.py:336), or NULL. */
+int sgnn_dense_to_sparse(const float* dense_feats, const float* dense_out, int32_t nb, int32_t c,
+                         int32_t d0, int32_t d1, int32_t d2, int32_t* locs, float* feats,
+                         int32_t ld_feats, float* cand_out, int32_t* count, void* scratch,
+                         size_t scratch_bytes, void* stream);
+
+/* ---- a9: Refinement heads + mask + compaction (model.py:230-247) on the 8*n_parent candidates.
+ *   x dev [n_cand, ld_x] post-BatchNormReLU features (16 ch); w_occ/w_sdf dev [c]; b_occ/b_sdf dev [1].
+ *   cand_out dev [n_cand,2] = (occ, sdf) for every candidate (model.py:240,247).
+ *   kept (sigmoid(occ) > 0.5), candidate order preserved:
+ *     locs dev [cap,4] = 2*parent_coords + child offset (z-major child order, model.py:195-198)
+ *     feats dev [cap, ld_feats] = [x(c), occ, sdf]   (model.py:242);  *count dev int32 */
+int sgnn_heads_compact(const float* x, int32_t ld_x, int32_t c, const float* w_occ,
+                       const float* b_occ, const float* w_sdf, const float* b_sdf,
+                       const int32_t* parent_coords, int64_t n_parent, float* cand_out,
+                       int32_t* locs, float* feats, int32_t ld_feats, int32_t* count,
+                       void* scratch, size_t scratch_bytes, void* stream);
+
+/* Candidate coordinates of model.py:192-207: out dev [8*n_parent,4]. */
+int sgnn_children_coords(const int32_t* parent_coords, int64_t n_parent, int32_t* out, void* stream);
+
+/* ---- a10: GenModel.concat_skip (model.py:338-355): dst[i][col0:col0+c] = src[row of coords[i] in g] or 0. */
+int sgnn_concat_skip(const SgnnGrid* g, const float* src, int32_t ld_src, int32_t c,
+                     const int32_t* coords, int64_t n, float* dst, int32_t ld_dst, int32_t col0,
+                     void* stream);
+
+/* int32 [n,4] -> int64 [n,4] (LongTensor coordinates at the Python boundary). */
+int sgnn_coords_to_i64(const int32_t* in, int64_t n, int64_t* out, void* stream);
+
+int sgnn_version(void);
+const char* sgnn_error_string(int code);
+int sgnn_last_cuda_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGNN_B200_H */

@@ -1,0 +1,95 @@
+"""ctypes binding of libsgnn_b200.so (include/sgnn_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a symbol is absent this
+module raises at import time, and every non-zero return code becomes a RuntimeError
+(scn raises Python exceptions from C++ asserts; the reference caller catches them at
+test_scene.py:83).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libsgnn_b200.so')
+
+SGNN_F32, SGNN_BF16 = 0, 1
+CONV_TILE = 128
+
+
+class SgnnGrid(C.Structure):
+    _fields_ = [('nb', C.c_int32), ('d0', C.c_int32), ('d1', C.c_int32), ('d2', C.c_int32),
+                ('wx', C.c_int32), ('reserved', C.c_int32), ('n_words', C.c_int64),
+                ('mask', C.c_void_p), ('prefix', C.c_void_p), ('row_of_rank', C.c_void_p)]
+
+
+class SgnnEpilogue(C.Structure):
+    _fields_ = [('out', C.c_void_p), ('ld', C.c_int32), ('relu', C.c_int32),
+                ('scale', C.c_void_p), ('shift', C.c_void_p)]
+
+
+class SgnnConvArgs(C.Structure):
+    _fields_ = [('in_', C.c_void_p), ('ld_in', C.c_int32), ('dtype', C.c_int32),
+                ('nbr', C.c_void_p), ('nbr_stride', C.c_int64), ('K', C.c_int32),
+                ('child_mode', C.c_int32), ('weight', C.c_void_p), ('cin', C.c_int32),
+                ('cout', C.c_int32), ('n_out', C.c_int64), ('residual', C.c_void_p),
+                ('ld_res', C.c_int32), ('reserved', C.c_int32),
+                ('a', SgnnEpilogue), ('b', SgnnEpilogue)]
+
+
+_P, _I, _L, _Z = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+_G, _E = C.POINTER(SgnnGrid), C.POINTER(SgnnEpilogue)
+
+# name -> (restype, argtypes); mirrors include/sgnn_b200.h one to one
+SIGNATURES = {
+    'sgnn_scan_scratch_bytes': (_Z, [_L]),
+    'sgnn_compact_scratch_bytes': (_Z, [_L]),
+    'sgnn_grid_build': (_I, [_G, _P, _I, _L, _P, _P, _P, _Z, _P]),
+    'sgnn_grid_coarsen': (_I, [_G, _G, _P, _Z, _P]),
+    'sgnn_grid_enumerate': (_I, [_G, _P, _P]),
+    'sgnn_grid_lookup': (_I, [_G, _P, _L, _I, _P, _P]),
+    'sgnn_rulebook_submanifold': (_I, [_G, _P, _L, _P, _P]),
+    'sgnn_rulebook_strided': (_I, [_G, _P, _L, _P, _P, _L, _P]),
+    'sgnn_conv_forward': (_I, [C.POINTER(SgnnConvArgs), _P]),
+    'sgnn_deconv_forward': (_I, [_P, _I, _I, _P, _P, _I, _I, _L, _E, _P]),
+    'sgnn_unpool': (_I, [_P, _I, _P, _I, _L, _E, _P]),
+    'sgnn_affine_relu': (_I, [_P, _I, _P, _I, _L, _I, _P, _P, _I, _P]),
+    'sgnn_add_rows': (_I, [_P, _I, _P, _I, _P, _I, _L, _I, _P]),
+    'sgnn_copy_cols': (_I, [_P, _I, _P, _I, _L, _I, _P]),
+    'sgnn_linear': (_I, [_P, _I, _P, _P, _P, _I, _L, _I, _I, _P]),
+    'sgnn_sparse_to_dense': (_I, [_P, _I, _P, _L, _I, _P, _I, _I, _I, _I, _P]),
+    'sgnn_dense_to_sparse': (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _Z, _P]),
+    'sgnn_heads_compact': (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _P, _P, _Z, _P]),
+    'sgnn_children_coords': (_I, [_P, _L, _P, _P]),
+    'sgnn_concat_skip': (_I, [_G, _P, _I, _I, _P, _L, _P, _I, _I, _P]),
+    'sgnn_coords_to_i64': (_I, [_P, _L, _P, _P]),
+    'sgnn_version': (_I, []),
+    'sgnn_error_string': (C.c_char_p, [_I]),
+    'sgnn_last_cuda_error': (_I, []),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            'sgnn_b200: %s not found -- run `python -c "import __graft_entry__ as g; g.build()"` '
+            '(there is no CPU or PyTorch fallback for the hot path)' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+class SgnnError(RuntimeError):
+    pass
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib.sgnn_error_string(rc).decode()
+        if rc == -2:
+            msg += ' (cudaError %d)' % lib.sgnn_last_cuda_error()
+        raise SgnnError('%s failed: %s [%d]' % (what or 'sgnn call', msg, rc))

@@ -1,0 +1,84 @@
+// common.cuh -- shared device helpers for libsgnn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/sgnn_b200.h"
+
+extern int g_sgnn_last_cuda_error;
+
+#define SGNN_CHECK_LAUNCH()                                   \
+  do {                                                        \
+    cudaError_t e__ = cudaGetLastError();                     \
+    if (e__ != cudaSuccess) {                                 \
+      g_sgnn_last_cuda_error = (int)e__;                      \
+      return SGNN_E_CUDA;                                     \
+    }                                                         \
+  } while (0)
+
+#define SGNN_CUDA(call)                                       \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) {                                 \
+      g_sgnn_last_cuda_error = (int)e__;                      \
+      return SGNN_E_CUDA;                                     \
+    }                                                         \
+  } while (0)
+
+static inline int sgnn_blocks(int64_t n, int threads, int64_t cap = (int64_t)148 * 64) {
+  int64_t b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > cap) b = cap;
+  return (int)b;
+}
+
+// Device view of SgnnGrid (passed by value to kernels).
+struct GridView {
+  int nb, d0, d1, d2, wx;
+  long long n_words;
+  const unsigned long long* mask;
+  const int* prefix;
+  const int* row_of_rank;
+};
+
+static inline GridView make_view(const SgnnGrid* g) {
+  GridView v;
+  v.nb = g->nb; v.d0 = g->d0; v.d1 = g->d1; v.d2 = g->d2; v.wx = g->wx;
+  v.n_words = g->n_words;
+  v.mask = (const unsigned long long*)g->mask;
+  v.prefix = g->prefix;
+  v.row_of_rank = g->row_of_rank;
+  return v;
+}
+
+// word index of the x-row holding (b,z,y,x); caller guarantees in-extent coordinates
+__device__ __forceinline__ long long grid_word(const GridView& g, int b, int z, int y, int x) {
+  return (((long long)b * g.d0 + z) * g.d1 + y) * g.wx + (x >> 6);
+}
+
+// row id of an in-extent cell, or -1
+__device__ __forceinline__ int grid_row(const GridView& g, int b, int z, int y, int x) {
+  long long w = grid_word(g, b, z, y, x);
+  unsigned long long m = __ldg(g.mask + w);
+  unsigned long long bit = 1ull << (x & 63);
+  if (!(m & bit)) return -1;
+  int rank = __ldg(g.prefix + w) + __popcll(m & (bit - 1));
+  return g.row_of_rank ? __ldg(g.row_of_rank + rank) : rank;
+}
+
+__device__ __forceinline__ int grid_row_checked(const GridView& g, int b, int z, int y, int x) {
+  if ((unsigned)b >= (unsigned)g.nb || (unsigned)z >= (unsigned)g.d0 ||
+      (unsigned)y >= (unsigned)g.d1 || (unsigned)x >= (unsigned)g.d2)
+    return -1;
+  return grid_row(g, b, z, y, x);
+}
+
+// literal fp32 restatement of `nn.Sigmoid()(x) > 0.5` (model.py:233,322)
+__device__ __forceinline__ bool sigmoid_gt_half(float x) {
+  float s = 1.0f / (1.0f + expf(-x));
+  return s > 0.5f;
+}
+
+// scan.cu
+int sgnn_scan_exclusive(const void* in, int mode, int* out, int64_t n, void* scratch,
+                        size_t scratch_bytes, cudaStream_t st);
+enum { SCAN_I32 = 0, SCAN_POPC64 = 1, SCAN_U8 = 2 };

@@ -1,0 +1,395 @@
+// conv.cu -- sparse convolution forward, output-stationary gather -> small-GEMM (SURVEY §8 rows a3, a4,
+// a6, a9).  fp32 FFMA path with a SPECIFIED summation order (k ascending, then ci ascending, one fmaf
+// chain per output element starting from +0) so that results are bit-reproducible and equal to
+// oracle/o3.c.  No scatter and no atomics: the rulebook is a neighbour table nbr[k][row].
+//
+// Tile: SGNN_CONV_TILE output rows x Cout per CTA.  Thread (sg, cg) owns rows {sg + 32 t, t<4} and output
+// channels [4cg, 4cg+4): 16 accumulators.  Per stage (filter offset k, 16-channel slice of Cin) the CTA
+// gathers the 128 neighbour row slices into shared memory with cp.async (16-byte chunks, zero rows for
+// absent neighbours), double buffered against the FFMA loop.  The filter bank [K][Cin][Cout] is staged in
+// shared memory once per CTA.  Row stride of the X tile is 20 words so the 8 distinct rows a warp reads with
+// one LDS.128 fall on disjoint banks.
+#include "common.cuh"
+
+#define TM SGNN_CONV_TILE
+#define TS 4
+#define NSG (TM / TS)  // 32 site groups
+#define CHUNK 16       // input channels per stage
+#define XS (CHUNK + 4) // X tile row stride (floats)
+
+struct ConvParams {
+  const float* in;
+  int ld_in;
+  const int* nbr;
+  long long nbr_stride;
+  int K;
+  int child_mode;
+  const float* weight;
+  int cin, cout;
+  long long n_out;
+  const float* residual;
+  int ld_res;
+  float* out_a; int ld_a; int relu_a; const float* scale_a; const float* shift_a;
+  float* out_b; int ld_b; int relu_b; const float* scale_b; const float* shift_b;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// neighbour row feeding output row j at filter offset k
+__device__ __forceinline__ int conv_src_row(const ConvParams& p, long long j, int k) {
+  if (!p.child_mode) return __ldg(p.nbr + (long long)k * p.nbr_stride + j);
+  // child c of parent row j>>3; offset (dz,dy,dx) lands in parent offset floor((c_a + d_a) / 2) per axis
+  const int c = (int)(j & 7);
+  const int dz = k / 9 - 1, dy = (k / 3) % 3 - 1, dx = k % 3 - 1;
+  const int pz = (((c >> 2) & 1) + dz + 2) / 2 - 1;
+  const int py = (((c >> 1) & 1) + dy + 2) / 2 - 1;
+  const int px = ((c & 1) + dx + 2) / 2 - 1;
+  const int kp = (pz + 1) * 9 + (py + 1) * 3 + (px + 1);
+  return __ldg(p.nbr + (long long)kp * p.nbr_stride + (j >> 3));
+}
+
+template <int COUT, int VEC>
+__global__ void __launch_bounds__(NSG * (COUT / 4))
+conv_gather_f32_kernel(ConvParams p) {
+  constexpr int NCG = COUT / 4;
+  constexpr int NT = NSG * NCG;
+  extern __shared__ __align__(16) float smem[];
+  const int cinp = (p.cin + 3) & ~3;
+  float* W_s = smem;                            // [K][cinp][COUT]
+  float* X_s = smem + (size_t)p.K * cinp * COUT;  // [2][TM][XS]
+  const int tid = threadIdx.x;
+  const int sg = tid / NCG, cg = tid % NCG;
+  const long long tile_base = (long long)blockIdx.x * TM;
+  const int nchunks = (cinp + CHUNK - 1) / CHUNK;
+  const int S = p.K * nchunks;
+
+  // ---- stage the filter bank (zero rows for the channel padding)
+  for (int idx = tid; idx < p.K * cinp * NCG; idx += NT) {
+    int c4 = idx % NCG;
+    int ci = (idx / NCG) % cinp;
+    int k = idx / (NCG * cinp);
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ci < p.cin)
+      w = __ldg(reinterpret_cast<const float4*>(p.weight + ((size_t)k * p.cin + ci) * COUT) + c4);
+    reinterpret_cast<float4*>(W_s + ((size_t)k * cinp + ci) * COUT)[c4] = w;
+  }
+
+  float acc[TS][4];
+#pragma unroll
+  for (int t = 0; t < TS; ++t)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[t][c] = 0.f;
+
+  // gather of stage s into buffer s&1; returns whether this thread copied any live row
+  auto issue = [&](int s) -> int {
+    const int k = s / nchunks, c0 = (s % nchunks) * CHUNK;
+    const int cw = min(CHUNK, cinp - c0);  // multiple of 4
+    float* X = X_s + (size_t)(s & 1) * TM * XS;
+    int live = 0;
+    if (VEC == 4) {
+      const int cpr = cw >> 2;  // 16-byte chunks per row
+      for (int idx = tid; idx < TM * cpr; idx += NT) {
+        const int site = idx / cpr, ch = idx % cpr;
+        const long long j = tile_base + site;
+        int r = -1;
+        if (j < p.n_out) r = conv_src_row(p, j, k);
+        float* dst = X + site * XS + ch * 4;
+        const int cb = c0 + ch * 4;
+        if (r >= 0) {
+          live = 1;
+          const float* src = p.in + (long long)r * p.ld_in + cb;
+          if (cb + 4 <= p.cin) {
+            cp_async16(dst, src);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (cb + e < p.cin) cp_async4(dst + e, src + e);
+              else dst[e] = 0.f;
+            }
+          }
+        } else {
+          *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    } else {
+      for (int idx = tid; idx < TM * cw; idx += NT) {
+        const int site = idx / cw, e = idx % cw;
+        const long long j = tile_base + site;
+        int r = -1;
+        if (j < p.n_out) r = conv_src_row(p, j, k);
+        float* dst = X + site * XS + e;
+        if (r >= 0 && c0 + e < p.cin) {
+          live = 1;
+          cp_async4(dst, p.in + (long long)r * p.ld_in + c0 + e);
+        } else {
+          *dst = 0.f;
+        }
+      }
+    }
+    return live;
+  };
+
+  int live_cur = issue(0);
+  cp_async_commit();
+  for (int s = 0; s < S; ++s) {
+    int live_next = 0;
+    if (s + 1 < S) {
+      live_next = issue(s + 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    const int any = __syncthreads_or(live_cur);
+    if (any) {
+      const int k = s / nchunks, c0 = (s % nchunks) * CHUNK;
+      const int cw = min(CHUNK, cinp - c0);
+      const float* X = X_s + (size_t)(s & 1) * TM * XS;
+      const float* Wk = W_s + ((size_t)k * cinp + c0) * COUT + cg * 4;
+      for (int c4 = 0; c4 < cw; c4 += 4) {
+        float4 xv[TS];
+#pragma unroll
+        for (int t = 0; t < TS; ++t)
+          xv[t] = *reinterpret_cast<const float4*>(X + (sg + NSG * t) * XS + c4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float4 w = *reinterpret_cast<const float4*>(Wk + (size_t)(c4 + e) * COUT);
+#pragma unroll
+          for (int t = 0; t < TS; ++t) {
+            const float x = e == 0 ? xv[t].x : e == 1 ? xv[t].y : e == 2 ? xv[t].z : xv[t].w;
+            acc[t][0] = fmaf(x, w.x, acc[t][0]);
+            acc[t][1] = fmaf(x, w.y, acc[t][1]);
+            acc[t][2] = fmaf(x, w.z, acc[t][2]);
+            acc[t][3] = fmaf(x, w.w, acc[t][3]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    live_cur = live_next;
+  }
+
+  // ---- epilogue
+  float4 sa = make_float4(1.f, 1.f, 1.f, 1.f), ta = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa, tb = ta;
+  if (p.out_a && p.scale_a) {
+    sa = __ldg(reinterpret_cast<const float4*>(p.scale_a) + cg);
+    ta = __ldg(reinterpret_cast<const float4*>(p.shift_a) + cg);
+  }
+  if (p.out_b && p.scale_b) {
+    sb = __ldg(reinterpret_cast<const float4*>(p.scale_b) + cg);
+    tb = __ldg(reinterpret_cast<const float4*>(p.shift_b) + cg);
+  }
+#pragma unroll
+  for (int t = 0; t < TS; ++t) {
+    const long long j = tile_base + sg + NSG * t;
+    if (j >= p.n_out) continue;
+    float4 v = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+    if (p.residual) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + j * p.ld_res) + cg);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (p.out_a) {
+      float4 y = v;
+      if (p.scale_a) {
+        y.x = fmaf(v.x, sa.x, ta.x); y.y = fmaf(v.y, sa.y, ta.y);
+        y.z = fmaf(v.z, sa.z, ta.z); y.w = fmaf(v.w, sa.w, ta.w);
+      }
+      if (p.relu_a) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+      reinterpret_cast<float4*>(p.out_a + j * p.ld_a)[cg] = y;
+    }
+    if (p.out_b) {
+      float4 y = v;
+      if (p.scale_b) {
+        y.x = fmaf(v.x, sb.x, tb.x); y.y = fmaf(v.y, sb.y, tb.y);
+        y.z = fmaf(v.z, sb.z, tb.z); y.w = fmaf(v.w, sb.w, tb.w);
+      }
+      if (p.relu_b) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+      reinterpret_cast<float4*>(p.out_b + j * p.ld_b)[cg] = y;
+    }
+  }
+}
+
+// Generic fallback: any Cout, one thread per (row, co).  Same summation order.
+__global__ void conv_gather_f32_generic_kernel(ConvParams p) {
+  const long long total = p.n_out * p.cout;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long j = idx / p.cout;
+    const int co = (int)(idx % p.cout);
+    float acc = 0.f;
+    for (int k = 0; k < p.K; ++k) {
+      const int r = conv_src_row(p, j, k);
+      if (r < 0) continue;
+      const float* x = p.in + (long long)r * p.ld_in;
+      const float* w = p.weight + (size_t)k * p.cin * p.cout + co;
+      for (int ci = 0; ci < p.cin; ++ci) acc = fmaf(__ldg(x + ci), __ldg(w + (size_t)ci * p.cout), acc);
+    }
+    float v = acc;
+    if (p.residual) v += p.residual[j * p.ld_res + co];
+    if (p.out_a) {
+      float y = v;
+      if (p.scale_a) y = fmaf(v, p.scale_a[co], p.shift_a[co]);
+      if (p.relu_a) y = fmaxf(y, 0.f);
+      p.out_a[j * p.ld_a + co] = y;
+    }
+    if (p.out_b) {
+      float y = v;
+      if (p.scale_b) y = fmaf(v, p.scale_b[co], p.shift_b[co]);
+      if (p.relu_b) y = fmaxf(y, 0.f);
+      p.out_b[j * p.ld_b + co] = y;
+    }
+  }
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+template <int COUT>
+static int launch_conv(const ConvParams& p, bool vec, cudaStream_t st) {
+  constexpr int NT = NSG * (COUT / 4);
+  const int cinp = (p.cin + 3) & ~3;
+  const size_t smem = ((size_t)p.K * cinp * COUT + 2 * (size_t)TM * XS) * sizeof(float);
+  if (smem > 227 * 1024) return SGNN_E_UNSUPPORTED;
+  const long long tiles = (p.n_out + TM - 1) / TM;
+  if (tiles > 0x7fffffff) return SGNN_E_TOO_LARGE;
+  if (vec) {
+    SGNN_CUDA(cudaFuncSetAttribute(conv_gather_f32_kernel<COUT, 4>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_gather_f32_kernel<COUT, 4><<<(int)tiles, NT, smem, st>>>(p);
+  } else {
+    SGNN_CUDA(cudaFuncSetAttribute(conv_gather_f32_kernel<COUT, 1>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_gather_f32_kernel<COUT, 1><<<(int)tiles, NT, smem, st>>>(p);
+  }
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+static int check_epilogue(const SgnnEpilogue& e, bool need_vec) {
+  if (!e.out) return SGNN_OK;
+  if ((e.scale == nullptr) != (e.shift == nullptr)) return SGNN_E_INVALID;
+  if (need_vec && (!aligned16(e.out) || (e.ld & 3) || (e.scale && (!aligned16(e.scale) || !aligned16(e.shift)))))
+    return SGNN_E_ALIGN;
+  return SGNN_OK;
+}
+
+extern "C" int sgnn_conv_forward(const SgnnConvArgs* a, void* stream) {
+  if (!a || a->n_out < 0 || a->cin <= 0 || a->cout <= 0 || !a->weight) return SGNN_E_INVALID;
+  if (a->dtype != SGNN_F32) return SGNN_E_UNSUPPORTED;
+  if (a->K != 27 && a->K != 8) return SGNN_E_UNSUPPORTED;
+  if (a->child_mode && a->K != 27) return SGNN_E_INVALID;
+  if (!a->a.out && !a->b.out) return SGNN_E_INVALID;
+  if (a->n_out == 0) return SGNN_OK;
+  if (!a->in || !a->nbr) return SGNN_E_INVALID;
+  if (a->cin > 64) return SGNN_E_UNSUPPORTED;
+  ConvParams p;
+  p.in = (const float*)a->in; p.ld_in = a->ld_in;
+  p.nbr = a->nbr; p.nbr_stride = a->nbr_stride; p.K = a->K; p.child_mode = a->child_mode;
+  p.weight = (const float*)a->weight; p.cin = a->cin; p.cout = a->cout; p.n_out = a->n_out;
+  p.residual = (const float*)a->residual; p.ld_res = a->ld_res;
+  p.out_a = (float*)a->a.out; p.ld_a = a->a.ld; p.relu_a = a->a.relu; p.scale_a = a->a.scale; p.shift_a = a->a.shift;
+  p.out_b = (float*)a->b.out; p.ld_b = a->b.ld; p.relu_b = a->b.relu; p.scale_b = a->b.scale; p.shift_b = a->b.shift;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tiled = (a->cout == 4 || a->cout == 8 || a->cout == 12 || a->cout == 16);
+  int rc;
+  if ((rc = check_epilogue(a->a, tiled))) return rc;
+  if ((rc = check_epilogue(a->b, tiled))) return rc;
+  if (tiled) {
+    if (!aligned16(a->weight)) return SGNN_E_ALIGN;
+    if (a->residual && (!aligned16(a->residual) || (a->ld_res & 3))) return SGNN_E_ALIGN;
+    const bool vec = aligned16(a->in) && (a->ld_in & 3) == 0;
+    switch (a->cout) {
+      case 4: return launch_conv<4>(p, vec, st);
+      case 8: return launch_conv<8>(p, vec, st);
+      case 12: return launch_conv<12>(p, vec, st);
+      default: return launch_conv<16>(p, vec, st);
+    }
+  }
+  conv_gather_f32_generic_kernel<<<sgnn_blocks(a->n_out * a->cout, 256), 256, 0, st>>>(p);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+// ------------------------------------------------------------ deconvolution (filter 2, stride 2)
+// every fine row has exactly one coarse parent: out[i] = in[parent>>3] @ W[parent&7]
+__global__ void deconv_f32_kernel(const float* __restrict__ in, int ld_in, const int* __restrict__ parent,
+                                  const float* __restrict__ weight, int cin, int cout, long long n,
+                                  float* out, int ld, int relu, const float* scale, const float* shift) {
+  extern __shared__ float W_s[];  // [8][cin][cout]
+  for (int i = threadIdx.x; i < 8 * cin * cout; i += blockDim.x) W_s[i] = weight[i];
+  __syncthreads();
+  const long long total = n * cout;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx / cout;
+    const int co = (int)(idx % cout);
+    const int pk = __ldg(parent + i);
+    float acc = 0.f;
+    if (pk >= 0) {
+      const float* x = in + (long long)(pk >> 3) * ld_in;
+      const float* w = W_s + (size_t)(pk & 7) * cin * cout + co;
+      for (int ci = 0; ci < cin; ++ci) acc = fmaf(__ldg(x + ci), w[(size_t)ci * cout], acc);
+    }
+    float y = acc;
+    if (scale) y = fmaf(acc, scale[co], shift[co]);
+    if (relu) y = fmaxf(y, 0.f);
+    out[i * ld + co] = y;
+  }
+}
+
+extern "C" int sgnn_deconv_forward(const void* in, int32_t ld_in, int32_t dtype, const int32_t* parent,
+                                   const void* weight, int32_t cin, int32_t cout, int64_t n_fine,
+                                   const SgnnEpilogue* ep, void* stream) {
+  if (n_fine < 0 || cin <= 0 || cout <= 0 || !ep || !ep->out || !weight) return SGNN_E_INVALID;
+  if (dtype != SGNN_F32) return SGNN_E_UNSUPPORTED;
+  if ((ep->scale == nullptr) != (ep->shift == nullptr)) return SGNN_E_INVALID;
+  if (n_fine == 0) return SGNN_OK;
+  if (!in || !parent) return SGNN_E_INVALID;
+  const size_t smem = (size_t)8 * cin * cout * 4;
+  if (smem > 200 * 1024) return SGNN_E_UNSUPPORTED;
+  SGNN_CUDA(cudaFuncSetAttribute(deconv_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  deconv_f32_kernel<<<sgnn_blocks(n_fine * cout, 256, 148 * 8), 256, smem, (cudaStream_t)stream>>>(
+      (const float*)in, ld_in, parent, (const float*)weight, cin, cout, (long long)n_fine,
+      (float*)ep->out, ep->ld, ep->relu, ep->scale, ep->shift);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+// ------------------------------------------------------------ unpooling
+__global__ void unpool_kernel(const float* __restrict__ in, int ld_in, const int* __restrict__ parent, int c,
+                              long long n, float* out, int ld, int relu, const float* scale, const float* shift) {
+  const long long total = n * c;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx / c;
+    const int ch = (int)(idx % c);
+    const int pk = __ldg(parent + i);
+    float v = pk >= 0 ? __ldg(in + (long long)(pk >> 3) * ld_in + ch) : 0.f;
+    if (scale) v = fmaf(v, scale[ch], shift[ch]);
+    if (relu) v = fmaxf(v, 0.f);
+    out[i * ld + ch] = v;
+  }
+}
+
+extern "C" int sgnn_unpool(const float* in, int32_t ld_in, const int32_t* parent, int32_t c, int64_t n_fine,
+                           const SgnnEpilogue* ep, void* stream) {
+  if (n_fine < 0 || c <= 0 || !ep || !ep->out) return SGNN_E_INVALID;
+  if ((ep->scale == nullptr) != (ep->shift == nullptr)) return SGNN_E_INVALID;
+  if (n_fine == 0) return SGNN_OK;
+  if (!in || !parent) return SGNN_E_INVALID;
+  unpool_kernel<<<sgnn_blocks(n_fine * c, 256), 256, 0, (cudaStream_t)stream>>>(
+      in, ld_in, parent, c, (long long)n_fine, (float*)ep->out, ep->ld, ep->relu, ep->scale, ep->shift);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}

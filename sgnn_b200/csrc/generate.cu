@@ -1,0 +1,207 @@
+// generate.cu -- the generative (coarse-to-fine) steps of SG-NN as device kernels:
+// occupancy heads, the literal `sigmoid(x) > 0.5` mask, and STABLE compaction of the kept candidates
+// (flags -> exclusive scan -> ordered write), replacing the host-synchronising boolean-mask indexing of
+// model.py:238-246 and :322-335.  Candidate order is preserved so output rows match the reference order.
+#include "common.cuh"
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+extern "C" size_t sgnn_compact_scratch_bytes(int64_t n_items) {
+  int64_t n = n_items < 1 ? 1 : n_items;
+  return align256((size_t)n) + align256((size_t)(n + 1) * 4) + sgnn_scan_scratch_bytes(n);
+}
+
+struct CompactScratch {
+  unsigned char* flags;
+  int* offs;
+  void* scan;
+  size_t scan_bytes;
+};
+
+static int carve(void* scratch, size_t bytes, int64_t n, CompactScratch* cs) {
+  if (!scratch || bytes < sgnn_compact_scratch_bytes(n)) return SGNN_E_INVALID;
+  int64_t m = n < 1 ? 1 : n;
+  char* p = (char*)scratch;
+  cs->flags = (unsigned char*)p; p += align256((size_t)m);
+  cs->offs = (int*)p; p += align256((size_t)(m + 1) * 4);
+  cs->scan = p;
+  cs->scan_bytes = bytes - (size_t)(p - (char*)scratch);
+  return SGNN_OK;
+}
+
+// ------------------------------------------------------------ a8: dense_coarse_to_sparse
+__global__ void d2s_flag_kernel(const float* __restrict__ dense_out, int nb, long long vol,
+                                unsigned char* __restrict__ flags, float* __restrict__ cand_out) {
+  const long long total = (long long)nb * vol;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / vol, cell = i % vol;
+    const float occ = dense_out[(b * 2 + 0) * vol + cell];
+    const float sdf = dense_out[(b * 2 + 1) * vol + cell];
+    flags[i] = sigmoid_gt_half(occ) ? 1 : 0;
+    if (cand_out) reinterpret_cast<float2*>(cand_out)[i] = make_float2(occ, sdf);
+  }
+}
+
+__global__ void d2s_write_kernel(const float* __restrict__ dense_feats, const float* __restrict__ dense_out, int nb,
+                                 int c, int d0, int d1, int d2, const unsigned char* __restrict__ flags,
+                                 const int* __restrict__ offs, int* __restrict__ locs, float* __restrict__ feats,
+                                 int ld, int* __restrict__ count) {
+  const long long vol = (long long)d0 * d1 * d2;
+  const long long total = (long long)nb * vol;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *count = offs[total];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (!flags[i]) continue;
+    const long long b = i / vol, cell = i % vol;
+    const int x = (int)(cell % d2), y = (int)((cell / d2) % d1), z = (int)(cell / ((long long)d1 * d2));
+    const int pos = offs[i];
+    reinterpret_cast<int4*>(locs)[pos] = make_int4(z, y, x, (int)b);
+    float* f = feats + (long long)pos * ld;
+    f[0] = dense_out[(b * 2 + 0) * vol + cell];
+    f[1] = dense_out[(b * 2 + 1) * vol + cell];
+    for (int ch = 0; ch < c; ++ch) f[2 + ch] = dense_feats[(b * c + ch) * vol + cell];
+  }
+}
+
+extern "C" int sgnn_dense_to_sparse(const float* dense_feats, const float* dense_out, int32_t nb, int32_t c,
+                                    int32_t d0, int32_t d1, int32_t d2, int32_t* locs, float* feats,
+                                    int32_t ld_feats, float* cand_out, int32_t* count, void* scratch,
+                                    size_t scratch_bytes, void* stream) {
+  if (nb < 0 || c < 0 || d0 < 0 || d1 < 0 || d2 < 0 || !count || ld_feats < c + 2) return SGNN_E_INVALID;
+  const long long total = (long long)nb * d0 * d1 * d2;
+  if (total > 0x7fffffffLL) return SGNN_E_TOO_LARGE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (total == 0) {
+    SGNN_CUDA(cudaMemsetAsync(count, 0, 4, st));
+    return SGNN_OK;
+  }
+  if (!dense_feats || !dense_out || !locs || !feats) return SGNN_E_INVALID;
+  CompactScratch cs;
+  int rc = carve(scratch, scratch_bytes, total, &cs);
+  if (rc) return rc;
+  d2s_flag_kernel<<<sgnn_blocks(total, 256), 256, 0, st>>>(dense_out, nb, (long long)d0 * d1 * d2, cs.flags,
+                                                           cand_out);
+  SGNN_CHECK_LAUNCH();
+  rc = sgnn_scan_exclusive(cs.flags, SCAN_U8, cs.offs, total, cs.scan, cs.scan_bytes, st);
+  if (rc) return rc;
+  d2s_write_kernel<<<sgnn_blocks(total, 256), 256, 0, st>>>(dense_feats, dense_out, nb, c, d0, d1, d2, cs.flags,
+                                                            cs.offs, locs, feats, ld_feats, count);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+// ------------------------------------------------------------ a9: heads + mask + compaction
+__global__ void heads_flag_kernel(const float* __restrict__ x, int ld_x, int c, const float* __restrict__ w_occ,
+                                  const float* __restrict__ b_occ, const float* __restrict__ w_sdf,
+                                  const float* __restrict__ b_sdf, long long n_cand,
+                                  unsigned char* __restrict__ flags, float* __restrict__ cand_out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_cand;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float* xr = x + i * ld_x;
+    float occ = 0.f, sdf = 0.f;
+    for (int ch = 0; ch < c; ++ch) {
+      const float v = xr[ch];
+      occ = fmaf(v, __ldg(w_occ + ch), occ);
+      sdf = fmaf(v, __ldg(w_sdf + ch), sdf);
+    }
+    occ += __ldg(b_occ);
+    sdf += __ldg(b_sdf);
+    flags[i] = sigmoid_gt_half(occ) ? 1 : 0;
+    reinterpret_cast<float2*>(cand_out)[i] = make_float2(occ, sdf);
+  }
+}
+
+__global__ void heads_write_kernel(const float* __restrict__ x, int ld_x, int c, const float* __restrict__ cand_out,
+                                   const int* __restrict__ parent_coords, long long n_cand,
+                                   const unsigned char* __restrict__ flags, const int* __restrict__ offs,
+                                   int* __restrict__ locs, float* __restrict__ feats, int ld,
+                                   int* __restrict__ count) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *count = offs[n_cand];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_cand;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (!flags[i]) continue;
+    const int pos = offs[i];
+    const int4 p = __ldg(reinterpret_cast<const int4*>(parent_coords) + (i >> 3));
+    const int ch8 = (int)(i & 7);
+    reinterpret_cast<int4*>(locs)[pos] =
+        make_int4(2 * p.x + ((ch8 >> 2) & 1), 2 * p.y + ((ch8 >> 1) & 1), 2 * p.z + (ch8 & 1), p.w);
+    float* f = feats + (long long)pos * ld;
+    const float* xr = x + i * ld_x;
+    for (int ch = 0; ch < c; ++ch) f[ch] = xr[ch];
+    const float2 os = reinterpret_cast<const float2*>(cand_out)[i];
+    f[c] = os.x;
+    f[c + 1] = os.y;
+  }
+}
+
+extern "C" int sgnn_heads_compact(const float* x, int32_t ld_x, int32_t c, const float* w_occ, const float* b_occ,
+                                  const float* w_sdf, const float* b_sdf, const int32_t* parent_coords,
+                                  int64_t n_parent, float* cand_out, int32_t* locs, float* feats,
+                                  int32_t ld_feats, int32_t* count, void* scratch, size_t scratch_bytes,
+                                  void* stream) {
+  if (n_parent < 0 || c <= 0 || !count || ld_feats < c + 2 || !w_occ || !b_occ || !w_sdf || !b_sdf)
+    return SGNN_E_INVALID;
+  const long long n_cand = (long long)n_parent * 8;
+  if (n_cand > 0x7fffffffLL) return SGNN_E_TOO_LARGE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_cand == 0) {
+    SGNN_CUDA(cudaMemsetAsync(count, 0, 4, st));
+    return SGNN_OK;
+  }
+  if (!x || !parent_coords || !cand_out || !locs || !feats) return SGNN_E_INVALID;
+  CompactScratch cs;
+  int rc = carve(scratch, scratch_bytes, n_cand, &cs);
+  if (rc) return rc;
+  heads_flag_kernel<<<sgnn_blocks(n_cand, 256), 256, 0, st>>>(x, ld_x, c, w_occ, b_occ, w_sdf, b_sdf, n_cand,
+                                                              cs.flags, cand_out);
+  SGNN_CHECK_LAUNCH();
+  rc = sgnn_scan_exclusive(cs.flags, SCAN_U8, cs.offs, n_cand, cs.scan, cs.scan_bytes, st);
+  if (rc) return rc;
+  heads_write_kernel<<<sgnn_blocks(n_cand, 256), 256, 0, st>>>(x, ld_x, c, cand_out, parent_coords, n_cand,
+                                                               cs.flags, cs.offs, locs, feats, ld_feats, count);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+// ------------------------------------------------------------ candidate coordinates (model.py:192-207)
+__global__ void children_coords_kernel(const int* __restrict__ parent_coords, long long n_cand,
+                                       int* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_cand;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int4 p = __ldg(reinterpret_cast<const int4*>(parent_coords) + (i >> 3));
+    const int c = (int)(i & 7);
+    reinterpret_cast<int4*>(out)[i] =
+        make_int4(2 * p.x + ((c >> 2) & 1), 2 * p.y + ((c >> 1) & 1), 2 * p.z + (c & 1), p.w);
+  }
+}
+
+extern "C" int sgnn_children_coords(const int32_t* parent_coords, int64_t n_parent, int32_t* out, void* stream) {
+  if (n_parent < 0 || (n_parent > 0 && (!parent_coords || !out))) return SGNN_E_INVALID;
+  if (n_parent * 8 > 0x7fffffffLL) return SGNN_E_TOO_LARGE;
+  if (n_parent > 0) {
+    children_coords_kernel<<<sgnn_blocks(n_parent * 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        parent_coords, (long long)n_parent * 8, out);
+    SGNN_CHECK_LAUNCH();
+  }
+  return SGNN_OK;
+}
+
+// ------------------------------------------------------------ ABI bookkeeping
+int g_sgnn_last_cuda_error = 0;
+
+extern "C" int sgnn_version(void) { return SGNN_VERSION; }
+
+extern "C" int sgnn_last_cuda_error(void) { return g_sgnn_last_cuda_error; }
+
+extern "C" const char* sgnn_error_string(int code) {
+  switch (code) {
+    case SGNN_OK: return "ok";
+    case SGNN_E_INVALID: return "invalid argument";
+    case SGNN_E_CUDA: return "CUDA runtime error (see sgnn_last_cuda_error)";
+    case SGNN_E_TOO_LARGE: return "extent or row count exceeds 2^31-1 indexing";
+    case SGNN_E_UNSUPPORTED: return "unsupported configuration";
+    case SGNN_E_ALIGN: return "pointer or leading dimension violates the 16-byte alignment rule";
+    default: return "unknown sgnn error code";
+  }
+}

@@ -1,0 +1,133 @@
+// pointwise.cu -- per-row kernels: BatchNormReLU (eval), AddTable, JoinTable slot copy, nn.Linear heads,
+// SparseToDense.  All HBM-bound; rows are short (<= 48 floats) so the
+// mapping is one thread per element with the channel index fastest (coalesced across a row).
+#include "common.cuh"
+
+__global__ void affine_relu_kernel(const float* __restrict__ x, int ld_x, float* __restrict__ y, int ld_y,
+                                   long long n, int c, const float* __restrict__ scale,
+                                   const float* __restrict__ shift, int relu) {
+  const long long total = n * c;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx / c;
+    const int ch = (int)(idx % c);
+    float v = x[i * ld_x + ch];
+    if (scale) v = fmaf(v, __ldg(scale + ch), __ldg(shift + ch));
+    if (relu) v = fmaxf(v, 0.f);
+    y[i * ld_y + ch] = v;
+  }
+}
+
+extern "C" int sgnn_affine_relu(const float* x, int32_t ld_x, float* y, int32_t ld_y, int64_t n, int32_t c,
+                                const float* scale, const float* shift, int32_t relu, void* stream) {
+  if (n < 0 || c <= 0 || (scale == nullptr) != (shift == nullptr)) return SGNN_E_INVALID;
+  if (n == 0) return SGNN_OK;
+  if (!x || !y) return SGNN_E_INVALID;
+  affine_relu_kernel<<<sgnn_blocks(n * c, 256), 256, 0, (cudaStream_t)stream>>>(x, ld_x, y, ld_y, (long long)n, c,
+                                                                                scale, shift, relu);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+__global__ void add_rows_kernel(const float* __restrict__ a, int ld_a, const float* __restrict__ b, int ld_b,
+                                float* __restrict__ y, int ld_y, long long n, int c) {
+  const long long total = n * c;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx / c;
+    const int ch = (int)(idx % c);
+    y[i * ld_y + ch] = a[i * ld_a + ch] + b[i * ld_b + ch];
+  }
+}
+
+extern "C" int sgnn_add_rows(const float* a, int32_t ld_a, const float* b, int32_t ld_b, float* y, int32_t ld_y,
+                             int64_t n, int32_t c, void* stream) {
+  if (n < 0 || c <= 0) return SGNN_E_INVALID;
+  if (n == 0) return SGNN_OK;
+  if (!a || !b || !y) return SGNN_E_INVALID;
+  add_rows_kernel<<<sgnn_blocks(n * c, 256), 256, 0, (cudaStream_t)stream>>>(a, ld_a, b, ld_b, y, ld_y,
+                                                                             (long long)n, c);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+__global__ void copy_cols_kernel(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int ld_dst,
+                                 long long n, int c) {
+  const long long total = n * c;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx / c;
+    const int ch = (int)(idx % c);
+    dst[i * ld_dst + ch] = src[i * ld_src + ch];
+  }
+}
+
+extern "C" int sgnn_copy_cols(const float* src, int32_t ld_src, float* dst, int32_t ld_dst, int64_t n, int32_t c,
+                              void* stream) {
+  if (n < 0 || c <= 0) return SGNN_E_INVALID;
+  if (n == 0) return SGNN_OK;
+  if (!src || !dst) return SGNN_E_INVALID;
+  copy_cols_kernel<<<sgnn_blocks(n * c, 256), 256, 0, (cudaStream_t)stream>>>(src, ld_src, dst, ld_dst,
+                                                                              (long long)n, c);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+// y[i][o] = (fma chain over c ascending of x[i][c]*w[o][c], from +0) + b[o]
+__global__ void linear_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ w,
+                              const float* __restrict__ b, float* __restrict__ y, int ld_y, long long n, int cin,
+                              int cout) {
+  const long long total = n * cout;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx / cout;
+    const int o = (int)(idx % cout);
+    const float* xr = x + i * ld_x;
+    const float* wr = w + (size_t)o * cin;
+    float acc = 0.f;
+    for (int c = 0; c < cin; ++c) acc = fmaf(xr[c], __ldg(wr + c), acc);
+    if (b) acc += __ldg(b + o);
+    y[i * ld_y + o] = acc;
+  }
+}
+
+extern "C" int sgnn_linear(const float* x, int32_t ld_x, const float* w, const float* b, float* y, int32_t ld_y,
+                           int64_t n, int32_t cin, int32_t cout, void* stream) {
+  if (n < 0 || cin <= 0 || cout <= 0 || !w) return SGNN_E_INVALID;
+  if (n == 0) return SGNN_OK;
+  if (!x || !y) return SGNN_E_INVALID;
+  linear_kernel<<<sgnn_blocks(n * cout, 256), 256, 0, (cudaStream_t)stream>>>(x, ld_x, w, b, y, ld_y, (long long)n,
+                                                                              cin, cout);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+__global__ void sparse_to_dense_kernel(const float* __restrict__ feats, int ld, const int* __restrict__ coords,
+                                       long long n, int c, float* __restrict__ dense, int nb, int d0, int d1,
+                                       int d2) {
+  const long long total = n * c;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx / c;
+    const int ch = (int)(idx % c);
+    const int4 p = __ldg(reinterpret_cast<const int4*>(coords) + i);
+    if ((unsigned)p.x >= (unsigned)d0 || (unsigned)p.y >= (unsigned)d1 || (unsigned)p.z >= (unsigned)d2 ||
+        (unsigned)p.w >= (unsigned)nb)
+      continue;
+    dense[((((long long)p.w * c + ch) * d0 + p.x) * d1 + p.y) * d2 + p.z] = feats[i * ld + ch];
+  }
+}
+
+extern "C" int sgnn_sparse_to_dense(const float* feats, int32_t ld, const int32_t* coords, int64_t n, int32_t c,
+                                    float* dense, int32_t nb, int32_t d0, int32_t d1, int32_t d2, void* stream) {
+  if (n < 0 || c <= 0 || nb < 0 || d0 < 0 || d1 < 0 || d2 < 0 || !dense) return SGNN_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t bytes = (size_t)nb * c * d0 * d1 * d2 * 4;
+  if (bytes) SGNN_CUDA(cudaMemsetAsync(dense, 0, bytes, st));
+  if (n == 0 || bytes == 0) return SGNN_OK;
+  if (!feats || !coords) return SGNN_E_INVALID;
+  sparse_to_dense_kernel<<<sgnn_blocks(n * c, 256), 256, 0, st>>>(feats, ld, coords, (long long)n, c, dense, nb, d0,
+                                                                  d1, d2);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}

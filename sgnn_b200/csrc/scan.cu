@@ -1,0 +1,108 @@
+// scan.cu -- exclusive prefix sums (int32) used by the grid build (popcount ranks) and by the
+// stable mask compactions (model.py:238,242,325,335).  Hierarchical: 2048 items per CTA, CTA
+// totals scanned recursively, offsets added back.  out has n+1 entries; out[n] = total.
+#include "common.cuh"
+
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ int scan_load(const void* in, int mode, long long i) {
+  if (mode == SCAN_I32) return ((const int*)in)[i];
+  if (mode == SCAN_POPC64) return __popcll(((const unsigned long long*)in)[i]);
+  return (int)((const unsigned char*)in)[i];
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_block_kernel(const void* __restrict__ in, int mode, int* __restrict__ out, long long n,
+                  int* __restrict__ sums) {
+  __shared__ int warp_tot[SCAN_THREADS / 32];
+  const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  int tsum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    long long idx = base + i;
+    v[i] = idx < n ? scan_load(in, mode, idx) : 0;
+    tsum += v[i];
+  }
+  // inclusive warp scan of thread sums
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = tsum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = lane < SCAN_THREADS / 32 ? warp_tot[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < SCAN_THREADS / 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += t;
+    }
+    if (lane < SCAN_THREADS / 32) warp_tot[lane] = w;  // inclusive
+  }
+  __syncthreads();
+  int excl = inc - tsum + (wid ? warp_tot[wid - 1] : 0);
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    long long idx = base + i;
+    if (idx < n) out[idx] = excl;
+    excl += v[i];
+  }
+  if (threadIdx.x == SCAN_THREADS - 1) {
+    sums[blockIdx.x] = excl;
+    if (gridDim.x == 1) out[n] = excl;
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_add_kernel(int* __restrict__ out, long long n, const int* __restrict__ sums_ex, int nb) {
+  const int off = sums_ex[blockIdx.x];
+  const long long base = (long long)blockIdx.x * SCAN_TILE;
+  for (int i = threadIdx.x; i < SCAN_TILE; i += SCAN_THREADS) {
+    long long idx = base + i;
+    if (idx < n) out[idx] += off;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = sums_ex[nb];
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" size_t sgnn_scan_scratch_bytes(int64_t n_items) {
+  size_t total = 256;
+  int64_t n = n_items < 1 ? 1 : n_items;
+  while (true) {
+    int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    total += align_up((size_t)nb * 4, 256) + align_up((size_t)(nb + 1) * 4, 256);
+    if (nb <= 1) break;
+    n = nb;
+  }
+  return total;
+}
+
+int sgnn_scan_exclusive(const void* in, int mode, int* out, int64_t n, void* scratch,
+                        size_t scratch_bytes, cudaStream_t st) {
+  if (n < 0 || !out || (!in && n > 0) || !scratch) return SGNN_E_INVALID;
+  if (scratch_bytes < sgnn_scan_scratch_bytes(n)) return SGNN_E_INVALID;
+  int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (nb < 1) nb = 1;
+  if (nb > 0x7fffffff) return SGNN_E_TOO_LARGE;
+  int* sums = (int*)scratch;
+  scan_block_kernel<<<(int)nb, SCAN_THREADS, 0, st>>>(in, mode, out, (long long)n, sums);
+  SGNN_CHECK_LAUNCH();
+  if (nb > 1) {
+    size_t used = align_up((size_t)nb * 4, 256);
+    int* sums_ex = (int*)((char*)scratch + used);
+    used += align_up((size_t)(nb + 1) * 4, 256);
+    int rc = sgnn_scan_exclusive(sums, SCAN_I32, sums_ex, nb, (char*)scratch + used,
+                                 scratch_bytes - used, st);
+    if (rc) return rc;
+    scan_add_kernel<<<(int)nb, SCAN_THREADS, 0, st>>>(out, (long long)n, sums_ex, (int)nb);
+    SGNN_CHECK_LAUNCH();
+  }
+  return SGNN_OK;
+}
