@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- active-voxels/s through the SG-NN generator (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W                 B200 arm (this repo's engine)
+  python bench.py --impl reference --gpus N --steps K --warmup W reference arm: the CPU path
+                                                                 (oracle port of model.py + restated scn)
+
+One step = one pass of the hot path (GenModel forward, loss_weights = ones(5), eval) over one batch of
+`--blocks` synthetic 64^3 TSDF blocks @5 % per GPU (BASELINE.json configs[1]; SURVEY §8(d) inputs).
+Weak scaling: every rank owns its own blocks (block i -> rank i mod N), one NCCL broadcast of the weights,
+no data-path collective.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'input_active_voxels_per_s_through_sgnn_generator'
+UNIT = 'voxels/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--blocks', type=int, default=32, help='64^3 blocks per GPU per step')
+    ap.add_argument('--sets', type=int, default=4, help='distinct input batches rotated across steps')
+    ap.add_argument('--param-seed', type=int, default=0)
+    ap.add_argument('--cpu-blocks', type=int, default=1, help='blocks per CPU-baseline forward')
+    ap.add_argument('--cpu-reps', type=int, default=3)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ledger', default='', help='write the per-layer ledger JSON here')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_forward_rate(n_blocks, reps, seed, first_block=0):
+    """Times the oracle port of the reference CPU path (oracle/genmodel.py on oracle/sparseconvnet).
+    This is the ONE place bench.py executes oracle code: as the thing the B200 arm is compared with."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    from genmodel import OracleGenModel
+    from sgnn_b200.synth import fill_parameters, synthetic_batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = OracleGenModel()
+    fill_parameters(m, seed)
+    m.eval()
+    locs, feats = synthetic_batch(n_blocks, 64, 0.05, first=first_block)
+    times = []
+    with torch.no_grad():
+        m(locs, feats)                      # warm-up (allocator, thread pool)
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            m(locs, feats)
+            times.append(time.perf_counter() - t0)
+    t = float(np.median(times))
+    return locs.shape[0] / t, t, cores, locs.shape[0]
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    # each "step" = one forward over a bounded sample (cpu_blocks blocks) of the same workload
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    from genmodel import OracleGenModel
+    from sgnn_b200.synth import fill_parameters, synthetic_batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = OracleGenModel()
+    fill_parameters(m, args.param_seed)
+    m.eval()
+    steps = min(args.steps, 8)
+    warm = min(args.warmup, 1)
+    vox, t_total = 0, 0.0
+    with torch.no_grad():
+        for s in range(warm + steps):
+            locs, feats = synthetic_batch(args.cpu_blocks, 64, 0.05, first=s * args.cpu_blocks)
+            t0 = time.perf_counter()
+            m(locs, feats)
+            dt = time.perf_counter() - t0
+            if s >= warm:
+                vox += locs.shape[0]
+                t_total += dt
+    value = vox / t_total
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * t_total / steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'configs[1] sampled: %d x 64^3 block(s) @5%% per step, full 3-level generator'
+                               % args.cpu_blocks, 'host': 'cpu'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': '%d forward(s) of %d block(s); restated SparseConvNet-CPU path (oracle O2) '
+                                   'under the oracle port of model.py' % (steps, args.cpu_blocks)},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
+                self.rows.append([v.strip() for v in out.stdout.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        rows = [r for r in self.rows if len(r) >= 7]
+        if not rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        sm = sorted(float(r[0]) for r in rows if r[0].replace('.', '').isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith('active') for r in rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': float(rows[0][1]), 'reasons': reasons,
+                'samples': len(rows)}
+
+
+class ConvProfiler(object):
+    """Event pair around every sgnn_conv_forward of the timed steps + the algorithmic-byte ledger
+    (bytes = (N_in*Cin + N_out*Cout)*4 + 8*R + K*Cin*Cout*4, flops = 2*R*Cin*Cout)."""
+
+    def __init__(self):
+        self.events, self.ledger, self.count_rules = [], [], False
+
+    class _Ctx(object):
+        def __init__(self, prof, rec):
+            self.prof, self.rec = prof, rec
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+        def done(self):
+            self.e1.record()
+            self.prof.events.append((self.e0, self.e1, self.rec))
+
+    def conv(self, x, nbr, weight, n_out, child_mode, has_res, has_b):
+        K, cin, cout = weight.shape
+        rec = {'op': 'conv_child' if child_mode else ('conv_k27' if K == 27 else 'conv_k8'),
+               'n_in': int(x.shape[0]), 'n_out': n_out, 'cin': cin, 'cout': cout, 'K': K}
+        if self.count_rules:
+            rec['R'] = child_rule_count(nbr) if child_mode else int((nbr >= 0).sum().item())
+            self.ledger.append(rec)
+        return ConvProfiler._Ctx(self, rec)
+
+
+def child_rule_count(nbr):
+    """Rules of the child-mode convolution = for each parent/child/offset with an existing parent neighbour."""
+    present = (nbr >= 0).view(3, 3, 3, -1).float()           # [pz,py,px, n]
+    # per axis a child at c in {0,1} reaches parent offsets {-1,0,0} (c=0) or {0,0,1} (c=1): weights (1,2,0),(0,2,1)
+    wz = torch.tensor([[1., 2., 0.], [0., 2., 1.]], device=nbr.device)
+    tot = torch.einsum('az,by,cx,zyxn->', wz, wz, wz, present)
+    return int(tot.item())
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    import sgnn_b200
+    import sgnn_b200.engine as E
+    from sgnn_b200 import shard
+    from sgnn_b200._lib import lib
+    from sgnn_b200.synth import fill_parameters, synthetic_batch
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: the B200 arm needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    ones = np.ones(5, dtype=np.float32)
+
+    model = sgnn_b200.GenModel(8, 64, 1, 16, 16, 4, True, True, 1, 1)
+    if rank == 0:
+        fill_parameters(model, args.param_seed)
+    model = model.to(dev).eval()
+    shard.broadcast_parameters(model, src=0)          # the one collective of the path (2.57 MB)
+    model.return_long = True
+
+    # inputs: `sets` distinct batches per rank (global block id = (set*world + rank)*blocks + i), resident in HBM
+    host, resident = [], []
+    for s in range(args.sets):
+        locs, feats = synthetic_batch(args.blocks, 64, 0.05, first=(s * world + rank) * args.blocks)
+        host.append((locs.pin_memory(), feats.pin_memory()))
+        resident.append((locs.to(dev), feats.to(dev)))
+    vox = [int(h[0].shape[0]) for h in host]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step(i):
+        locs, feats = resident[i % args.sets]
+        return model([locs, feats], ones)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also builds the byte ledger of set 0 on rank 0)
+    prof = ConvProfiler()
+    for w in range(max(args.warmup, 3)):
+        step(w)
+    torch.cuda.synchronize()
+    ledger = []
+    if rank == 0:
+        prof.count_rules = True
+        E.PROFILER = prof
+        out = step(0)
+        torch.cuda.synchronize()
+        E.PROFILER = None
+        prof.count_rules = False
+        ledger = prof.ledger
+        prof.events, prof.ledger = [], []
+        final_rows = int(out[0][0].shape[0])
+        level_rows = [int(l[0].shape[0]) if not isinstance(l[0], list) else 0 for l in out[1]]
+    # ---- timed region: exactly K steps, L2 flushed before each (flush inside the bracket, ~40 us of 256 MiB write)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        E.PROFILER = prof
+    barrier()
+    l0 = lib.sgnn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)
+        step(i)
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = (lib.sgnn_launch_count() - l0) / max(args.steps, 1)
+    E.PROFILER = None
+    dev_ms = e0.elapsed_time(e1)
+    ms = shard.max_over_ranks(dev_ms, dev)
+    vox_timed = sum(vox[i % args.sets] for i in range(args.steps))
+    total_vox = shard.sum_over_ranks(vox_timed, dev)
+    value = total_vox / (ms * 1e-3)
+
+    # ---- e2e: HOST buffers in, host result out, through the public API (GenModel.forward), copies inside the region
+    out_host = None
+
+    def e2e_step(i):
+        hl, hf = host[i % args.sets]
+        dl = hl.to(dev, non_blocking=True)
+        df = hf.to(dev, non_blocking=True)
+        (ol, osdf), _ = model([dl, df], ones)
+        return ol.to('cpu', non_blocking=True), osdf.to('cpu', non_blocking=True), ol.shape[0]
+
+    for w in range(2):
+        e2e_step(w)
+    barrier()
+    e0.record()
+    d2h = 0
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)
+        ol, osdf, n = e2e_step(i)
+        d2h += n * (4 * 8 + 4)
+    e1.record()
+    barrier()
+    e2e_ms = shard.max_over_ranks(e0.elapsed_time(e1), dev)
+    e2e_value = total_vox / (e2e_ms * 1e-3)
+    h2d = sum(host[i % args.sets][0].numel() * 8 + host[i % args.sets][1].numel() * 4 for i in range(args.steps))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    sampler.stop_flag = True
+    sampler.join(2)
+
+    # ---- roofline of the dominant kernel (conv_gather_f32_kernel, all shapes): algorithmic bytes / measured time
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'MEASURED_PEAKS.json hbm_gbs (measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
+    per_set_bytes, per_set_flops = 0.0, 0.0
+    for rec in ledger:
+        r = rec['R']
+        rec['bytes'] = (rec['n_in'] * rec['cin'] + rec['n_out'] * rec['cout']) * 4 + 8 * r + rec['K'] * rec['cin'] * rec['cout'] * 4
+        rec['flops'] = 2.0 * r * rec['cin'] * rec['cout']
+        per_set_bytes += rec['bytes']
+        per_set_flops += rec['flops']
+    conv_ms = sum(a.elapsed_time(b) for a, b, _ in prof.events)
+    n_conv = max(len(prof.events), 1)
+    convs_per_step = len(prof.events) / max(args.steps, 1)
+    # ledger is of set 0; all sets are statistically alike (same generator) -> scale by launches
+    alg_bytes_total = per_set_bytes * args.steps
+    achieved = alg_bytes_total / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0
+    roofline = {
+        'kernel': 'conv_gather_f32_kernel (all %d launches per step)' % round(convs_per_step),
+        'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
+        'traffic': None, 'peak_source': peak_src,
+        'algorithmic_bytes_per_launch': per_set_bytes / max(convs_per_step, 1),
+        'avg_launch_us': 1e3 * conv_ms / n_conv,
+        'share_of_step': conv_ms / dev_ms if dev_ms > 0 else None,
+        'gflops_per_step': per_set_flops / 1e9,
+        'achieved_tflops_fp32': per_set_flops * args.steps / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0,
+        'note': 'fp32 FFMA path: compute-bound above ~11 flop/B; HBM fraction reported per SURVEY 8(d)',
+    }
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, t, cores, nvox = cpu_forward_rate(args.cpu_blocks, args.cpu_reps, args.param_seed)
+        cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+               'sample': 'median of %d forwards of %d x 64^3 block(s) (%d voxels, %.2f s each); restated '
+                         'SparseConvNet-CPU path (oracle O2) under the oracle port of model.py' %
+                         (args.cpu_reps, args.cpu_blocks, nvox, t)}
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'BASELINE configs[1]: %d synthetic 64^3 TSDF blocks @5%% per GPU per step, full '
+                               '3-level coarse-to-fine generator, fp32' % args.blocks,
+                   'blocks_per_gpu': args.blocks, 'input_voxels_per_step_per_gpu': vox[0],
+                   'level_candidates_set0': level_rows, 'output_voxels_set0': final_rows,
+                   'parallelism': 'independent blocks, rank = block mod %d, one NCCL weight broadcast' % world,
+                   'l2': '256 MiB flush before every step (inside the timed bracket); %d rotating input sets'
+                         % args.sets,
+                   'params': 'deterministic hash fill seed %d (643735 params)' % args.param_seed},
+        'roofline': roofline, 'cpu_baseline': cpu,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d // args.steps,
+                'd2h_bytes_per_step': d2h // max(args.steps, 1), 'ms_per_step': e2e_ms / args.steps},
+        'gpu_launches': launches, 'clocks': sampler.summary(), 'wall_s': wall,
+    }
+    if args.ledger:
+        with open(args.ledger, 'w') as f:
+            json.dump({'ledger_set0': ledger, 'bytes': per_set_bytes, 'flops': per_set_flops}, f, indent=1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -209,6 +209,9 @@ int sgnn_concat_skip(const SgnnGrid* g, const float* src, int32_t ld_src, int32_
 /* int32 [n,4] -> int64 [n,4] (LongTensor coordinates at the Python boundary). */
 int sgnn_coords_to_i64(const int32_t* in, int64_t n, int64_t* out, void* stream);
 
+/* Number of CUDA kernels this library has launched in the calling process (monotonic). */
+int64_t sgnn_launch_count(void);
+
 int sgnn_version(void);
 const char* sgnn_error_string(int code);
 int sgnn_last_cuda_error(void);

@@ -61,6 +61,7 @@ SIGNATURES = {
     'sgnn_children_coords': (_I, [_P, _L, _P, _P]),
     'sgnn_concat_skip': (_I, [_G, _P, _I, _I, _P, _L, _P, _I, _I, _P]),
     'sgnn_coords_to_i64': (_I, [_P, _L, _P, _P]),
+    'sgnn_launch_count': (_L, []),
     'sgnn_version': (_I, []),
     'sgnn_error_string': (C.c_char_p, [_I]),
     'sgnn_last_cuda_error': (_I, []),

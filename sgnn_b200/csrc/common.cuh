@@ -5,9 +5,11 @@
 #include "../../include/sgnn_b200.h"
 
 extern int g_sgnn_last_cuda_error;
+extern long long g_sgnn_launches;  // kernels launched by this library (bench.py's gpu_launches evidence)
 
 #define SGNN_CHECK_LAUNCH()                                   \
   do {                                                        \
+    ++g_sgnn_launches;                                        \
     cudaError_t e__ = cudaGetLastError();                     \
     if (e__ != cudaSuccess) {                                 \
       g_sgnn_last_cuda_error = (int)e__;                      \

@@ -189,6 +189,9 @@ extern "C" int sgnn_children_coords(const int32_t* parent_coords, int64_t n_pare
 
 // ------------------------------------------------------------ ABI bookkeeping
 int g_sgnn_last_cuda_error = 0;
+long long g_sgnn_launches = 0;
+
+extern "C" int64_t sgnn_launch_count(void) { return (int64_t)g_sgnn_launches; }
 
 extern "C" int sgnn_version(void) { return SGNN_VERSION; }
 

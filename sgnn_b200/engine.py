@@ -28,6 +28,11 @@ def _need_cuda(*ts):
             raise RuntimeError('sgnn_b200: tensors must be CUDA tensors (no CPU fallback in the product path)')
 
 
+# Optional profiler hook (bench.py): an object with .conv(tag, x, nbr, weight, n_out, child_mode) -> ctx or None,
+# where ctx has .done().  None in normal operation: zero overhead.
+PROFILER = None
+
+
 def _scratch(nbytes, device):
     return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
 
@@ -167,7 +172,11 @@ def conv(x, nbr, weight, n_out, out_a, child_mode=False, residual=None, scale_a=
         a.ld_res = 0
     a.a = _epilogue(out_a, scale_a, shift_a, relu_a)
     a.b = _epilogue(out_b, scale_b, shift_b, relu_b)
+    ctx = PROFILER.conv(x, nbr, weight, int(n_out), child_mode, residual is not None,
+                        out_b is not None) if PROFILER is not None else None
     check(lib.sgnn_conv_forward(C.byref(a), _stream()), 'sgnn_conv_forward')
+    if ctx is not None:
+        ctx.done()
     return out_a
 
 

@@ -1,0 +1,212 @@
+"""-m gpu: floating-point kernels through the C ABI.  fp32 results are compared BIT-EXACT with oracle O3
+(fixed fmaf order) and to 1e-4 with the dense-conv identity O1."""
+import numpy as np
+import pytest
+import torch
+
+import o3
+import dense_equiv as o1
+from helpers import random_coords, nbr_table, coarse_sets
+
+pytestmark = pytest.mark.gpu
+
+PAIRS = [(1, 8), (8, 8), (8, 12), (12, 12), (12, 16), (16, 16), (34, 16), (30, 16), (26, 16), (48, 16), (18, 4)]
+
+
+def _E():
+    import sgnn_b200.engine as E
+    return E
+
+
+def _site_case(seed, nb=2, dims=(12, 10, 14), occ=0.35):
+    rng = np.random.default_rng(seed)
+    c = random_coords(rng, nb, dims, occ)
+    return rng, c, dims, nb
+
+
+@pytest.mark.parametrize('cin,cout', PAIRS)
+@pytest.mark.parametrize('pad', [0, 1])
+def test_submanifold_conv_bit_exact(cin, cout, pad):
+    E = _E()
+    rng, c, dims, nb = _site_case(cin * 31 + cout)
+    n = c.shape[0]
+    ld = (cin + 3) // 4 * 4 if pad else cin                   # padded rows -> 16-byte gather path
+    xbuf = torch.zeros((n, ld), dtype=torch.float32)
+    xbuf[:, :cin] = torch.from_numpy(rng.standard_normal((n, cin)).astype(np.float32))
+    if ld > cin:
+        xbuf[:, cin:] = float('nan')                          # padding must never be read into the sum
+    w = torch.from_numpy((rng.standard_normal((27, cin, cout)) * 0.1).astype(np.float32))
+    nbr = torch.from_numpy(nbr_table(c))
+    want = o3.conv(xbuf[:, :cin], nbr, w, n)
+    xd = xbuf.cuda()
+    out = torch.empty((n, cout), dtype=torch.float32, device='cuda')
+    E.conv(xd[:, :cin], nbr.cuda(), w.cuda(), n, out)
+    assert torch.equal(out.cpu(), want)
+    dense = o1.submanifold_conv(torch.from_numpy(c), xbuf[:, :cin].contiguous(), w, nb, dims)
+    assert torch.allclose(out.cpu(), dense, atol=1e-4, rtol=1e-4)
+
+
+def test_conv_epilogues_residual_dual_slot_views():
+    E = _E()
+    rng, c, dims, nb = _site_case(5)
+    n = c.shape[0]
+    x = torch.from_numpy(rng.standard_normal((n, 16)).astype(np.float32))
+    r = torch.from_numpy(rng.standard_normal((n, 16)).astype(np.float32))
+    w = torch.from_numpy((rng.standard_normal((27, 16, 16)) * 0.1).astype(np.float32))
+    sa, ta = torch.rand(16) + 0.5, torch.rand(16) - 0.5
+    sb, tb = torch.rand(16) + 0.5, torch.rand(16) - 0.5
+    nbr = torch.from_numpy(nbr_table(c))
+    wa = o3.conv(x, nbr, w, n, residual=r, scale=sa, shift=ta, relu=True)
+    wb = o3.conv(x, nbr, w, n, residual=r, scale=sb, shift=tb, relu=False)
+    wide = torch.full((n, 48), -7.0, device='cuda')           # JoinTable slot: columns 16..31 of a 48-wide row
+    ob = torch.empty((n, 16), device='cuda')
+    E.conv(x.cuda(), nbr.cuda(), w.cuda(), n, wide[:, 16:32], residual=r.cuda(), scale_a=sa.cuda(),
+           shift_a=ta.cuda(), relu_a=True, out_b=ob, scale_b=sb.cuda(), shift_b=tb.cuda(), relu_b=False)
+    assert torch.equal(wide[:, 16:32].cpu(), wa) and torch.equal(ob.cpu(), wb)
+    assert (wide[:, :16] == -7).all() and (wide[:, 32:] == -7).all()
+    raw = torch.empty((n, 16), device='cuda')
+    E.conv(x.cuda(), nbr.cuda(), w.cuda(), n, raw)
+    assert torch.equal(raw.cpu(), o3.conv(x, nbr, w, n))
+
+
+@pytest.mark.parametrize('c_', [8, 12, 16])
+def test_strided_conv_deconv_unpool(c_):
+    E = _E()
+    rng, c, dims, nb = _site_case(c_, dims=(12, 10, 14))
+    n = c.shape[0]
+    cc, parent, children, cd = coarse_sets(c, dims)
+    x = torch.from_numpy(rng.standard_normal((n, c_)).astype(np.float32))
+    w = torch.from_numpy((rng.standard_normal((8, c_, c_)) * 0.2).astype(np.float32))
+    want = o3.conv(x, torch.from_numpy(children), w, cc.shape[0])
+    out = torch.empty((cc.shape[0], c_), device='cuda')
+    E.conv(x.cuda(), torch.from_numpy(children).cuda(), w.cuda(), cc.shape[0], out)
+    assert torch.equal(out.cpu(), want)
+    assert torch.allclose(want, o1.strided_conv(torch.from_numpy(c), x, w, nb, dims, torch.from_numpy(cc)), atol=1e-4)
+    # deconvolution back to the fine set (BASELINE.json configs[2] op pair)
+    wd = torch.from_numpy((rng.standard_normal((8, c_, c_)) * 0.2).astype(np.float32))
+    dz = torch.empty((n, c_), device='cuda')
+    E.deconv(out, torch.from_numpy(parent).cuda(), wd.cuda(), dz)
+    assert torch.equal(dz.cpu(), o3.deconv(want, torch.from_numpy(parent), wd))
+    assert torch.allclose(dz.cpu(), o1.strided_deconv(torch.from_numpy(cc), want, wd, nb, cd, torch.from_numpy(c)),
+                          atol=1e-4)
+    up = torch.empty((n, c_), device='cuda')
+    E.unpool(out, torch.from_numpy(parent).cuda(), up)
+    assert torch.equal(up.cpu(), o1.unpool(torch.from_numpy(cc), want, nb, cd, torch.from_numpy(c)))
+    s, t = torch.rand(c_) + 0.5, torch.rand(c_) - 0.5
+    E.unpool(out, torch.from_numpy(parent).cuda(), up, scale=s.cuda(), shift=t.cuda(), relu=True)
+    assert torch.equal(up.cpu(), o3.affine_relu(o1.unpool(torch.from_numpy(cc), want, nb, cd, torch.from_numpy(c)), s, t))
+
+
+def test_child_mode_conv_bit_exact():
+    E = _E()
+    rng, c, dims, nb = _site_case(9, dims=(7, 6, 9), occ=0.4)
+    n = c.shape[0]
+    x = torch.from_numpy(rng.standard_normal((n, 48)).astype(np.float32))
+    w = torch.from_numpy((rng.standard_normal((27, 48, 16)) * 0.05).astype(np.float32))
+    s, t = torch.rand(16) + 0.5, torch.rand(16) - 0.5
+    nbr = torch.from_numpy(nbr_table(c))
+    want = o3.conv(x, nbr, w, 8 * n, child_mode=True, scale=s, shift=t, relu=True)
+    out = torch.empty((8 * n, 16), device='cuda')
+    E.conv(x.cuda(), nbr.cuda(), w.cuda(), 8 * n, out, child_mode=True, scale_a=s.cuda(), shift_a=t.cuda(), relu_a=True)
+    assert torch.equal(out.cpu(), want)
+
+
+def test_generic_cout_and_empty():
+    E = _E()
+    rng, c, dims, nb = _site_case(3)
+    n = c.shape[0]
+    x = torch.from_numpy(rng.standard_normal((n, 5)).astype(np.float32))
+    w = torch.from_numpy((rng.standard_normal((27, 5, 7)) * 0.1).astype(np.float32))
+    nbr = torch.from_numpy(nbr_table(c))
+    out = torch.empty((n, 7), device='cuda')
+    E.conv(x.cuda(), nbr.cuda(), w.cuda(), n, out)
+    assert torch.equal(out.cpu(), o3.conv(x, nbr, w, n))
+    E.conv(x.cuda()[:0], nbr.cuda()[:, :0], w.cuda(), 0, out[:0])          # n_out == 0 is a no-op
+
+
+def test_pointwise_kernels():
+    E = _E()
+    rng = np.random.default_rng(0)
+    n = 1000
+    x = torch.from_numpy(rng.standard_normal((n, 48)).astype(np.float32))
+    s, t = torch.rand(48) + 0.5, torch.rand(48) - 0.5
+    y = torch.empty((n, 48), device='cuda')
+    E.affine_relu(x.cuda(), y, s.cuda(), t.cuda())
+    assert torch.equal(y.cpu(), o3.affine_relu(x, s, t))
+    b = torch.from_numpy(rng.standard_normal((n, 48)).astype(np.float32))
+    E.add_rows(x.cuda(), b.cuda(), y)
+    assert torch.equal(y.cpu(), x + b)
+    wide = torch.zeros((n, 64), device='cuda')
+    E.copy_cols(x.cuda(), wide[:, 8:56])
+    assert torch.equal(wide[:, 8:56].cpu(), x) and float(wide[:, :8].abs().sum()) == 0
+    lin = torch.nn.Linear(48, 1)
+    o = torch.empty((n, 1), device='cuda')
+    E.linear(x.cuda(), lin.weight.detach().cuda(), lin.bias.detach().cuda(), o)
+    assert torch.equal(o.cpu(), o3.linear(x, lin.weight.detach(), lin.bias.detach()))
+
+
+def test_sparse_to_dense_and_back():
+    E = _E()
+    rng, c, dims, nb = _site_case(4, nb=3, dims=(8, 8, 8), occ=0.3)
+    n = c.shape[0]
+    f = torch.from_numpy(rng.standard_normal((n, 16)).astype(np.float32))
+    d = E.sparse_to_dense(f.cuda(), torch.from_numpy(c.astype(np.int32)).cuda(), nb, list(dims))
+    assert torch.equal(d.cpu(), o1.densify(torch.from_numpy(c), f, nb, dims))
+    occsdf = torch.from_numpy(rng.standard_normal((nb, 2, 8, 8, 8)).astype(np.float32))
+    occsdf[0, 0, 0, 0, :4] = torch.tensor([0.0, 5e-8, 1.3e-7, -1e-9])      # threshold edge
+    locs, feats, cand, m = E.dense_to_sparse(d, occsdf.cuda(), ld_feats=36)
+    keep = o3.sigmoid_gt_half(occsdf[:, 0].reshape(-1))
+    assert torch.equal(keep, torch.sigmoid(occsdf[:, 0].reshape(-1)) > 0.5)
+    assert m == int(keep.sum())
+    zz, yy, xx = torch.meshgrid(torch.arange(8), torch.arange(8), torch.arange(8), indexing='ij')
+    cell = torch.stack([zz, yy, xx], -1).view(-1, 3)
+    all_locs = torch.cat([cell.repeat(nb, 1), torch.arange(nb).repeat_interleave(512).view(-1, 1)], 1)
+    assert torch.equal(locs.cpu().long(), all_locs[keep])
+    allf = torch.cat([occsdf.permute(0, 2, 3, 4, 1).reshape(-1, 2), d.cpu().permute(0, 2, 3, 4, 1).reshape(-1, 16)], 1)
+    assert torch.equal(feats[:, :18].cpu(), allf[keep]) and float(feats[:, 18:].abs().sum()) == 0
+    assert torch.equal(cand.cpu(), allf[:, :2])
+
+
+def test_heads_compact_and_children_and_skip():
+    E = _E()
+    rng, c, dims, nb = _site_case(6, dims=(6, 6, 6), occ=0.4)
+    n = c.shape[0]
+    x = torch.from_numpy(rng.standard_normal((8 * n, 16)).astype(np.float32))
+    lo, ls = torch.nn.Linear(16, 1), torch.nn.Linear(16, 1)
+    pc = torch.from_numpy(c.astype(np.int32)).cuda()
+    locs, feats, cand, m = E.heads_compact(x.cuda(), lo.weight.detach().view(-1).cuda(), lo.bias.detach().cuda(),
+                                           ls.weight.detach().view(-1).cuda(), ls.bias.detach().cuda(), pc, ld_feats=36)
+    occ = o3.linear(x, lo.weight.detach(), lo.bias.detach())
+    sdf = o3.linear(x, ls.weight.detach(), ls.bias.detach())
+    assert torch.equal(cand.cpu(), torch.cat([occ, sdf], 1))
+    keep = o3.sigmoid_gt_half(occ.view(-1))
+    kids = (c[:, None, :] * np.array([2, 2, 2, 1]) +
+            np.array([[z, y, x_, 0] for z in (0, 1) for y in (0, 1) for x_ in (0, 1)])[None]).reshape(-1, 4)
+    assert np.array_equal(E.children_coords(pc).cpu().numpy(), kids)
+    assert m == int(keep.sum())
+    assert np.array_equal(locs.cpu().numpy(), kids[keep.numpy()])
+    assert torch.equal(feats[:, :18].cpu(), torch.cat([x, occ, sdf], 1)[keep])
+    # concat_skip: join an "encoder" set onto the kept children by coordinate
+    enc_c = random_coords(np.random.default_rng(8), nb, (12, 12, 12), 0.5)
+    enc_f = torch.from_numpy(rng.standard_normal((enc_c.shape[0], 12)).astype(np.float32))
+    g = E.build_grid(torch.from_numpy(enc_c).cuda(), nb, (12, 12, 12))
+    E.concat_skip(g, enc_f.cuda(), locs, feats, 18)
+    import sparseconvnet as o2
+    rows = o2._SiteSet(torch.from_numpy(enc_c)).lookup(kids[keep.numpy()])
+    want = torch.where(torch.from_numpy(rows >= 0).view(-1, 1), enc_f[np.maximum(rows, 0)], torch.zeros(1))
+    assert torch.equal(feats[:, 18:30].cpu(), want)
+
+
+def test_error_codes():
+    E = _E()
+    from sgnn_b200._lib import SgnnError
+    x = torch.zeros((10, 16), device='cuda')
+    nbr = torch.full((27, 10), -1, dtype=torch.int32, device='cuda')
+    w = torch.zeros((27, 16, 16), device='cuda')
+    bad = torch.zeros((10, 17), device='cuda')[:, 1:]                # misaligned output rows
+    with pytest.raises(SgnnError, match='alignment'):
+        E.conv(x, nbr, w, 10, bad)
+    with pytest.raises(SgnnError, match='unsupported'):
+        E.conv(x, nbr[:5], w[:5].contiguous(), 10, torch.empty((10, 16), device='cuda'))
+    with pytest.raises(RuntimeError):
+        E.conv(x.cpu(), nbr, w, 10, torch.empty((10, 16), device='cuda'))

@@ -1,0 +1,167 @@
+"""-m gpu: the whole generator through the drop-in boundary.
+
+Parity gates (north_star): TSDF head within 1e-3 fp32, occupancy coordinates bit-exact -- against (1) the golden
+fixtures the UNMODIFIED reference model.py produced on oracle O2 (tests/golden/make_golden.py), (2) the oracle
+generator run live on the CPU, and, at BASELINE.json sizes, through size-independent properties
+(fused == module-by-module bit for bit, determinism, row-order / batch-composition invariance).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from helpers import sorted_rows
+
+pytestmark = pytest.mark.gpu
+ONES = np.ones(5, dtype=np.float32)
+TOL_SDF = 1e-3          # north_star tolerance on the TSDF regression head
+TOL_LOGIT = 1e-4        # occupancy logits / candidate sdf (tighter than required)
+
+
+def _model(dims, seed):
+    import sgnn_b200
+    from sgnn_b200.synth import fill_parameters
+    m = sgnn_b200.GenModel(8, list(dims), 1, 16, 16, 4, True, True, 1, 1)
+    fill_parameters(m, seed)
+    return m.cuda().eval()
+
+
+def _same_outputs(a, b):
+    (la, sa), lva = a
+    (lb, sb), lvb = b
+    assert torch.equal(la, lb) and torch.equal(sa, sb)
+    assert len(lva) == len(lvb)
+    for x, y in zip(lva, lvb):
+        assert torch.equal(x[0], y[0]) and torch.equal(x[1], y[1])
+
+
+@pytest.mark.parametrize('name', ['b2_s32', 'ragged', 'b1_s64'])
+def test_golden_fixture_from_reference_model(name):
+    g = np.load(os.path.join(GOLDEN, 'sgnn_ref_%s.npz' % name))
+    m = _model(g['dims'], int(g['param_seed']))
+    locs = torch.from_numpy(g['in_locs'].astype(np.int64))          # CPU LongTensor, as test_scene.py:81 leaves it
+    feats = torch.from_numpy(g['in_feats']).cuda()
+    (out_locs, out_sdf), levels = m([locs, feats], ONES)
+    # fixture margin: no oracle logit within 2e-5 of the threshold -> coordinates must match EXACTLY, in order
+    assert float(g['margin']) > 2e-5
+    for i, l in enumerate(levels):
+        assert np.array_equal(l[0].cpu().numpy(), g['cand%d_locs' % i].astype(np.int64)), 'level %d candidates' % i
+        assert np.abs(l[1].cpu().numpy() - g['cand%d' % i]).max() <= TOL_LOGIT
+        kept = int((torch.sigmoid(l[1][:, 0]) > 0.5).sum())
+        assert kept == int(g['kept'][i])
+    assert np.array_equal(out_locs.cpu().numpy(), g['out_locs'].astype(np.int64))
+    assert np.abs(out_sdf.cpu().numpy() - g['out_sdf']).max() <= TOL_SDF
+    # and the reference-shaped (module by module) path gives the SAME bits as the fused path
+    _same_outputs(((out_locs, out_sdf), levels), m.forward_modules([locs, feats], ONES))
+
+
+@pytest.mark.parametrize('dims,nb,occ,seed', [((32, 32, 64), 2, 0.07, 21), ((32, 32, 32), 3, 0.1, 22)])
+def test_against_live_oracle_generator(dims, nb, occ, seed):
+    from genmodel import OracleGenModel
+    from sgnn_b200.synth import fill_parameters, synthetic_batch
+    locs, feats = synthetic_batch(nb, list(dims), occ, seed0=seed)
+    ora = OracleGenModel(input_dim=list(dims))
+    fill_parameters(ora, seed)
+    ora.eval()
+    with torch.no_grad():
+        (wl, ws), wlv = ora(locs, feats)
+    m = _model(dims, seed)
+    (gl, gs), glv = m([locs.cuda(), feats.cuda()], ONES)
+    diverged = False
+    for i, (w, gg) in enumerate(zip(wlv, glv)):
+        if diverged:
+            break
+        assert torch.equal(w[0], gg[0].cpu()), 'candidate coordinates at level %d' % i
+        assert (w[1] - gg[1].cpu()).abs().max() <= TOL_LOGIT
+        wk = torch.sigmoid(w[1][:, 0]) > 0.5
+        gk = torch.sigmoid(gg[1][:, 0].cpu()) > 0.5
+        flips = wk != gk
+        # margin-aware: a flip is only legal where the oracle logit is within 1e-5 of the threshold
+        assert bool((w[1][:, 0][flips].abs() < 1e-5).all())
+        diverged = bool(flips.any())
+    if not diverged:
+        assert torch.equal(wl, gl.cpu())
+        assert (ws - gs.cpu()).abs().max() <= TOL_SDF
+
+
+def test_row_order_and_batch_composition_invariance():
+    from sgnn_b200.synth import synthetic_batch
+    dims = (32, 32, 32)
+    m = _model(dims, 0)
+    locs, feats = synthetic_batch(2, list(dims), 0.08)
+    base = m([locs.cuda(), feats.cuda()], ONES)
+    perm = torch.randperm(locs.shape[0], generator=torch.Generator().manual_seed(0))
+    shuf = m([locs[perm].cuda(), feats[perm].cuda()], ONES)
+    # encoder rows are permuted, but everything downstream of the dense grid is keyed by coordinates
+    a = sorted_rows(base[0][0].cpu().numpy(), base[0][1].cpu().numpy())
+    b = sorted_rows(shuf[0][0].cpu().numpy(), shuf[0][1].cpu().numpy())
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # a block gives the same result alone and inside a batch (eval BN is per row; blocks share no rules)
+    for bidx in range(2):
+        sel = locs[:, 3] == bidx
+        l1 = locs[sel].clone()
+        l1[:, 3] = 0
+        one = m([l1.cuda(), feats[sel].cuda()], ONES)
+        in_batch = base[0][0][:, 3].cpu() == bidx
+        x = sorted_rows(one[0][0].cpu().numpy()[:, :3], one[0][1].cpu().numpy())
+        y = sorted_rows(base[0][0].cpu().numpy()[in_batch.numpy()][:, :3], base[0][1].cpu().numpy()[in_batch.numpy()])
+        if x[0].shape == y[0].shape and np.array_equal(x[0], y[0]):        # cuDNN may pick another algo per batch size
+            assert np.abs(x[1] - y[1]).max() <= TOL_SDF
+
+
+def test_baseline_config_properties():
+    """BASELINE.json configs[1]: 32 synthetic 64^3 blocks @5 %, full 3-level generator, fp32."""
+    from sgnn_b200.synth import synthetic_batch
+    m = _model((64, 64, 64), 0)
+    locs, feats = synthetic_batch(32, 64, 0.05)
+    a = m([locs.cuda(), feats.cuda()], ONES)
+    b = m([locs.cuda(), feats.cuda()], ONES)
+    _same_outputs(a, b)                                             # deterministic (no atomics on the float path)
+    _same_outputs(a, m.forward_modules([locs.cuda(), feats.cuda()], ONES))
+    (fl, fs), lv = a
+    assert lv[0][0].shape[0] == 32 * 512
+    for i in range(1, 4):
+        kept_prev = int((torch.sigmoid(lv[i - 1][1][:, 0]) > 0.5).sum())
+        assert lv[i][0].shape[0] == 8 * kept_prev                  # 8 children per kept parent (model.py:192-207)
+    assert fl.shape[0] == int((torch.sigmoid(lv[3][1][:, 0]) > 0.5).sum()) and fs.shape == (fl.shape[0], 1)
+    assert torch.isfinite(fs).all()
+    assert int(fl[:, :3].max()) < 64 and int(fl[:, 3].max()) < 32
+
+
+def test_dropin_sparseconvnet_modules_against_oracle():
+    """`import sparseconvnet as scn` bound to the engine: module-level parity with oracle O2."""
+    import sys
+    from conftest import ROOT
+    import sparseconvnet as o2                  # oracle (conftest path)
+    import sgnn_b200.scn as scn
+    from helpers import random_coords
+    rng = np.random.default_rng(3)
+    dims = [16, 16, 16]
+    c = torch.from_numpy(random_coords(rng, 2, dims, 0.2))
+    f = torch.from_numpy(rng.standard_normal((c.shape[0], 4)).astype(np.float32))
+
+    def net(lib):
+        torch.manual_seed(0)
+        s = lib.Sequential()
+        s.add(lib.SubmanifoldConvolution(3, 4, 16, 3, False))
+        s.add(lib.FullyConvolutionalNet(3, reps=1, nPlanes=[16, 16, 16], residual_blocks=True))
+        s.add(lib.BatchNormReLU(48))
+        s.add(lib.Convolution(3, 48, 16, 2, 2, False))
+        s.add(lib.Deconvolution(3, 16, 8, 2, 2, False))
+        return s
+    a, b = net(o2).eval(), net(scn)
+    b.load_state_dict(a.state_dict())
+    b = b.cuda().eval()
+    with torch.no_grad():
+        ta = a(o2.InputLayer(3, dims, mode=0)([c, f]))
+        tb = b(scn.InputLayer(3, dims, mode=0)([c, f.cuda()]))
+        assert torch.equal(tb.metadata.getSpatialLocations(tb.spatial_size).cpu(),
+                           ta.metadata.getSpatialLocations(ta.spatial_size))
+        assert torch.allclose(scn.OutputLayer(3)(tb).cpu(), o2.OutputLayer(3)(ta), atol=1e-4, rtol=1e-4)
+        da = o2.SparseToDense(3, 8)(ta)
+        db = scn.SparseToDense(3, 8)(tb)
+        assert db.shape == da.shape and torch.allclose(db.cpu(), da, atol=1e-4, rtol=1e-4)
+    with pytest.raises(NotImplementedError):
+        b.train()(scn.InputLayer(3, dims, mode=0)([c, f.cuda()]))
