@@ -17,5 +17,8 @@ from .model import GenModel   # noqa: F401
 # fp32 parity of the dense 8^3 U-Net: cuDNN / cuBLAS TF32 would perturb the first mask.
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
+# run-to-run reproducibility of the library part (cuDNN may otherwise pick atomics-based algorithms)
+torch.backends.cudnn.deterministic = True
+torch.backends.cudnn.benchmark = False
 
 __version__ = '0.1.0'

@@ -289,8 +289,8 @@ extern "C" int sgnn_conv_forward(const SgnnConvArgs* a, void* stream) {
   if (a->dtype != SGNN_F32) return SGNN_E_UNSUPPORTED;
   if (a->K != 27 && a->K != 8) return SGNN_E_UNSUPPORTED;
   if (a->child_mode && a->K != 27) return SGNN_E_INVALID;
-  if (!a->a.out && !a->b.out) return SGNN_E_INVALID;
   if (a->n_out == 0) return SGNN_OK;
+  if (!a->a.out && !a->b.out) return SGNN_E_INVALID;
   if (!a->in || !a->nbr) return SGNN_E_INVALID;
   if (a->cin > 64) return SGNN_E_UNSUPPORTED;
   ConvParams p;

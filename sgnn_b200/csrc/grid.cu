@@ -63,7 +63,7 @@ extern "C" int sgnn_grid_build(const SgnnGrid* g, const void* coords, int coords
       g->n_words != (int64_t)g->nb * g->d0 * g->d1 * g->wx)
     return SGNN_E_INVALID;
   if (n > 0x7fffffffLL || g->n_words > 0x7fffffffLL) return SGNN_E_TOO_LARGE;
-  if (g->row_of_rank && !coords_i32_out) return SGNN_E_INVALID;
+  if (g->row_of_rank && !coords_i32_out && n > 0) return SGNN_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   GridView v = make_view(g);
   SGNN_CUDA(cudaMemsetAsync(g->mask, 0, (size_t)g->n_words * 8, st));

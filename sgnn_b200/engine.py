@@ -70,7 +70,8 @@ class Grid(object):
 def build_grid(coords, nb, dims, status=None):
     """a1: grid from caller-ordered coords (int64 or int32 CUDA tensor [n,4])."""
     _need_cuda(coords)
-    assert coords.dim() == 2 and coords.shape[1] == 4 and coords.is_contiguous()
+    assert coords.dim() == 2 and coords.shape[1] == 4
+    coords = coords.contiguous()
     n = coords.shape[0]
     g = Grid(nb, dims, coords.device, True)
     g.n = n
@@ -99,12 +100,14 @@ def coarsen(fine, dims_cap=None):
     check(lib.sgnn_grid_coarsen(fine.ref(), g.ref(), _ptr(scr), sb, _stream()), 'sgnn_grid_coarsen')
     g.n = int(g.prefix[g.n_words].item())
     g.coords = torch.empty((g.n, 4), dtype=torch.int32, device=fine.device)
-    check(lib.sgnn_grid_enumerate(g.ref(), _ptr(g.coords), _stream()), 'sgnn_grid_enumerate')
+    if g.n:
+        check(lib.sgnn_grid_enumerate(g.ref(), _ptr(g.coords), _stream()), 'sgnn_grid_enumerate')
     return g
 
 
 def grid_lookup(grid, coords, shift=0):
     _need_cuda(coords)
+    coords = coords.contiguous()
     rows = torch.empty(coords.shape[0], dtype=torch.int32, device=coords.device)
     check(lib.sgnn_grid_lookup(grid.ref(), _ptr(coords), coords.shape[0], shift, _ptr(rows), _stream()),
           'sgnn_grid_lookup')
@@ -233,6 +236,7 @@ def linear(x, weight, bias, out):
 
 def sparse_to_dense(feats, coords, nb, dims):
     _need_cuda(feats, coords)
+    coords = coords.contiguous()
     c = feats.shape[1]
     dense = torch.empty((nb, c, dims[0], dims[1], dims[2]), dtype=torch.float32, device=feats.device)
     check(lib.sgnn_sparse_to_dense(_ptr(feats), feats.stride(0) if feats.shape[0] else c, _ptr(coords),
@@ -266,6 +270,7 @@ def heads_compact(x, w_occ, b_occ, w_sdf, b_sdf, parent_coords, ld_feats=None):
     """a9.  x [8*n_parent, c] post-BNReLU candidate features.  Returns locs [M,4] int32, feats [M, ld]
     (= [x, occ, sdf] in the first c+2 columns), cand [8*n_parent, 2], M (one host read)."""
     _need_cuda(x, w_occ, b_occ, w_sdf, b_sdf, parent_coords)
+    parent_coords = parent_coords.contiguous()
     n_parent = parent_coords.shape[0]
     n_cand = 8 * n_parent
     c = x.shape[1]
@@ -287,6 +292,7 @@ def heads_compact(x, w_occ, b_occ, w_sdf, b_sdf, parent_coords, ld_feats=None):
 
 def children_coords(parent_coords):
     _need_cuda(parent_coords)
+    parent_coords = parent_coords.contiguous()
     n = parent_coords.shape[0]
     out = torch.empty((8 * n, 4), dtype=torch.int32, device=parent_coords.device)
     check(lib.sgnn_children_coords(_ptr(parent_coords), n, _ptr(out), _stream()), 'sgnn_children_coords')
@@ -296,6 +302,7 @@ def children_coords(parent_coords):
 def concat_skip(grid, src, coords, dst, col0):
     """a10: dst[:, col0:col0+c] = src[row of coords in grid] or 0."""
     _need_cuda(src, coords, dst)
+    coords = coords.contiguous()
     assert dst.stride(1) == 1 and (src.shape[0] == 0 or src.stride(1) == 1)
     check(lib.sgnn_concat_skip(grid.ref(), _ptr(src), src.stride(0) if src.shape[0] else src.shape[1],
                                src.shape[1], _ptr(coords), coords.shape[0], _ptr(dst), dst.stride(0), col0,

@@ -49,7 +49,7 @@ def synthetic_block(b, size=64, occ=0.05, seed0=1234):
     mask = rng.random(tuple(size)) < occ
     c = np.argwhere(mask)
     f = rng.uniform(-3, 3, (c.shape[0], 1)).astype(np.float32)
-    return np.concatenate([c, np.full((c.shape[0], 1), b, dtype=np.int64)], 1).astype(np.int64), f
+    return np.ascontiguousarray(np.concatenate([c, np.full((c.shape[0], 1), b, dtype=np.int64)], 1).astype(np.int64)), f
 
 
 def synthetic_batch(blocks, size=64, occ=0.05, seed0=1234, first=0):
@@ -59,4 +59,5 @@ def synthetic_batch(blocks, size=64, occ=0.05, seed0=1234, first=0):
         c[:, 3] = i
         cs.append(c)
         fs.append(f)
-    return torch.from_numpy(np.concatenate(cs)), torch.from_numpy(np.concatenate(fs))
+    return (torch.from_numpy(np.ascontiguousarray(np.concatenate(cs))),
+            torch.from_numpy(np.ascontiguousarray(np.concatenate(fs))))

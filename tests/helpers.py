@@ -17,7 +17,7 @@ def random_coords(rng, nb, dims, occ, empty=()):
         cs.append(np.concatenate([c, np.full((c.shape[0], 1), b)], 1))
     if not cs:
         return np.zeros((0, 4), dtype=np.int64)
-    return np.concatenate(cs).astype(np.int64)
+    return np.ascontiguousarray(np.concatenate(cs).astype(np.int64))
 
 
 def nbr_table(coords):
@@ -55,5 +55,6 @@ def coarse_sets(coords, dims):
 def sorted_rows(locs, *vals):
     """Sort rows by (b,z,y,x) for set comparison; locs numpy [n,4]."""
     locs = np.asarray(locs).astype(np.int64)
-    order = np.lexsort((locs[:, 2], locs[:, 1], locs[:, 0], locs[:, 3]))
+    keys = [locs[:, i] for i in range(locs.shape[1])]
+    order = np.lexsort(tuple(keys[:3][::-1]) + ((keys[3],) if len(keys) > 3 else ()))
     return (locs[order],) + tuple(np.asarray(v)[order] for v in vals)
