@@ -60,6 +60,49 @@ __device__ __forceinline__ int conv_src_row(const ConvParams& p, long long j, in
   return __ldg(p.nbr + (long long)kp * p.nbr_stride + (j >> 3));
 }
 
+// Shared epilogue: residual add, two output slots with optional affine + relu (see SgnnEpilogue).
+template <int COUT>
+__device__ __forceinline__ void conv_epilogue(const ConvParams& p, const float (&acc)[TS][4], long long tile_base,
+                                              int sg, int cg) {
+  float4 sa = make_float4(1.f, 1.f, 1.f, 1.f), ta = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa, tb = ta;
+  if (p.out_a && p.scale_a) {
+    sa = __ldg(reinterpret_cast<const float4*>(p.scale_a) + cg);
+    ta = __ldg(reinterpret_cast<const float4*>(p.shift_a) + cg);
+  }
+  if (p.out_b && p.scale_b) {
+    sb = __ldg(reinterpret_cast<const float4*>(p.scale_b) + cg);
+    tb = __ldg(reinterpret_cast<const float4*>(p.shift_b) + cg);
+  }
+#pragma unroll
+  for (int t = 0; t < TS; ++t) {
+    const long long j = tile_base + sg + NSG * t;
+    if (j >= p.n_out) continue;
+    float4 v = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+    if (p.residual) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + j * p.ld_res) + cg);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (p.out_a) {
+      float4 y = v;
+      if (p.scale_a) {
+        y.x = fmaf(v.x, sa.x, ta.x); y.y = fmaf(v.y, sa.y, ta.y);
+        y.z = fmaf(v.z, sa.z, ta.z); y.w = fmaf(v.w, sa.w, ta.w);
+      }
+      if (p.relu_a) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+      reinterpret_cast<float4*>(p.out_a + j * p.ld_a)[cg] = y;
+    }
+    if (p.out_b) {
+      float4 y = v;
+      if (p.scale_b) {
+        y.x = fmaf(v.x, sb.x, tb.x); y.y = fmaf(v.y, sb.y, tb.y);
+        y.z = fmaf(v.z, sb.z, tb.z); y.w = fmaf(v.w, sb.w, tb.w);
+      }
+      if (p.relu_b) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+      reinterpret_cast<float4*>(p.out_b + j * p.ld_b)[cg] = y;
+    }
+  }
+}
+
 template <int COUT, int VEC>
 __global__ void __launch_bounds__(NSG * (COUT / 4))
 conv_gather_f32_kernel(ConvParams p) {
@@ -181,44 +224,182 @@ conv_gather_f32_kernel(ConvParams p) {
     live_cur = live_next;
   }
 
-  // ---- epilogue
-  float4 sa = make_float4(1.f, 1.f, 1.f, 1.f), ta = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa, tb = ta;
-  if (p.out_a && p.scale_a) {
-    sa = __ldg(reinterpret_cast<const float4*>(p.scale_a) + cg);
-    ta = __ldg(reinterpret_cast<const float4*>(p.shift_a) + cg);
+  conv_epilogue<COUT>(p, acc, tile_base, sg, cg);
+}
+
+// ------------------------------------------------------------------------------------------------
+// v2 tile kernel: channel counts are compile-time (every loop unrolls, every LDS has an immediate
+// offset), the 27 x 128 neighbour indices of the tile are fetched ONCE into shared memory (coalesced;
+// the child-mode offset arithmetic is paid once per entry, not once per copied chunk), the filter bank
+// is streamed one offset per stage next to the gathered rows (3 KB instead of 83 KB resident -> 2-4 CTAs
+// per SM), dead offsets (no live neighbour in the tile) are skipped without a barrier, and the
+// cp.async ring is NS deep with a single __syncthreads per stage.
+// Same arithmetic as the v1 kernel: k ascending, ci ascending, one fmaf chain per output element.
+template <int CINP>
+struct TileCfg {
+  static constexpr int XS2 = (CINP % 8 == 4) ? CINP : CINP + 4;  // row stride == 4 (mod 8) words: conflict-free LDS.128
+  static constexpr int NS = CINP >= 28 ? 2 : 3;
+  static constexpr int CPR = CINP / 4;
+};
+
+template <int COUT, int CINP>
+__global__ void __launch_bounds__(NSG * (COUT / 4), (CINP >= 28 ? 2 : 4))
+conv_tile_f32_kernel(ConvParams p) {
+  constexpr int NCG = COUT / 4;
+  constexpr int NT = NSG * NCG;
+  constexpr int XS2 = TileCfg<CINP>::XS2;
+  constexpr int NS = TileCfg<CINP>::NS;
+  constexpr int CPR = TileCfg<CINP>::CPR;
+  constexpr int XT = TM * XS2;
+  constexpr int WT = CINP * COUT;
+  constexpr int PAIRS = TM * CPR;
+  extern __shared__ __align__(16) float smem[];
+  int* idx_s = reinterpret_cast<int*>(smem);  // [27][TM]
+  float* stage0 = smem + 27 * TM;              // NS x (X tile [TM][XS2] + W slice [CINP][COUT])
+  __shared__ unsigned live_mask_s;
+
+  const int tid = threadIdx.x;
+  const int sg = tid / NCG, cg = tid % NCG;
+  const long long tile_base = (long long)blockIdx.x * TM;
+
+  if (tid == 0) live_mask_s = 0u;
+  // zero the weight rows of the channel padding once (cp.async only ever writes rows < cin)
+  for (int b = 0; b < NS; ++b) {
+    float* Wd = stage0 + b * (XT + WT) + XT;
+    for (int q = p.cin * COUT + tid; q < WT; q += NT) Wd[q] = 0.f;
   }
-  if (p.out_b && p.scale_b) {
-    sb = __ldg(reinterpret_cast<const float4*>(p.scale_b) + cg);
-    tb = __ldg(reinterpret_cast<const float4*>(p.shift_b) + cg);
+  __syncthreads();
+  unsigned my_live = 0u;
+  for (int e = tid; e < p.K * TM; e += NT) {
+    const int k = e / TM, site = e % TM;
+    const long long j = tile_base + site;
+    const int r = (j < p.n_out) ? conv_src_row(p, j, k) : -1;
+    idx_s[e] = r;
+    if (r >= 0) my_live |= 1u << k;
   }
+  my_live = __reduce_or_sync(0xffffffffu, my_live);
+  if ((tid & 31) == 0 && my_live) atomicOr(&live_mask_s, my_live);
+  __syncthreads();
+  unsigned issue_mask = live_mask_s;
+  const int S = __popc(issue_mask);
+
+  float acc[TS][4];
 #pragma unroll
-  for (int t = 0; t < TS; ++t) {
-    const long long j = tile_base + sg + NSG * t;
-    if (j >= p.n_out) continue;
-    float4 v = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
-    if (p.residual) {
-      const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + j * p.ld_res) + cg);
-      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-    }
-    if (p.out_a) {
-      float4 y = v;
-      if (p.scale_a) {
-        y.x = fmaf(v.x, sa.x, ta.x); y.y = fmaf(v.y, sa.y, ta.y);
-        y.z = fmaf(v.z, sa.z, ta.z); y.w = fmaf(v.w, sa.w, ta.w);
+  for (int t = 0; t < TS; ++t)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[t][c] = 0.f;
+
+  auto issue = [&](int k, int buf) {
+    float* X = stage0 + buf * (XT + WT);
+    float* Wd = X + XT;
+    const int* idk = idx_s + k * TM;
+#pragma unroll
+    for (int it = 0; it < (PAIRS + NT - 1) / NT; ++it) {
+      const int pi = tid + it * NT;
+      if (PAIRS % NT != 0 && pi >= PAIRS) break;
+      const int site = pi / CPR, ch = pi % CPR;
+      const int r = idk[site];
+      float* dst = X + site * XS2 + ch * 4;
+      if (r >= 0) {
+        const float* src = p.in + (long long)r * p.ld_in + ch * 4;
+        if (ch * 4 + 4 <= p.cin) {
+          cp_async16(dst, src);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (ch * 4 + e < p.cin) cp_async4(dst + e, src + e);
+            else dst[e] = 0.f;
+          }
+        }
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (p.relu_a) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-      reinterpret_cast<float4*>(p.out_a + j * p.ld_a)[cg] = y;
     }
-    if (p.out_b) {
-      float4 y = v;
-      if (p.scale_b) {
-        y.x = fmaf(v.x, sb.x, tb.x); y.y = fmaf(v.y, sb.y, tb.y);
-        y.z = fmaf(v.z, sb.z, tb.z); y.w = fmaf(v.w, sb.w, tb.w);
+    const float* Wk = p.weight + (size_t)k * p.cin * COUT;
+    for (int q = tid; q < p.cin * NCG; q += NT) cp_async16(Wd + q * 4, Wk + q * 4);
+  };
+
+#pragma unroll
+  for (int i = 0; i < NS - 1; ++i) {
+    if (issue_mask) {
+      const int k = __ffs(issue_mask) - 1;
+      issue_mask &= issue_mask - 1;
+      issue(k, i);
+    }
+    cp_async_commit();
+  }
+  for (int s = 0; s < S; ++s) {
+    cp_async_wait<NS - 2>();
+    __syncthreads();
+    if (issue_mask) {
+      const int k = __ffs(issue_mask) - 1;
+      issue_mask &= issue_mask - 1;
+      issue(k, (s + NS - 1) % NS);
+    }
+    cp_async_commit();
+    const float* X = stage0 + (s % NS) * (XT + WT);
+    const float* Wd = X + XT + cg * 4;
+    const float* Xr = X + sg * XS2;
+#pragma unroll
+    for (int c4 = 0; c4 < CINP; c4 += 4) {
+      float4 xv[TS];
+#pragma unroll
+      for (int t = 0; t < TS; ++t) xv[t] = *reinterpret_cast<const float4*>(Xr + NSG * t * XS2 + c4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 w = *reinterpret_cast<const float4*>(Wd + (c4 + e) * COUT);
+#pragma unroll
+        for (int t = 0; t < TS; ++t) {
+          const float x = e == 0 ? xv[t].x : e == 1 ? xv[t].y : e == 2 ? xv[t].z : xv[t].w;
+          acc[t][0] = fmaf(x, w.x, acc[t][0]);
+          acc[t][1] = fmaf(x, w.y, acc[t][1]);
+          acc[t][2] = fmaf(x, w.z, acc[t][2]);
+          acc[t][3] = fmaf(x, w.w, acc[t][3]);
+        }
       }
-      if (p.relu_b) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-      reinterpret_cast<float4*>(p.out_b + j * p.ld_b)[cg] = y;
     }
   }
+  cp_async_wait<0>();
+  conv_epilogue<COUT>(p, acc, tile_base, sg, cg);
+}
+
+template <int COUT, int CINP>
+static int launch_tile(const ConvParams& p, cudaStream_t st) {
+  constexpr int NT = NSG * (COUT / 4);
+  const size_t smem = ((size_t)27 * TM + (size_t)TileCfg<CINP>::NS * (TM * TileCfg<CINP>::XS2 + CINP * COUT)) *
+                      sizeof(float);
+  const long long tiles = (p.n_out + TM - 1) / TM;
+  if (tiles > 0x7fffffff) return SGNN_E_TOO_LARGE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SGNN_CUDA(cudaFuncSetAttribute(conv_tile_f32_kernel<COUT, CINP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    attr_set = true;
+  }
+  conv_tile_f32_kernel<COUT, CINP><<<(int)tiles, NT, smem, st>>>(p);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+// (cin padded to 4, cout) pairs of the SG-NN channel plan get the v2 kernel
+static int dispatch_tile(const ConvParams& p, cudaStream_t st, bool* handled) {
+  const int cinp = (p.cin + 3) & ~3;
+  *handled = true;
+#define SGNN_TILE_CASE(CO, CI) \
+  if (p.cout == CO && cinp == CI) return launch_tile<CO, CI>(p, st);
+  SGNN_TILE_CASE(8, 4)
+  SGNN_TILE_CASE(8, 8)
+  SGNN_TILE_CASE(12, 8)
+  SGNN_TILE_CASE(12, 12)
+  SGNN_TILE_CASE(16, 12)
+  SGNN_TILE_CASE(16, 16)
+  SGNN_TILE_CASE(16, 28)
+  SGNN_TILE_CASE(16, 32)
+  SGNN_TILE_CASE(16, 36)
+  SGNN_TILE_CASE(16, 48)
+#undef SGNN_TILE_CASE
+  *handled = false;
+  return SGNN_OK;
 }
 
 // Generic fallback: any Cout, one thread per (row, co).  Same summation order.
@@ -309,6 +490,11 @@ extern "C" int sgnn_conv_forward(const SgnnConvArgs* a, void* stream) {
     if (!aligned16(a->weight)) return SGNN_E_ALIGN;
     if (a->residual && (!aligned16(a->residual) || (a->ld_res & 3))) return SGNN_E_ALIGN;
     const bool vec = aligned16(a->in) && (a->ld_in & 3) == 0;
+    if (vec) {
+      bool handled = false;
+      rc = dispatch_tile(p, st, &handled);
+      if (handled) return rc;
+    }
     switch (a->cout) {
       case 4: return launch_conv<4>(p, vec, st);
       case 8: return launch_conv<8>(p, vec, st);
