@@ -176,6 +176,18 @@ int sgnn_sparse_to_dense(const float* feats, int32_t ld, const int32_t* coords, 
                          int32_t c, float* dense, int32_t nb, int32_t d0, int32_t d1, int32_t d2,
                          void* stream);
 
+/* ---- a12: dense coarse U-Net layers (model.py:89-136,152-166: nn.Conv3d / nn.ConvTranspose3d + BatchNorm3d + ReLU).
+ * NCDHW fp32; the input is the channel concatenation of in0 [nb,c0,d0,d1,d2] and (optional) in1 [nb,c1,...]
+ * (torch.cat of model.py:156,160).  conv3d weight [cout][c0+c1][k][k][k]; convT3d weight [c0+c1][cout][k][k][k]
+ * (PyTorch layouts).  out [nb,cout,o0,o1,o2] with the usual output sizes.  Fixed order: ci ascending, then
+ * kz,ky,kx ascending, one fmaf chain; optional folded BatchNorm (scale, shift per cout) and relu. */
+int sgnn_dense_conv3d(const float* in0, int32_t c0, const float* in1, int32_t c1, int32_t nb, int32_t d0,
+                      int32_t d1, int32_t d2, const float* w, int32_t cout, int32_t ksize, int32_t stride,
+                      int32_t pad, const float* scale, const float* shift, int32_t relu, float* out, void* stream);
+int sgnn_dense_convT3d(const float* in0, int32_t c0, const float* in1, int32_t c1, int32_t nb, int32_t d0,
+                       int32_t d1, int32_t d2, const float* w, int32_t cout, int32_t ksize, int32_t stride,
+                       int32_t pad, const float* scale, const float* shift, int32_t relu, float* out, void* stream);
+
 /* ---- a8: GenModel.dense_coarse_to_sparse (model.py:315-336).
  * dense_feats dev [nb,c,d0,d1,d2]; dense_out dev [nb,2,d0,d1,d2] (occ logit, sdf).
  * keep = sigmoid(occ) > 0.5 evaluated literally in fp32.  Kept cells are compacted in raster order:

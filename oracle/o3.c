@@ -95,3 +95,42 @@ void o3_sigmoid_gt_half(const float* x, int64_t n, uint8_t* out) {
     out[i] = s > 0.5f ? 1 : 0;
   }
 }
+
+/* Dense coarse U-Net layers (model.py:89-136,152-166), NCDHW, fixed order: ci asc, then kz,ky,kx asc.
+ * transposed == 0: nn.Conv3d, weight [cout][cin][k][k][k]; transposed == 1: nn.ConvTranspose3d, weight
+ * [cin][cout][k][k][k].  Optional folded BatchNorm3d (scale, shift) and relu. */
+void o3_dense_conv(int transposed, const float* in, int cin, int nb, int d0, int d1, int d2, const float* w,
+                   int cout, int ks, int stride, int pad, const float* scale, const float* shift, int relu,
+                   float* out, int o0, int o1, int o2) {
+  int64_t ivol = (int64_t)d0 * d1 * d2, ovol = (int64_t)o0 * o1 * o2;
+  int k3 = ks * ks * ks;
+  for (int b = 0; b < nb; ++b)
+    for (int co = 0; co < cout; ++co)
+      for (int z = 0; z < o0; ++z)
+        for (int y = 0; y < o1; ++y)
+          for (int x = 0; x < o2; ++x) {
+            float acc = 0.0f;
+            for (int ci = 0; ci < cin; ++ci) {
+              const float* src = in + ((int64_t)b * cin + ci) * ivol;
+              const float* wk = transposed ? w + ((int64_t)ci * cout + co) * k3 : w + ((int64_t)co * cin + ci) * k3;
+              for (int kz = 0; kz < ks; ++kz)
+                for (int ky = 0; ky < ks; ++ky)
+                  for (int kx = 0; kx < ks; ++kx) {
+                    int iz, iy, ix;
+                    if (!transposed) {
+                      iz = z * stride - pad + kz; iy = y * stride - pad + ky; ix = x * stride - pad + kx;
+                    } else {
+                      int tz = z + pad - kz, ty = y + pad - ky, tx = x + pad - kx;
+                      if (tz < 0 || ty < 0 || tx < 0 || tz % stride || ty % stride || tx % stride) continue;
+                      iz = tz / stride; iy = ty / stride; ix = tx / stride;
+                    }
+                    if (iz < 0 || iy < 0 || ix < 0 || iz >= d0 || iy >= d1 || ix >= d2) continue;
+                    acc = fmaf(src[((int64_t)iz * d1 + iy) * d2 + ix], wk[(kz * ks + ky) * ks + kx], acc);
+                  }
+            }
+            float v = acc;
+            if (scale) v = fmaf(v, scale[co], shift[co]);
+            if (relu) v = v > 0.0f ? v : 0.0f;
+            out[(((int64_t)b * cout + co) * o0 + z) * o1 * o2 + (int64_t)y * o2 + x] = v;
+          }
+}

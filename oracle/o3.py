@@ -81,3 +81,21 @@ def sigmoid_gt_half(x):
     out = torch.empty(x.shape[0], dtype=torch.uint8)
     lib().o3_sigmoid_gt_half(_p(x), C.c_int64(x.shape[0]), _p(out))
     return out.bool()
+
+
+def dense_conv(x, weight, ksize, stride, pad, scale=None, shift=None, relu=False, transposed=False):
+    x = x.contiguous().float()
+    weight = weight.contiguous().float()
+    nb, cin, d0, d1, d2 = x.shape
+    cout = weight.shape[1] if transposed else weight.shape[0]
+    if transposed:
+        o = [(d - 1) * stride - 2 * pad + ksize for d in (d0, d1, d2)]
+    else:
+        o = [(d + 2 * pad - ksize) // stride + 1 for d in (d0, d1, d2)]
+    out = torch.empty((nb, cout, o[0], o[1], o[2]), dtype=torch.float32)
+    lib().o3_dense_conv(C.c_int(1 if transposed else 0), _p(x), C.c_int(cin), C.c_int(nb), C.c_int(d0), C.c_int(d1),
+                        C.c_int(d2), _p(weight), C.c_int(cout), C.c_int(ksize), C.c_int(stride), C.c_int(pad),
+                        _p(scale.contiguous().float() if scale is not None else None),
+                        _p(shift.contiguous().float() if shift is not None else None), C.c_int(1 if relu else 0),
+                        _p(out), C.c_int(o[0]), C.c_int(o[1]), C.c_int(o[2]))
+    return out

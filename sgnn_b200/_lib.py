@@ -56,6 +56,8 @@ SIGNATURES = {
     'sgnn_copy_cols': (_I, [_P, _I, _P, _I, _L, _I, _P]),
     'sgnn_linear': (_I, [_P, _I, _P, _P, _P, _I, _L, _I, _I, _P]),
     'sgnn_sparse_to_dense': (_I, [_P, _I, _P, _L, _I, _P, _I, _I, _I, _I, _P]),
+    'sgnn_dense_conv3d': (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
+    'sgnn_dense_convT3d': (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
     'sgnn_dense_to_sparse': (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _Z, _P]),
     'sgnn_heads_compact': (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _P, _P, _Z, _P]),
     'sgnn_children_coords': (_I, [_P, _L, _P, _P]),

@@ -1,0 +1,187 @@
+// dense.cu -- the coarse dense U-Net of the SG-NN encoder (reference torch/model.py:89-136,152-166; SURVEY §8
+// row a12) as direct convolutions with a SPECIFIED summation order, so the whole generator is bit-reproducible
+// (cuDNN picks algorithms per shape/batch and cost ~3.8 ms per step for 32 8^3 volumes -- 17 % of the step).
+// The volumes are tiny (8^3 .. 2^3 per block): one thread per output element, weights broadcast within a warp
+// (consecutive threads = consecutive x of the same output channel), inputs served by L1.
+//   conv3d : out[b,co,o] = sum_{ci asc} sum_{kz,ky,kx asc} in[b,ci,o*s-p+k] * w[co,ci,k]        (nn.Conv3d)
+//   convT3d: out[b,co,o] = sum_{ci asc} sum_{kz,ky,kx asc, (o+p-k)%s==0} in[b,ci,(o+p-k)/s] * w[ci,co,k] (nn.ConvTranspose3d)
+// one fmaf chain from +0, then optional y = fmaf(y, scale[co], shift[co]) (eval BatchNorm3d folded on the host)
+// and relu.  The input may be the channel concatenation of two tensors (torch.cat of model.py:156,160).
+#include "common.cuh"
+
+struct DenseArgs {
+  const float* in0; int c0;
+  const float* in1; int c1;
+  int nb, d0, d1, d2;      // input extent
+  int o0, o1, o2;          // output extent
+  const float* w; int cout;
+  int ks, stride, pad;
+  const float* scale; const float* shift; int relu;
+  float* out;
+};
+
+__device__ __forceinline__ const float* dense_chan(const DenseArgs& a, int b, int ci, long long vol) {
+  return ci < a.c0 ? a.in0 + ((long long)b * a.c0 + ci) * vol
+                   : a.in1 + ((long long)b * a.c1 + (ci - a.c0)) * vol;
+}
+
+__global__ void __launch_bounds__(128)
+dense_conv3d_kernel(DenseArgs a) {
+  const long long ovol = (long long)a.o0 * a.o1 * a.o2, ivol = (long long)a.d0 * a.d1 * a.d2;
+  const long long total = (long long)a.nb * a.cout * ovol;
+  const int cin = a.c0 + a.c1, k3 = a.ks * a.ks * a.ks;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % a.o2), y = (int)((idx / a.o2) % a.o1), z = (int)((idx / ((long long)a.o1 * a.o2)) % a.o0);
+    const int co = (int)((idx / ovol) % a.cout), b = (int)(idx / (ovol * a.cout));
+    const int z0 = z * a.stride - a.pad, y0 = y * a.stride - a.pad, x0 = x * a.stride - a.pad;
+    float acc = 0.f;
+    for (int ci = 0; ci < cin; ++ci) {
+      const float* src = dense_chan(a, b, ci, ivol);
+      const float* wk = a.w + ((long long)co * cin + ci) * k3;
+      for (int kz = 0; kz < a.ks; ++kz) {
+        const int iz = z0 + kz;
+        if ((unsigned)iz >= (unsigned)a.d0) continue;
+        for (int ky = 0; ky < a.ks; ++ky) {
+          const int iy = y0 + ky;
+          if ((unsigned)iy >= (unsigned)a.d1) continue;
+          const float* row = src + ((long long)iz * a.d1 + iy) * a.d2;
+          const float* wr = wk + (kz * a.ks + ky) * a.ks;
+          for (int kx = 0; kx < a.ks; ++kx) {
+            const int ix = x0 + kx;
+            if ((unsigned)ix < (unsigned)a.d2) acc = fmaf(__ldg(row + ix), __ldg(wr + kx), acc);
+          }
+        }
+      }
+    }
+    float v = acc;
+    if (a.scale) v = fmaf(v, __ldg(a.scale + co), __ldg(a.shift + co));
+    if (a.relu) v = fmaxf(v, 0.f);
+    a.out[idx] = v;
+  }
+}
+
+// Transposed convolution: per axis only the taps k == (o + pad) (mod stride) reach an input cell; they are
+// enumerated once per output element (at most 4 per axis), so the channel loop runs over live taps only.
+// Order of the live taps is kz, ky, kx ascending -- the order of the full loop with the dead taps removed.
+__global__ void __launch_bounds__(128)
+dense_convT3d_kernel(DenseArgs a) {
+  const long long ovol = (long long)a.o0 * a.o1 * a.o2, ivol = (long long)a.d0 * a.d1 * a.d2;
+  const long long total = (long long)a.nb * a.cout * ovol;
+  const int cin = a.c0 + a.c1, k2 = a.ks * a.ks, k3 = k2 * a.ks;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % a.o2), y = (int)((idx / a.o2) % a.o1), z = (int)((idx / ((long long)a.o1 * a.o2)) % a.o0);
+    const int co = (int)((idx / ovol) % a.cout), b = (int)(idx / (ovol * a.cout));
+    int kzs[4], izs[4], kys[4], iys[4], kxs[4], ixs[4];
+    int nz = 0, ny = 0, nx = 0;
+    for (int k = 0; k < a.ks; ++k) {
+      int t = z + a.pad - k;
+      if (t >= 0 && t % a.stride == 0 && t / a.stride < a.d0 && nz < 4) { kzs[nz] = k; izs[nz++] = t / a.stride; }
+      t = y + a.pad - k;
+      if (t >= 0 && t % a.stride == 0 && t / a.stride < a.d1 && ny < 4) { kys[ny] = k; iys[ny++] = t / a.stride; }
+      t = x + a.pad - k;
+      if (t >= 0 && t % a.stride == 0 && t / a.stride < a.d2 && nx < 4) { kxs[nx] = k; ixs[nx++] = t / a.stride; }
+    }
+    float acc = 0.f;
+    for (int ci = 0; ci < cin; ++ci) {
+      const float* src = dense_chan(a, b, ci, ivol);
+      const float* wk = a.w + ((long long)ci * a.cout + co) * k3;
+#pragma unroll 2
+      for (int iz = 0; iz < nz; ++iz) {
+#pragma unroll 2
+        for (int iy = 0; iy < ny; ++iy) {
+          const float* row = src + ((long long)izs[iz] * a.d1 + iys[iy]) * a.d2;
+          const float* wr = wk + kzs[iz] * k2 + kys[iy] * a.ks;
+#pragma unroll 2
+          for (int ix = 0; ix < nx; ++ix) acc = fmaf(__ldg(row + ixs[ix]), __ldg(wr + kxs[ix]), acc);
+        }
+      }
+    }
+    float v = acc;
+    if (a.scale) v = fmaf(v, __ldg(a.scale + co), __ldg(a.shift + co));
+    if (a.relu) v = fmaxf(v, 0.f);
+    a.out[idx] = v;
+  }
+}
+
+// Fast path of the two decoder layers (model.py:112,121): kernel 4, stride 2, padding 1 -> exactly two taps per
+// axis, k in {(o+1)&1, ((o+1)&1)+2}, everything in registers.  Same tap order as the general kernel.
+__global__ void __launch_bounds__(128)
+dense_convT3d_k4s2p1_kernel(DenseArgs a) {
+  const long long ovol = (long long)a.o0 * a.o1 * a.o2, ivol = (long long)a.d0 * a.d1 * a.d2;
+  const long long total = (long long)a.nb * a.cout * ovol;
+  const int cin = a.c0 + a.c1;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % a.o2), y = (int)((idx / a.o2) % a.o1), z = (int)((idx / ((long long)a.o1 * a.o2)) % a.o0);
+    const int co = (int)((idx / ovol) % a.cout), b = (int)(idx / (ovol * a.cout));
+    const int kz0 = (z + 1) & 1, ky0 = (y + 1) & 1, kx0 = (x + 1) & 1;
+    int off[8], wof[8];
+    bool ok[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int kz = kz0 + 2 * (t >> 2), ky = ky0 + 2 * ((t >> 1) & 1), kx = kx0 + 2 * (t & 1);
+      const int tz = z + 1 - kz, ty = y + 1 - ky, tx = x + 1 - kx;
+      const int iz = tz >> 1, iy = ty >> 1, ix = tx >> 1;
+      ok[t] = tz >= 0 && ty >= 0 && tx >= 0 && iz < a.d0 && iy < a.d1 && ix < a.d2;
+      off[t] = (iz * a.d1 + iy) * a.d2 + ix;
+      wof[t] = (kz * 4 + ky) * 4 + kx;
+    }
+    float acc = 0.f;
+    for (int ci = 0; ci < cin; ++ci) {
+      const float* src = dense_chan(a, b, ci, ivol);
+      const float* wk = a.w + ((long long)ci * a.cout + co) * 64;
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        if (ok[t]) acc = fmaf(__ldg(src + off[t]), __ldg(wk + wof[t]), acc);
+    }
+    float v = acc;
+    if (a.scale) v = fmaf(v, __ldg(a.scale + co), __ldg(a.shift + co));
+    if (a.relu) v = fmaxf(v, 0.f);
+    a.out[idx] = v;
+  }
+}
+
+static int dense_launch(bool transposed, const float* in0, int c0, const float* in1, int c1, int nb, int d0, int d1,
+                        int d2, const float* w, int cout, int ks, int stride, int pad, const float* scale,
+                        const float* shift, int relu, float* out, void* stream) {
+  if (nb < 0 || c0 <= 0 || c1 < 0 || d0 <= 0 || d1 <= 0 || d2 <= 0 || cout <= 0 || ks <= 0 || stride <= 0 ||
+      pad < 0 || !in0 || (c1 > 0 && !in1) || !w || !out || (scale == nullptr) != (shift == nullptr))
+    return SGNN_E_INVALID;
+  DenseArgs a;
+  a.in0 = in0; a.c0 = c0; a.in1 = in1; a.c1 = c1; a.nb = nb; a.d0 = d0; a.d1 = d1; a.d2 = d2;
+  if (!transposed) {
+    a.o0 = (d0 + 2 * pad - ks) / stride + 1; a.o1 = (d1 + 2 * pad - ks) / stride + 1; a.o2 = (d2 + 2 * pad - ks) / stride + 1;
+  } else {
+    a.o0 = (d0 - 1) * stride - 2 * pad + ks; a.o1 = (d1 - 1) * stride - 2 * pad + ks; a.o2 = (d2 - 1) * stride - 2 * pad + ks;
+  }
+  if (a.o0 <= 0 || a.o1 <= 0 || a.o2 <= 0) return SGNN_E_INVALID;
+  if (transposed && (ks + stride - 1) / stride > 4) return SGNN_E_UNSUPPORTED;
+  a.w = w; a.cout = cout; a.ks = ks; a.stride = stride; a.pad = pad; a.scale = scale; a.shift = shift; a.relu = relu;
+  a.out = out;
+  const long long total = (long long)nb * cout * a.o0 * a.o1 * a.o2;
+  if (total == 0) return SGNN_OK;
+  const int blocks = sgnn_blocks(total, 128, (int64_t)148 * 32);
+  if (transposed && ks == 4 && stride == 2 && pad == 1) dense_convT3d_k4s2p1_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a);
+  else if (transposed) dense_convT3d_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a);
+  else dense_conv3d_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+extern "C" int sgnn_dense_conv3d(const float* in0, int32_t c0, const float* in1, int32_t c1, int32_t nb, int32_t d0,
+                                 int32_t d1, int32_t d2, const float* w, int32_t cout, int32_t ksize, int32_t stride,
+                                 int32_t pad, const float* scale, const float* shift, int32_t relu, float* out,
+                                 void* stream) {
+  return dense_launch(false, in0, c0, in1, c1, nb, d0, d1, d2, w, cout, ksize, stride, pad, scale, shift, relu, out,
+                      stream);
+}
+
+extern "C" int sgnn_dense_convT3d(const float* in0, int32_t c0, const float* in1, int32_t c1, int32_t nb, int32_t d0,
+                                  int32_t d1, int32_t d2, const float* w, int32_t cout, int32_t ksize, int32_t stride,
+                                  int32_t pad, const float* scale, const float* shift, int32_t relu, float* out,
+                                  void* stream) {
+  return dense_launch(true, in0, c0, in1, c1, nb, d0, d1, d2, w, cout, ksize, stride, pad, scale, shift, relu, out,
+                      stream);
+}

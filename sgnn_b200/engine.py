@@ -11,7 +11,7 @@ from ._lib import lib, check, SgnnGrid, SgnnEpilogue, SgnnConvArgs
 __all__ = ['Grid', 'build_grid', 'coarsen', 'rulebook_submanifold', 'rulebook_strided',
            'conv', 'deconv', 'unpool', 'affine_relu', 'add_rows', 'copy_cols', 'linear',
            'sparse_to_dense', 'dense_to_sparse', 'heads_compact', 'children_coords',
-           'concat_skip', 'coords_to_i64', 'grid_lookup', 'fold_bn']
+           'concat_skip', 'coords_to_i64', 'grid_lookup', 'fold_bn', 'dense_conv']
 
 
 def _stream():
@@ -314,6 +314,28 @@ def coords_to_i64(coords):
     _need_cuda(coords)
     out = torch.empty(coords.shape, dtype=torch.int64, device=coords.device)
     check(lib.sgnn_coords_to_i64(_ptr(coords), coords.shape[0], _ptr(out), _stream()), 'sgnn_coords_to_i64')
+    return out
+
+
+def dense_conv(x0, x1, weight, cout, ksize, stride, pad, scale=None, shift=None, relu=False, transposed=False):
+    """a12: nn.Conv3d / nn.ConvTranspose3d (+ folded BatchNorm3d + ReLU) on NCDHW volumes; x1 (optional) is
+    concatenated behind x0 along channels without materialising the cat."""
+    _need_cuda(x0, x1, weight, scale, shift)
+    assert x0.is_contiguous() and x0.dtype == torch.float32 and weight.is_contiguous()
+    nb, c0, d0, d1, d2 = x0.shape
+    c1 = 0
+    if x1 is not None:
+        assert x1.is_contiguous() and x1.shape[0] == nb and tuple(x1.shape[2:]) == (d0, d1, d2)
+        c1 = x1.shape[1]
+    if transposed:
+        o = [(d - 1) * stride - 2 * pad + ksize for d in (d0, d1, d2)]
+        fn = lib.sgnn_dense_convT3d
+    else:
+        o = [(d + 2 * pad - ksize) // stride + 1 for d in (d0, d1, d2)]
+        fn = lib.sgnn_dense_conv3d
+    out = torch.empty((nb, cout, o[0], o[1], o[2]), dtype=torch.float32, device=x0.device)
+    check(fn(_ptr(x0), c0, _ptr(x1), c1, nb, d0, d1, d2, _ptr(weight), cout, ksize, stride, pad, _ptr(scale),
+             _ptr(shift), 1 if relu else 0, _ptr(out), _stream()), 'sgnn_dense_conv')
     return out
 
 

@@ -12,7 +12,8 @@ Two forward paths over the same parameters:
   * forward() = forward_fused(): same arithmetic (bit-identical results), but BatchNormReLU / residual add /
     channel concat are folded into convolution epilogues, the x8 child replication of model.py:202 is never
     materialised (child-mode convolution), and per-resolution grids/rulebooks are shared.
-The dense 8^3 U-Net (model.py:89-136,152-166) stays on PyTorch/cuDNN, TF32 disabled.
+The dense 8^3 U-Net (model.py:89-136,152-166) runs on the engine's fixed-order direct convolutions (dense.cu),
+so the whole generator is bit-reproducible; nn.Conv3d / BatchNorm3d modules only hold the parameters.
 """
 import numpy as np
 import torch
@@ -100,14 +101,22 @@ class TSDFEncoder(nn.Module):
         self.sdfpred = nn.Sequential(nn.Conv3d(nf_out, 1, kernel_size=1, bias=b))
 
     def dense_unet(self, x):
-        """model.py:152-166 (library ops)."""
-        enc0 = self.encode_dense0(x)
-        enc1 = self.encode_dense1(enc0)
-        bott = self.bottleneck_dense2(enc1)
-        dec0 = self.decode_dense3(torch.cat([bott, enc1], 1) if self.use_skip_dense else bott)
-        x = self.decode_dense4(torch.cat([dec0, enc0], 1) if self.use_skip_dense else dec0)
-        x = self.final(x)
-        return x, torch.cat([self.occpred(x), self.sdfpred(x)], 1)
+        """model.py:152-166 on the engine's fixed-order direct convolutions: BatchNorm3d + ReLU
+        folded into each convolution, torch.cat of model.py:156,160 read in place from its two sources."""
+        def cbr(seq, x0, x1=None, transposed=False):
+            conv, bn = seq[0], seq[1]
+            s, t = E.fold_bn(bn)
+            k, st, pd = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+            return E.dense_conv(x0, x1, conv.weight.detach(), conv.out_channels, k, st, pd, s, t, True, transposed)
+        x = x.contiguous()
+        enc0 = cbr(self.encode_dense0, x)
+        enc1 = cbr(self.encode_dense1, enc0)
+        bott = cbr(self.bottleneck_dense2, enc1)
+        dec0 = cbr(self.decode_dense3, bott, enc1 if self.use_skip_dense else None, True)
+        x = cbr(self.decode_dense4, dec0, enc0 if self.use_skip_dense else None, True)
+        x = cbr(self.final, x)
+        w2 = torch.cat([self.occpred[0].weight.detach(), self.sdfpred[0].weight.detach()], 0).contiguous()
+        return x, E.dense_conv(x, None, w2, 2, 1, 1, 0)
 
     def forward(self, x):
         skips = []

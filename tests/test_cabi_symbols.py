@@ -9,7 +9,7 @@ from conftest import ROOT
 def _header_functions():
     src = open(os.path.join(ROOT, 'include', 'sgnn_b200.h')).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
-    return sorted(set(re.findall(r'\b(sgnn_[a-z0-9_]+)\s*\(', src)))
+    return sorted(set(re.findall(r'\b(sgnn_[A-Za-z0-9_]+)\s*\(', src)))
 
 
 def test_every_declared_symbol_is_exported_and_bound():
@@ -18,7 +18,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert len(names) >= 20
     assert sorted(_lib.SIGNATURES) == names
     out = subprocess.check_output(['nm', '-D', '--defined-only', _lib.LIB_PATH]).decode()
-    exported = set(re.findall(r' T (sgnn_[a-z0-9_]+)', out))
+    exported = set(re.findall(r' T (sgnn_[A-Za-z0-9_]+)', out))
     assert set(names) <= exported
     for n in names:
         assert getattr(_lib.lib, n) is not None

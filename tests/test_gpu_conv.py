@@ -210,3 +210,30 @@ def test_error_codes():
         E.conv(x, nbr[:5], w[:5].contiguous(), 10, torch.empty((10, 16), device='cuda'))
     with pytest.raises(RuntimeError):
         E.conv(x.cpu(), nbr, w, 10, torch.empty((10, 16), device='cuda'))
+
+
+@pytest.mark.parametrize('transposed,c0,c1,cout,k,s,p,dims', [
+    (False, 16, 0, 24, 4, 2, 1, (8, 8, 8)), (False, 24, 0, 32, 4, 2, 1, (4, 4, 4)), (False, 32, 0, 32, 1, 1, 0, (2, 2, 2)),
+    (True, 32, 32, 32, 4, 2, 1, (2, 2, 2)), (True, 32, 24, 28, 4, 2, 1, (4, 6, 4)), (False, 28, 0, 16, 1, 1, 0, (8, 4, 8)),
+    (False, 16, 0, 2, 1, 1, 0, (8, 8, 8)),
+])
+def test_dense_unet_layers_bit_exact(transposed, c0, c1, cout, k, s, p, dims):
+    """a12: the coarse dense U-Net layers (model.py:89-136) -- bit-exact vs O3, 1e-5 vs torch."""
+    E = _E()
+    torch.manual_seed(c0 + cout)
+    nb = 3
+    x0 = torch.randn(nb, c0, *dims)
+    x1 = torch.randn(nb, c1, *dims) if c1 else None
+    cin = c0 + c1
+    w = torch.randn((cin, cout, k, k, k) if transposed else (cout, cin, k, k, k)) * 0.05
+    sc, sh = torch.rand(cout) + 0.5, torch.rand(cout) - 0.5
+    xcat = torch.cat([x0, x1], 1) if c1 else x0
+    want = o3.dense_conv(xcat, w, k, s, p, sc, sh, True, transposed)
+    got = E.dense_conv(x0.cuda(), x1.cuda() if c1 else None, w.cuda(), cout, k, s, p, sc.cuda(), sh.cuda(), True,
+                       transposed)
+    assert torch.equal(got.cpu(), want)
+    fn = torch.nn.functional.conv_transpose3d if transposed else torch.nn.functional.conv3d
+    ref = torch.relu(fn(xcat, w, stride=s, padding=p) * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1))
+    assert torch.allclose(got.cpu(), ref, atol=2e-5, rtol=1e-5)
+    raw = E.dense_conv(x0.cuda(), x1.cuda() if c1 else None, w.cuda(), cout, k, s, p, transposed=transposed)
+    assert torch.equal(raw.cpu(), o3.dense_conv(xcat, w, k, s, p, transposed=transposed))

@@ -73,3 +73,27 @@ def test_sigmoid_threshold_literal():
     assert torch.equal(o3.sigmoid_gt_half(x), torch.sigmoid(x) > 0.5)
     xs = torch.from_numpy(np.random.default_rng(0).standard_normal(100000).astype(np.float32) * 1e-7)
     assert torch.equal(o3.sigmoid_gt_half(xs), torch.sigmoid(xs) > 0.5)
+
+
+@pytest.mark.parametrize('transposed,cin,cout,k,s,p,dims', [
+    (False, 16, 24, 4, 2, 1, (8, 8, 8)), (False, 24, 32, 4, 2, 1, (4, 4, 4)), (False, 32, 32, 1, 1, 0, (2, 2, 2)),
+    (True, 64, 32, 4, 2, 1, (2, 2, 2)), (True, 56, 28, 4, 2, 1, (4, 6, 4)), (False, 28, 16, 1, 1, 0, (8, 4, 8)),
+])
+def test_o3_dense_layers_match_torch(transposed, cin, cout, k, s, p, dims):
+    torch.manual_seed(cin + cout)
+    x = torch.randn(2, cin, *dims)
+    if transposed:
+        m = torch.nn.ConvTranspose3d(cin, cout, k, s, p, bias=False)
+    else:
+        m = torch.nn.Conv3d(cin, cout, k, s, p, bias=False)
+    bn = torch.nn.BatchNorm3d(cout).eval()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5), bn.bias.uniform_(-0.3, 0.3)
+        bn.running_mean.uniform_(-0.3, 0.3), bn.running_var.uniform_(0.5, 1.5)
+        want = torch.relu(bn(m(x)))
+        inv = (bn.running_var + bn.eps).pow(-0.5)
+        scale = inv * bn.weight
+        shift = bn.bias - bn.running_mean * scale
+        got = o3.dense_conv(x, m.weight, k, s, p, scale, shift, True, transposed)
+    assert got.shape == want.shape
+    assert torch.allclose(got, want, atol=2e-5, rtol=1e-5)
