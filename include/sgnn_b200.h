@@ -39,7 +39,8 @@ enum {
   SGNN_E_CUDA = -2,        /* a CUDA runtime call failed; sgnn_last_cuda_error() has the code */
   SGNN_E_TOO_LARGE = -3,   /* extent or row count exceeds the 2^31-1 indexing of this build */
   SGNN_E_UNSUPPORTED = -4, /* valid in scn, not implemented here (e.g. filter size other than 3 / 2) */
-  SGNN_E_ALIGN = -5        /* pointer / leading dimension breaks an alignment rule stated below */
+  SGNN_E_ALIGN = -5,       /* pointer / leading dimension breaks an alignment rule stated below */
+  SGNN_E_NOMEM = -6        /* caller-provided workspace arena too small */
 };
 
 enum { SGNN_F32 = 0, SGNN_BF16 = 1 };
@@ -209,6 +210,71 @@ int sgnn_heads_compact(const float* x, int32_t ld_x, int32_t c, const float* w_o
                        const int32_t* parent_coords, int64_t n_parent, float* cand_out,
                        int32_t* locs, float* feats, int32_t ld_feats, int32_t* count,
                        void* scratch, size_t scratch_bytes, void* stream);
+
+/* Two-phase forms of the two compactions: phase 1 computes (occ, sdf), the literal sigmoid mask and its exclusive
+ * scan -- offs[n] is the kept count, readable with one 4-byte copy -- phase 2 writes exactly that many rows.
+ * flags dev [n] uint8, offs dev [n+1] int32, scratch >= sgnn_scan_scratch_bytes(n). */
+int sgnn_heads_flags(const float* x, int32_t ld_x, int32_t c, const float* w_occ, const float* b_occ,
+                     const float* w_sdf, const float* b_sdf, int64_t n_cand, float* cand_out, uint8_t* flags,
+                     int32_t* offs, void* scratch, size_t scratch_bytes, void* stream);
+int sgnn_heads_write(const float* x, int32_t ld_x, int32_t c, const float* cand_out,
+                     const int32_t* parent_coords, int64_t n_cand, const uint8_t* flags, const int32_t* offs,
+                     int32_t* locs, float* feats, int32_t ld_feats, void* stream);
+int sgnn_dense_flags(const float* dense_out, int32_t nb, int64_t vol, float* cand_out, uint8_t* flags,
+                     int32_t* offs, void* scratch, size_t scratch_bytes, void* stream);
+int sgnn_dense_write(const float* dense_feats, const float* dense_out, int32_t nb, int32_t c, int32_t d0,
+                     int32_t d1, int32_t d2, const uint8_t* flags, const int32_t* offs, int32_t* locs,
+                     float* feats, int32_t ld_feats, void* stream);
+
+/* ---- the whole generator in one native call: GenModel.forward of model.py:371-416 with the default SG-NN
+ * structure (test_scene.py:29-39: 3 sparse encoder levels, dense U-Net, 3 refinement levels, surface head,
+ * pass_occ + pass_feats, sparse + dense skips).  Host orchestration (site sets, rulebooks, fused convolutions,
+ * dense U-Net, generative upsampling) runs in C++ on `stream`; the only host<->device traffic is one 4-byte read
+ * per data-dependent row count.  All weights are device pointers in the layouts of the individual calls above;
+ * BatchNorm layers are passed folded (scale, shift).  Everything the call produces lives in the caller's `arena`
+ * (device memory); on SGNN_E_NOMEM out->arena_needed is a size that suffices for a retry. */
+typedef struct SgnnBnFold { const float* scale; const float* shift; } SgnnBnFold;
+typedef struct SgnnResBlockW {      /* ConcatTable(Identity, Seq(BNReLU, SMC, BNReLU, SMC)) + AddTable */
+  SgnnBnFold bn0; const float* w0; SgnnBnFold bn1; const float* w1;
+} SgnnResBlockW;
+typedef struct SgnnEncLevelW {      /* SparseEncoderLayer, model.py:21-67 */
+  int32_t cin, c;
+  const float* w_in; SgnnResBlockW res; SgnnBnFold bn_out; const float* w_down; SgnnBnFold bn_down;
+} SgnnEncLevelW;
+typedef struct SgnnFcnW {           /* FullyConvolutionalNet(reps 1, [c,c,c], residual) + BatchNormReLU(3c) */
+  int32_t c, reserved;
+  SgnnResBlockW blk[3]; SgnnBnFold bn_down[2]; const float* w_down[2]; SgnnBnFold bn_join;
+} SgnnFcnW;
+typedef struct SgnnDenseLayerW {    /* Conv3d / ConvTranspose3d + BatchNorm3d + ReLU, model.py:89-129 */
+  const float* w; SgnnBnFold bn; int32_t cout, ksize, stride, pad, transposed, cat_with; /* cat_with: -1 or layer idx */
+} SgnnDenseLayerW;
+typedef struct SgnnRefineW {        /* Refinement, model.py:169-247 */
+  int32_t cin, c;
+  const float* w_in; SgnnFcnW fcn; const float* w_up; SgnnBnFold bn_up;
+  const float* w_occ; const float* b_occ; const float* w_sdf; const float* b_sdf;
+} SgnnRefineW;
+typedef struct SgnnSurfaceW {       /* SurfacePrediction, model.py:249-272 */
+  int32_t cin, c;
+  const float* w_in; SgnnFcnW fcn; const float* w_lin; const float* b_lin;
+} SgnnSurfaceW;
+typedef struct SgnnGeneratorW {
+  SgnnEncLevelW enc[3];
+  SgnnDenseLayerW dense[6];         /* encode0, encode1, bottleneck, decode3 (cat enc1), decode4 (cat enc0), final */
+  const float* w_heads;             /* [2][nf_coarse]: occpred, sdfpred (1x1x1, no bias) */
+  int32_t nf_coarse, reserved;
+  SgnnRefineW ref[3];
+  SgnnSurfaceW surf;
+} SgnnGeneratorW;
+typedef struct SgnnGeneratorOut {
+  int64_t n_out;        int32_t* out_locs;  float* out_sdf;        /* [n_out,4], [n_out,1] */
+  int64_t n_cand[4];    int32_t* cand_locs[4]; float* cand[4];     /* per level: [n,4] (if requested), [n,2] */
+  int64_t rows[16];     /* site counts: enc L0..L3, then per refinement/surface level its 3 FCN resolutions */
+  size_t arena_used, arena_needed;
+} SgnnGeneratorOut;
+#define SGNN_GEN_CAND_LOCS 1        /* materialise the candidate coordinates of every level (model.py:247,336) */
+int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coords, int coords_i64, const float* feats,
+                           int64_t n, int32_t nb, const int32_t* dims3, void* arena, size_t arena_bytes, int flags,
+                           SgnnGeneratorOut* out, void* stream);
 
 /* Candidate coordinates of model.py:192-207: out dev [8*n_parent,4]. */
 int sgnn_children_coords(const int32_t* parent_coords, int64_t n_parent, int32_t* out, void* stream);

@@ -35,6 +35,53 @@ class SgnnConvArgs(C.Structure):
                 ('a', SgnnEpilogue), ('b', SgnnEpilogue)]
 
 
+class SgnnBnFold(C.Structure):
+    _fields_ = [('scale', C.c_void_p), ('shift', C.c_void_p)]
+
+
+class SgnnResBlockW(C.Structure):
+    _fields_ = [('bn0', SgnnBnFold), ('w0', C.c_void_p), ('bn1', SgnnBnFold), ('w1', C.c_void_p)]
+
+
+class SgnnEncLevelW(C.Structure):
+    _fields_ = [('cin', C.c_int32), ('c', C.c_int32), ('w_in', C.c_void_p), ('res', SgnnResBlockW),
+                ('bn_out', SgnnBnFold), ('w_down', C.c_void_p), ('bn_down', SgnnBnFold)]
+
+
+class SgnnFcnW(C.Structure):
+    _fields_ = [('c', C.c_int32), ('reserved', C.c_int32), ('blk', SgnnResBlockW * 3), ('bn_down', SgnnBnFold * 2),
+                ('w_down', C.c_void_p * 2), ('bn_join', SgnnBnFold)]
+
+
+class SgnnDenseLayerW(C.Structure):
+    _fields_ = [('w', C.c_void_p), ('bn', SgnnBnFold), ('cout', C.c_int32), ('ksize', C.c_int32),
+                ('stride', C.c_int32), ('pad', C.c_int32), ('transposed', C.c_int32), ('cat_with', C.c_int32)]
+
+
+class SgnnRefineW(C.Structure):
+    _fields_ = [('cin', C.c_int32), ('c', C.c_int32), ('w_in', C.c_void_p), ('fcn', SgnnFcnW),
+                ('w_up', C.c_void_p), ('bn_up', SgnnBnFold), ('w_occ', C.c_void_p), ('b_occ', C.c_void_p),
+                ('w_sdf', C.c_void_p), ('b_sdf', C.c_void_p)]
+
+
+class SgnnSurfaceW(C.Structure):
+    _fields_ = [('cin', C.c_int32), ('c', C.c_int32), ('w_in', C.c_void_p), ('fcn', SgnnFcnW),
+                ('w_lin', C.c_void_p), ('b_lin', C.c_void_p)]
+
+
+class SgnnGeneratorW(C.Structure):
+    _fields_ = [('enc', SgnnEncLevelW * 3), ('dense', SgnnDenseLayerW * 6), ('w_heads', C.c_void_p),
+                ('nf_coarse', C.c_int32), ('reserved', C.c_int32), ('ref', SgnnRefineW * 3), ('surf', SgnnSurfaceW)]
+
+
+class SgnnGeneratorOut(C.Structure):
+    _fields_ = [('n_out', C.c_int64), ('out_locs', C.c_void_p), ('out_sdf', C.c_void_p),
+                ('n_cand', C.c_int64 * 4), ('cand_locs', C.c_void_p * 4), ('cand', C.c_void_p * 4),
+                ('rows', C.c_int64 * 16), ('arena_used', C.c_size_t), ('arena_needed', C.c_size_t)]
+
+
+GEN_CAND_LOCS = 1
+
 _P, _I, _L, _Z = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
 _G, _E = C.POINTER(SgnnGrid), C.POINTER(SgnnEpilogue)
 
@@ -60,6 +107,12 @@ SIGNATURES = {
     'sgnn_dense_convT3d': (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
     'sgnn_dense_to_sparse': (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _Z, _P]),
     'sgnn_heads_compact': (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _P, _P, _Z, _P]),
+    'sgnn_heads_flags': (_I, [_P, _I, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P, _Z, _P]),
+    'sgnn_heads_write': (_I, [_P, _I, _I, _P, _P, _L, _P, _P, _P, _P, _I, _P]),
+    'sgnn_dense_flags': (_I, [_P, _I, _L, _P, _P, _P, _P, _Z, _P]),
+    'sgnn_dense_write': (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
+    'sgnn_generator_forward': (_I, [C.POINTER(SgnnGeneratorW), _P, _I, _P, _L, _I, C.POINTER(C.c_int32), _P, _Z, _I,
+                                    C.POINTER(SgnnGeneratorOut), _P]),
     'sgnn_children_coords': (_I, [_P, _L, _P, _P]),
     'sgnn_concat_skip': (_I, [_G, _P, _I, _I, _P, _L, _P, _I, _I, _P]),
     'sgnn_coords_to_i64': (_I, [_P, _L, _P, _P]),

@@ -49,7 +49,7 @@ __global__ void d2s_write_kernel(const float* __restrict__ dense_feats, const fl
                                  int ld, int* __restrict__ count) {
   const long long vol = (long long)d0 * d1 * d2;
   const long long total = (long long)nb * vol;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *count = offs[total];
+  if (count && blockIdx.x == 0 && threadIdx.x == 0) *count = offs[total];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     if (!flags[i]) continue;
@@ -61,6 +61,7 @@ __global__ void d2s_write_kernel(const float* __restrict__ dense_feats, const fl
     f[0] = dense_out[(b * 2 + 0) * vol + cell];
     f[1] = dense_out[(b * 2 + 1) * vol + cell];
     for (int ch = 0; ch < c; ++ch) f[2 + ch] = dense_feats[(b * c + ch) * vol + cell];
+    for (int ch = c + 2; ch < ld; ++ch) f[ch] = 0.f;      // spare columns for the skip join
   }
 }
 
@@ -117,7 +118,7 @@ __global__ void heads_write_kernel(const float* __restrict__ x, int ld_x, int c,
                                    const unsigned char* __restrict__ flags, const int* __restrict__ offs,
                                    int* __restrict__ locs, float* __restrict__ feats, int ld,
                                    int* __restrict__ count) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) *count = offs[n_cand];
+  if (count && blockIdx.x == 0 && threadIdx.x == 0) *count = offs[n_cand];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_cand;
        i += (long long)gridDim.x * blockDim.x) {
     if (!flags[i]) continue;
@@ -132,6 +133,7 @@ __global__ void heads_write_kernel(const float* __restrict__ x, int ld_x, int c,
     const float2 os = reinterpret_cast<const float2*>(cand_out)[i];
     f[c] = os.x;
     f[c + 1] = os.y;
+    for (int ch = c + 2; ch < ld; ++ch) f[ch] = 0.f;       // spare columns for the skip join
   }
 }
 
@@ -160,6 +162,65 @@ extern "C" int sgnn_heads_compact(const float* x, int32_t ld_x, int32_t c, const
   if (rc) return rc;
   heads_write_kernel<<<sgnn_blocks(n_cand, 256), 256, 0, st>>>(x, ld_x, c, cand_out, parent_coords, n_cand,
                                                                cs.flags, cs.offs, locs, feats, ld_feats, count);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+
+// ------------------------------------------------------------ two-phase variants (count known before the write)
+// Phase 1 evaluates the heads / mask and scans; offs[n] is the kept count.  The caller reads it (one 4-byte D2H),
+// allocates exactly that many rows and calls phase 2.  Used by the native generator (generator.cu).
+extern "C" int sgnn_heads_flags(const float* x, int32_t ld_x, int32_t c, const float* w_occ, const float* b_occ,
+                                const float* w_sdf, const float* b_sdf, int64_t n_cand, float* cand_out,
+                                uint8_t* flags, int32_t* offs, void* scratch, size_t scratch_bytes, void* stream) {
+  if (n_cand < 0 || c <= 0 || !offs || !w_occ || !b_occ || !w_sdf || !b_sdf) return SGNN_E_INVALID;
+  if (n_cand > 0x7fffffffLL) return SGNN_E_TOO_LARGE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_cand > 0) {
+    if (!x || !cand_out || !flags) return SGNN_E_INVALID;
+    heads_flag_kernel<<<sgnn_blocks(n_cand, 256), 256, 0, st>>>(x, ld_x, c, w_occ, b_occ, w_sdf, b_sdf, n_cand, flags,
+                                                                cand_out);
+    SGNN_CHECK_LAUNCH();
+  }
+  return sgnn_scan_exclusive(flags, SCAN_U8, offs, n_cand, scratch, scratch_bytes, st);
+}
+
+extern "C" int sgnn_heads_write(const float* x, int32_t ld_x, int32_t c, const float* cand_out,
+                                const int32_t* parent_coords, int64_t n_cand, const uint8_t* flags,
+                                const int32_t* offs, int32_t* locs, float* feats, int32_t ld_feats, void* stream) {
+  if (n_cand < 0 || c <= 0 || ld_feats < c + 2) return SGNN_E_INVALID;
+  if (n_cand == 0) return SGNN_OK;
+  if (!x || !cand_out || !parent_coords || !flags || !offs || !locs || !feats) return SGNN_E_INVALID;
+  heads_write_kernel<<<sgnn_blocks(n_cand, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, ld_x, c, cand_out, parent_coords, n_cand, flags, offs, locs, feats, ld_feats, nullptr);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+extern "C" int sgnn_dense_flags(const float* dense_out, int32_t nb, int64_t vol, float* cand_out, uint8_t* flags,
+                                int32_t* offs, void* scratch, size_t scratch_bytes, void* stream) {
+  if (nb < 0 || vol < 0 || !offs) return SGNN_E_INVALID;
+  const long long total = (long long)nb * vol;
+  if (total > 0x7fffffffLL) return SGNN_E_TOO_LARGE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (total > 0) {
+    if (!dense_out || !flags) return SGNN_E_INVALID;
+    d2s_flag_kernel<<<sgnn_blocks(total, 256), 256, 0, st>>>(dense_out, nb, vol, flags, cand_out);
+    SGNN_CHECK_LAUNCH();
+  }
+  return sgnn_scan_exclusive(flags, SCAN_U8, offs, total, scratch, scratch_bytes, st);
+}
+
+extern "C" int sgnn_dense_write(const float* dense_feats, const float* dense_out, int32_t nb, int32_t c, int32_t d0,
+                                int32_t d1, int32_t d2, const uint8_t* flags, const int32_t* offs, int32_t* locs,
+                                float* feats, int32_t ld_feats, void* stream) {
+  if (nb < 0 || c < 0 || ld_feats < c + 2) return SGNN_E_INVALID;
+  const long long total = (long long)nb * d0 * d1 * d2;
+  if (total == 0) return SGNN_OK;
+  if (!dense_feats || !dense_out || !flags || !offs || !locs || !feats) return SGNN_E_INVALID;
+  d2s_write_kernel<<<sgnn_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(dense_feats, dense_out, nb, c, d0, d1, d2,
+                                                                             flags, offs, locs, feats, ld_feats,
+                                                                             nullptr);
   SGNN_CHECK_LAUNCH();
   return SGNN_OK;
 }
@@ -205,6 +266,7 @@ extern "C" const char* sgnn_error_string(int code) {
     case SGNN_E_TOO_LARGE: return "extent or row count exceeds 2^31-1 indexing";
     case SGNN_E_UNSUPPORTED: return "unsupported configuration";
     case SGNN_E_ALIGN: return "pointer or leading dimension violates the 16-byte alignment rule";
+    case SGNN_E_NOMEM: return "workspace arena too small (SgnnGeneratorOut.arena_needed has the size to retry with)";
     default: return "unknown sgnn error code";
   }
 }

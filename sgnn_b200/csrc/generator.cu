@@ -1,0 +1,391 @@
+// generator.cu -- native (C++) orchestration of the whole SG-NN generator forward (reference torch/model.py:371-416)
+// on top of the kernels of this library.  The reference drives ~130 scn ops + Python glue per pass from Python
+// with CPU-side metadata; here one C-ABI call enqueues the ~190 kernels of a pass on one stream and touches the
+// host only to read the data-dependent row counts (4 bytes each: coarse site counts, kept-candidate counts).
+// Memory comes from a caller-provided bump arena (no cudaMalloc on the path); temporaries are released in
+// stream order.  The arithmetic is the fused composition of sgnn_b200/fused.py -- bit-identical to the
+// module-by-module path.
+#include <string.h>
+#include "common.cuh"
+
+namespace {
+
+struct Arena {
+  char* base;
+  size_t cap, off, high;
+  bool oom;
+  void* get(size_t bytes) {
+    size_t a = (off + 255) & ~(size_t)255;
+    size_t end = a + (bytes ? bytes : 1);
+    if (end > high) high = end;
+    if (end > cap) { oom = true; return nullptr; }
+    off = end;
+    return base + a;
+  }
+};
+
+struct Ctx {
+  Arena ar;
+  cudaStream_t st;
+  void* stream;
+};
+
+struct Epi {
+  float* out; int ld; const float* scale; const float* shift; int relu;
+};
+static Epi epi(float* out, int ld, const float* scale = nullptr, const float* shift = nullptr, int relu = 0) {
+  Epi e; e.out = out; e.ld = ld; e.scale = scale; e.shift = shift; e.relu = relu; return e;
+}
+static Epi epi_bn(float* out, int ld, const SgnnBnFold& bn, int off = 0) {
+  return epi(out, ld, bn.scale + off, bn.shift + off, 1);
+}
+static const Epi kNoEpi = {nullptr, 0, nullptr, nullptr, 0};
+
+struct Level {
+  SgnnGrid g;
+  int32_t* coords;
+  int32_t* nbr;
+  int64_t n;
+  int dims[3];
+};
+
+#define RC(call)            \
+  do {                      \
+    int rc__ = (call);      \
+    if (rc__) return rc__;  \
+  } while (0)
+#define ALLOC(var, type, count)                                   \
+  type* var = (type*)c.ar.get((size_t)(count) * sizeof(type));    \
+  if (!var) return SGNN_E_NOMEM
+
+static int read_i32(Ctx& c, const int32_t* dev, int32_t* host) {
+  SGNN_CUDA(cudaMemcpyAsync(host, dev, 4, cudaMemcpyDeviceToHost, c.st));
+  SGNN_CUDA(cudaStreamSynchronize(c.st));
+  return SGNN_OK;
+}
+
+static void grid_shape(SgnnGrid* g, int nb, const int dims[3]) {
+  memset(g, 0, sizeof(*g));
+  g->nb = nb; g->d0 = dims[0]; g->d1 = dims[1]; g->d2 = dims[2];
+  g->wx = (dims[2] + 63) / 64;
+  g->n_words = (int64_t)nb * dims[0] * dims[1] * g->wx;
+}
+
+// a1 + a2: site set from explicit coordinates, with its 27-neighbour table
+static int build_level(Ctx& c, const void* coords, int is64, int64_t n, int nb, const int dims[3], int32_t* status,
+                       Level* L) {
+  grid_shape(&L->g, nb, dims);
+  for (int i = 0; i < 3; ++i) L->dims[i] = dims[i];
+  L->n = n;
+  ALLOC(mask, uint64_t, L->g.n_words);
+  ALLOC(prefix, int32_t, L->g.n_words + 1);
+  ALLOC(ror, int32_t, n);
+  ALLOC(ci32, int32_t, n * 4);
+  L->g.mask = mask; L->g.prefix = prefix; L->g.row_of_rank = ror; L->coords = ci32;
+  const size_t mark = c.ar.off;
+  const size_t sb = sgnn_scan_scratch_bytes(L->g.n_words);
+  ALLOC(scr, char, sb);
+  RC(sgnn_grid_build(&L->g, coords, is64, n, ci32, status, scr, sb, c.stream));
+  c.ar.off = mark;
+  ALLOC(nbr, int32_t, 27 * n);
+  L->nbr = nbr;
+  return sgnn_rulebook_submanifold(&L->g, ci32, n, nbr, c.stream);
+}
+
+// a4: stride-2 coarse set of `f` (raster rows) + strided rulebook (+ its own 27-neighbour table)
+static int coarsen_level(Ctx& c, const Level& f, Level* L, int32_t** parent, int32_t** children, bool want_nbr) {
+  int dims[3];
+  for (int i = 0; i < 3; ++i) dims[i] = f.dims[i] >= 2 ? (f.dims[i] - 2) / 2 + 1 : 0;  // scn output size
+  grid_shape(&L->g, f.g.nb, dims);
+  for (int i = 0; i < 3; ++i) L->dims[i] = dims[i];
+  ALLOC(mask, uint64_t, L->g.n_words);
+  ALLOC(prefix, int32_t, L->g.n_words + 1);
+  L->g.mask = mask; L->g.prefix = prefix; L->g.row_of_rank = nullptr;
+  const size_t mark = c.ar.off;
+  const size_t sb = sgnn_scan_scratch_bytes(L->g.n_words);
+  ALLOC(scr, char, sb);
+  RC(sgnn_grid_coarsen(&f.g, &L->g, scr, sb, c.stream));
+  c.ar.off = mark;
+  int32_t cnt = 0;
+  RC(read_i32(c, prefix + L->g.n_words, &cnt));
+  L->n = cnt;
+  ALLOC(cc, int32_t, (int64_t)cnt * 4);
+  L->coords = cc;
+  if (cnt) RC(sgnn_grid_enumerate(&L->g, cc, c.stream));
+  ALLOC(par, int32_t, f.n);
+  ALLOC(chi, int32_t, (int64_t)cnt * 8);
+  *parent = par; *children = chi;
+  RC(sgnn_rulebook_strided(&L->g, f.coords, f.n, par, chi, cnt, c.stream));
+  L->nbr = nullptr;
+  if (want_nbr) {
+    ALLOC(nbr, int32_t, (int64_t)cnt * 27);
+    L->nbr = nbr;
+    RC(sgnn_rulebook_submanifold(&L->g, cc, cnt, nbr, c.stream));
+  }
+  return SGNN_OK;
+}
+
+static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr, int64_t nbr_stride, int K,
+                int child, const float* w, int cout, int64_t n_out, const float* res, int ld_res, const Epi& a,
+                const Epi& b) {
+  SgnnConvArgs x;
+  memset(&x, 0, sizeof(x));
+  x.in = in; x.ld_in = ld_in; x.dtype = SGNN_F32; x.nbr = nbr; x.nbr_stride = nbr_stride; x.K = K;
+  x.child_mode = child; x.weight = w; x.cin = cin; x.cout = cout; x.n_out = n_out; x.residual = res; x.ld_res = ld_res;
+  x.a.out = a.out; x.a.ld = a.ld; x.a.relu = a.relu; x.a.scale = a.scale; x.a.shift = a.shift;
+  x.b.out = b.out; x.b.ld = b.ld; x.b.relu = b.relu; x.b.scale = b.scale; x.b.shift = b.shift;
+  return sgnn_conv_forward(&x, c.stream);
+}
+
+// y = SMC(BNReLU(SMC(x_bn))) + x_raw   with x_bn = BNReLU_0(x_raw) supplied by the producer of x_raw
+static int res_block(Ctx& c, const Level& lv, const SgnnResBlockW& rb, int ch, const float* x_raw, const float* x_bn,
+                     const Epi& a, const Epi& b) {
+  ALLOC(mid, float, lv.n * ch);
+  RC(conv(c, x_bn, ch, ch, lv.nbr, lv.n, 27, 0, rb.w0, ch, lv.n, nullptr, 0, epi_bn(mid, ch, rb.bn1), kNoEpi));
+  return conv(c, mid, ch, ch, lv.nbr, lv.n, 27, 0, rb.w1, ch, lv.n, x_raw, ch, a, b);
+}
+
+// FullyConvolutionalNet(reps 1, [c,c,c], residual) + BatchNormReLU(3c): J0 [n, 3c]   (model.py:180-181,255-256)
+static int fcn(Ctx& c, const Level& lv0, const SgnnFcnW& f, const float* x_raw, const float* x_bn, float** out,
+               int64_t rows[3]) {
+  const int ch = f.c;
+  ALLOC(J0, float, lv0.n * 3 * ch);
+  *out = J0;
+  rows[0] = lv0.n; rows[1] = rows[2] = 0;
+  if (lv0.n == 0) return SGNN_OK;
+  ALLOC(y0_bn, float, lv0.n * ch);
+  RC(res_block(c, lv0, f.blk[0], ch, x_raw, x_bn, epi_bn(J0, 3 * ch, f.bn_join), epi_bn(y0_bn, ch, f.bn_down[0])));
+  Level lv1;
+  int32_t *par01, *chi01;
+  RC(coarsen_level(c, lv0, &lv1, &par01, &chi01, true));
+  rows[1] = lv1.n;
+  ALLOC(J1, float, lv1.n * 2 * ch);
+  if (lv1.n) {
+    ALLOC(z1_raw, float, lv1.n * ch);
+    ALLOC(z1_bn, float, lv1.n * ch);
+    RC(conv(c, y0_bn, ch, ch, chi01, lv1.n, 8, 0, f.w_down[0], ch, lv1.n, nullptr, 0, epi(z1_raw, ch),
+            epi_bn(z1_bn, ch, f.blk[1].bn0)));
+    ALLOC(y1_bn, float, lv1.n * ch);
+    RC(res_block(c, lv1, f.blk[1], ch, z1_raw, z1_bn, epi(J1, 2 * ch), epi_bn(y1_bn, ch, f.bn_down[1])));
+    Level lv2;
+    int32_t *par12, *chi12;
+    RC(coarsen_level(c, lv1, &lv2, &par12, &chi12, true));
+    rows[2] = lv2.n;
+    ALLOC(y2, float, lv2.n * ch);
+    if (lv2.n) {
+      ALLOC(z2_raw, float, lv2.n * ch);
+      ALLOC(z2_bn, float, lv2.n * ch);
+      RC(conv(c, y1_bn, ch, ch, chi12, lv2.n, 8, 0, f.w_down[1], ch, lv2.n, nullptr, 0, epi(z2_raw, ch),
+              epi_bn(z2_bn, ch, f.blk[2].bn0)));
+      RC(res_block(c, lv2, f.blk[2], ch, z2_raw, z2_bn, epi(y2, ch), kNoEpi));
+    }
+    SgnnEpilogue e1;
+    e1.out = J1 + ch; e1.ld = 2 * ch; e1.relu = 0; e1.scale = nullptr; e1.shift = nullptr;
+    RC(sgnn_unpool(y2, ch, par12, ch, lv1.n, &e1, c.stream));
+  }
+  SgnnEpilogue e0;
+  e0.out = J0 + ch; e0.ld = 3 * ch; e0.relu = 1; e0.scale = f.bn_join.scale + ch; e0.shift = f.bn_join.shift + ch;
+  return sgnn_unpool(J1, 2 * ch, par01, 2 * ch, lv0.n, &e0, c.stream);
+}
+
+static int pad4(int v) { return (v + 3) / 4 * 4; }
+
+struct Skip { SgnnGrid g; const float* f; int c; int64_t n; };
+
+}  // namespace
+
+extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coords, int coords_i64,
+                                      const float* feats, int64_t n, int32_t nb, const int32_t* dims3, void* arena,
+                                      size_t arena_bytes, int flags, SgnnGeneratorOut* out, void* stream) {
+  if (!w || !out || !dims3 || n < 0 || nb <= 0 || (n > 0 && (!coords || !feats)) || !arena) return SGNN_E_INVALID;
+  memset(out, 0, sizeof(*out));
+  Ctx c;
+  c.ar.base = (char*)arena; c.ar.cap = arena_bytes; c.ar.off = 0; c.ar.high = 0; c.ar.oom = false;
+  c.st = (cudaStream_t)stream; c.stream = stream;
+  int rc = SGNN_OK;
+  do {
+#define GEN(call)                 \
+  if ((rc = (call)) != SGNN_OK) break
+#define GALLOC(var, type, count)                                \
+  type* var = (type*)c.ar.get((size_t)(count) * sizeof(type));  \
+  if (!var) { rc = SGNN_E_NOMEM; break; }
+    int dims[3] = {dims3[0], dims3[1], dims3[2]};
+    // ------------------------------------------------------------ encoder (model.py:145-150)
+    Level lv;
+    GEN(build_level(c, coords, coords_i64, n, nb, dims, nullptr, &lv));
+    out->rows[0] = n;
+    Skip skips[4];
+    const float* x = feats;
+    int ld_x = w->enc[0].cin;
+    bool enc_ok = true;
+    for (int l = 0; l < 3 && enc_ok; ++l) {
+      const SgnnEncLevelW& e = w->enc[l];
+      const int ch = e.c;
+      enc_ok = false;
+      GALLOC(a_raw, float, lv.n * ch);
+      GALLOC(a_bn, float, lv.n * ch);
+      GEN(conv(c, x, ld_x, e.cin, lv.nbr, lv.n, 27, 0, e.w_in, ch, lv.n, nullptr, 0, epi(a_raw, ch),
+               epi_bn(a_bn, ch, e.res.bn0)));
+      GALLOC(skip, float, lv.n * ch);
+      GEN(res_block(c, lv, e.res, ch, a_raw, a_bn, epi_bn(skip, ch, e.bn_out), kNoEpi));
+      skips[l].g = lv.g; skips[l].f = skip; skips[l].c = ch; skips[l].n = lv.n;
+      Level cl;
+      int32_t *par, *chi;
+      GEN(coarsen_level(c, lv, &cl, &par, &chi, l < 2));
+      out->rows[l + 1] = cl.n;
+      GALLOC(h, float, cl.n * ch);
+      if (cl.n)
+        GEN(conv(c, skip, ch, ch, chi, cl.n, 8, 0, e.w_down, ch, cl.n, nullptr, 0, epi_bn(h, ch, e.bn_down), kNoEpi));
+      lv = cl;
+      x = h;
+      ld_x = ch;
+      enc_ok = true;
+    }
+    if (rc || !enc_ok) { if (!rc) rc = SGNN_E_NOMEM; break; }
+    skips[3].g = lv.g; skips[3].f = x; skips[3].c = ld_x; skips[3].n = lv.n;   // ft3 (model.py:64)
+    int dd[3] = {lv.dims[0], lv.dims[1], lv.dims[2]};
+    // ------------------------------------------------------------ dense U-Net (model.py:152-166)
+    const int cd = ld_x;
+    const int64_t dvol = (int64_t)dd[0] * dd[1] * dd[2];
+    GALLOC(dense, float, (int64_t)nb * cd * dvol);
+    GEN(sgnn_sparse_to_dense(x, cd, lv.coords, lv.n, cd, dense, nb, dd[0], dd[1], dd[2], stream));
+    const float* lay_out[6];
+    int lay_c[6], lay_d[6][3];
+    const float* cur = dense;
+    int cur_c = cd, cur_d[3] = {dd[0], dd[1], dd[2]};
+    bool dense_ok = true;
+    for (int l = 0; l < 6 && dense_ok; ++l) {
+      const SgnnDenseLayerW& L = w->dense[l];
+      dense_ok = false;
+      const float* in1 = nullptr;
+      int c1 = 0;
+      if (L.cat_with >= 0) { in1 = lay_out[L.cat_with]; c1 = lay_c[L.cat_with]; }
+      int od[3];
+      for (int i = 0; i < 3; ++i)
+        od[i] = L.transposed ? (cur_d[i] - 1) * L.stride - 2 * L.pad + L.ksize
+                             : (cur_d[i] + 2 * L.pad - L.ksize) / L.stride + 1;
+      GALLOC(o, float, (int64_t)nb * L.cout * od[0] * od[1] * od[2]);
+      if (L.transposed)
+        GEN(sgnn_dense_convT3d(cur, cur_c, in1, c1, nb, cur_d[0], cur_d[1], cur_d[2], L.w, L.cout, L.ksize, L.stride,
+                               L.pad, L.bn.scale, L.bn.shift, 1, o, stream));
+      else
+        GEN(sgnn_dense_conv3d(cur, cur_c, in1, c1, nb, cur_d[0], cur_d[1], cur_d[2], L.w, L.cout, L.ksize, L.stride,
+                              L.pad, L.bn.scale, L.bn.shift, 1, o, stream));
+      lay_out[l] = o; lay_c[l] = L.cout;
+      for (int i = 0; i < 3; ++i) lay_d[l][i] = od[i];
+      cur = o; cur_c = L.cout;
+      for (int i = 0; i < 3; ++i) cur_d[i] = od[i];
+      dense_ok = true;
+    }
+    if (rc || !dense_ok) { if (!rc) rc = SGNN_E_NOMEM; break; }
+    if (cur_d[0] != dd[0] || cur_d[1] != dd[1] || cur_d[2] != dd[2] || cur_c != w->nf_coarse) { rc = SGNN_E_INVALID; break; }
+    GALLOC(occsdf, float, (int64_t)nb * 2 * dvol);
+    GEN(sgnn_dense_conv3d(cur, cur_c, nullptr, 0, nb, dd[0], dd[1], dd[2], w->w_heads, 2, 1, 1, 0, nullptr, nullptr, 0,
+                          occsdf, stream));
+    // ------------------------------------------------------------ a8: dense -> sparse (model.py:315-336)
+    const int64_t ncell = (int64_t)nb * dvol;
+    GALLOC(cand0, float, ncell * 2);
+    int64_t m = 0;
+    int32_t* locs = nullptr;
+    float* fts = nullptr;
+    int ld_f = 0, live_c = 0;
+    {
+      GALLOC(dflags, uint8_t, ncell);
+      GALLOC(offs, int32_t, ncell + 1);
+      const size_t mark = c.ar.off;
+      const size_t sb = sgnn_scan_scratch_bytes(ncell);
+      GALLOC(scr, char, sb);
+      GEN(sgnn_dense_flags(occsdf, nb, dvol, cand0, dflags, offs, scr, sb, stream));
+      c.ar.off = mark;
+      int32_t cnt = 0;
+      GEN(read_i32(c, offs + ncell, &cnt));
+      m = cnt;
+      live_c = w->nf_coarse + 2;
+      ld_f = pad4(live_c + skips[3].c);
+      GALLOC(l0, int32_t, m * 4);
+      GALLOC(f0, float, m * ld_f);
+      locs = l0; fts = f0;
+      GEN(sgnn_dense_write(cur, occsdf, nb, w->nf_coarse, dd[0], dd[1], dd[2], dflags, offs, locs, fts, ld_f, stream));
+    }
+    out->n_cand[0] = ncell; out->cand[0] = cand0;
+    out->cand_locs[0] = nullptr;   // level 0 candidates are ALL cells in batch-major raster order: implicit
+    // ------------------------------------------------------------ refinement levels (model.py:387-396)
+    int rdims[3] = {dd[0], dd[1], dd[2]};
+    bool ref_ok = true;
+    for (int h = 0; h < 3 && ref_ok; ++h) {
+      const SgnnRefineW& R = w->ref[h];
+      ref_ok = false;
+      if (m == 0) { ref_ok = true; continue; }
+      const Skip& sk = skips[3 - h];
+      if (sk.n) GEN(sgnn_concat_skip(&sk.g, sk.f, sk.c, sk.c, locs, m, fts, ld_f, live_c, stream));
+      // (rows of an empty skip set keep the zeros written with the row)
+      live_c += sk.c;
+      if (live_c != R.cin) { rc = SGNN_E_INVALID; break; }
+      Level rl;
+      GEN(build_level(c, locs, 0, m, nb, rdims, nullptr, &rl));
+      const int ch = R.c;
+      GALLOC(a_raw, float, m * ch);
+      GALLOC(a_bn, float, m * ch);
+      GEN(conv(c, fts, ld_f, R.cin, rl.nbr, m, 27, 0, R.w_in, ch, m, nullptr, 0, epi(a_raw, ch),
+               epi_bn(a_bn, ch, R.fcn.blk[0].bn0)));
+      float* J0 = nullptr;
+      GEN(fcn(c, rl, R.fcn, a_raw, a_bn, &J0, &out->rows[4 + 3 * h]));
+      // a9: 8 children per site, never materialised: n1 in child mode + n2, heads, mask, compaction
+      const int64_t ncand = 8 * m;
+      GALLOC(xc, float, ncand * ch);
+      GEN(conv(c, J0, 3 * ch, 3 * ch, rl.nbr, m, 27, 1, R.w_up, ch, ncand, nullptr, 0, epi_bn(xc, ch, R.bn_up), kNoEpi));
+      GALLOC(cand, float, ncand * 2);
+      GALLOC(flg, uint8_t, ncand);
+      GALLOC(offs, int32_t, ncand + 1);
+      const size_t mark = c.ar.off;
+      const size_t sb = sgnn_scan_scratch_bytes(ncand);
+      GALLOC(scr, char, sb);
+      GEN(sgnn_heads_flags(xc, ch, ch, R.w_occ, R.b_occ, R.w_sdf, R.b_sdf, ncand, cand, flg, offs, scr, sb, stream));
+      c.ar.off = mark;
+      int32_t cnt = 0;
+      GEN(read_i32(c, offs + ncand, &cnt));
+      out->n_cand[h + 1] = ncand; out->cand[h + 1] = cand;
+      if (flags & SGNN_GEN_CAND_LOCS) {
+        GALLOC(cl, int32_t, ncand * 4);
+        GEN(sgnn_children_coords(locs, m, cl, stream));
+        out->cand_locs[h + 1] = cl;
+      }
+      const int next_skip = h < 2 ? skips[2 - h].c : skips[0].c;
+      const int ld_n = pad4(ch + 2 + next_skip);
+      GALLOC(nl, int32_t, (int64_t)cnt * 4);
+      GALLOC(nf, float, (int64_t)cnt * ld_n);
+      GEN(sgnn_heads_write(xc, ch, ch, cand, locs, ncand, flg, offs, nl, nf, ld_n, stream));
+      locs = nl; fts = nf; ld_f = ld_n; live_c = ch + 2; m = cnt;
+      for (int i = 0; i < 3; ++i) rdims[i] *= 2;
+      ref_ok = true;
+    }
+    if (rc || !ref_ok) { if (!rc) rc = SGNN_E_NOMEM; break; }
+    // ------------------------------------------------------------ surface prediction (model.py:398-402)
+    out->n_out = m;
+    out->out_locs = locs;
+    if (m > 0) {
+      const SgnnSurfaceW& S = w->surf;
+      const Skip& sk = skips[0];
+      if (sk.n) GEN(sgnn_concat_skip(&sk.g, sk.f, sk.c, sk.c, locs, m, fts, ld_f, live_c, stream));
+      live_c += sk.c;
+      if (live_c != S.cin) { rc = SGNN_E_INVALID; break; }
+      Level sl;
+      GEN(build_level(c, locs, 0, m, nb, rdims, nullptr, &sl));
+      const int ch = S.c;
+      GALLOC(a_raw, float, m * ch);
+      GALLOC(a_bn, float, m * ch);
+      GEN(conv(c, fts, ld_f, S.cin, sl.nbr, m, 27, 0, S.w_in, ch, m, nullptr, 0, epi(a_raw, ch),
+               epi_bn(a_bn, ch, S.fcn.blk[0].bn0)));
+      float* J0 = nullptr;
+      GEN(fcn(c, sl, S.fcn, a_raw, a_bn, &J0, &out->rows[13]));
+      GALLOC(sdf, float, m);
+      GEN(sgnn_linear(J0, 3 * ch, S.w_lin, S.b_lin, sdf, 1, m, 3 * ch, 1, stream));
+      out->out_sdf = sdf;
+    }
+  } while (0);
+  out->arena_used = c.ar.off;
+  out->arena_needed = c.ar.high > arena_bytes ? 2 * c.ar.high : c.ar.high;
+  if (c.ar.oom && rc == SGNN_OK) rc = SGNN_E_NOMEM;
+  if (c.ar.oom) rc = SGNN_E_NOMEM;
+  return rc;
+}

@@ -219,6 +219,7 @@ class GenModel(nn.Module):
         self.surfacepred = SurfacePrediction(nf_in, nf, 1, self.refine_sizes[-1])
         self.return_long = True      # LongTensor coordinates at the boundary, like the reference
         self._plan = None
+        self._native = None
 
     # model.py:357-369.  The sizes are upper bounds of mode-0 InputLayers; the reference doubles
     # refine_max_dim inside the k loop -- mirrored, not "fixed": bounds only grow.
@@ -301,6 +302,14 @@ class GenModel(nn.Module):
             return [[], []], outputs
 
     def forward(self, x, loss_weights):
+        """Fast path: the native generator (one C-ABI call, csrc/generator.cu) when the model has the default
+        SG-NN structure and every level is requested; otherwise the Python-orchestrated fused path."""
+        from . import native
+        if native.supported(self) and all(float(v) > 0 for v in loss_weights):
+            return native.forward_native(self, x, loss_weights)
+        return self.forward_fused(x, loss_weights)
+
+    def forward_fused(self, x, loss_weights):
         from .fused import forward_fused
         return forward_fused(self, x, loss_weights)
 

@@ -1,0 +1,196 @@
+"""Python front of the native generator (csrc/generator.cu): flattens the module tree of GenModel into the
+SgnnGeneratorW struct of device pointers (cached until a parameter changes), owns the workspace arena, makes
+ONE C-ABI call per forward and wraps the results.  Same results, bit for bit, as fused.forward_fused /
+GenModel.forward_modules; only the default SG-NN structure (test_scene.py:29-39) is supported natively."""
+import ctypes as C
+
+import torch
+
+from . import engine as E
+from . import _lib
+from ._lib import lib, check
+
+
+def supported(model):
+    try:
+        return (len(model.refinement) == 3 and len(model.encoder.process_sparse) == 3 and model.pass_occ and
+                model.pass_feats and model.use_skip_sparse and model.encoder.use_skip_dense and model.PRED_SURF)
+    except Exception:
+        return False
+
+
+class _Weights(object):
+    """Keeps every tensor referenced by the struct alive."""
+
+    def __init__(self, model):
+        self.keep = []
+        self.key = self.version_key(model)
+        self.w = _lib.SgnnGeneratorW()
+        self.dev = next(model.parameters()).device
+        w = self.w
+        enc = model.encoder
+        for l, layer in enumerate(enc.process_sparse):
+            e = w.enc[l]
+            e.cin, e.c = layer.nf_in, layer.nf
+            e.w_in = self.conv(layer.p1)
+            self.res(e.res, layer.p2[0])
+            self.bn(e.bn_out, layer.p2[2])
+            e.w_down = self.conv(layer.p3[0])
+            self.bn(e.bn_down, layer.p3[1])
+        seqs = [enc.encode_dense0, enc.encode_dense1, enc.bottleneck_dense2, enc.decode_dense3, enc.decode_dense4,
+                enc.final]
+        cat = [-1, -1, -1, 1, 0, -1]
+        for i, seq in enumerate(seqs):
+            d = w.dense[i]
+            conv = seq[0]
+            d.w = self.t(conv.weight)
+            self.bn(d.bn, seq[1])
+            d.cout, d.ksize, d.stride, d.pad = conv.out_channels, conv.kernel_size[0], conv.stride[0], conv.padding[0]
+            d.transposed = 1 if isinstance(conv, torch.nn.ConvTranspose3d) else 0
+            d.cat_with = cat[i]
+        w.w_heads = self.t(torch.cat([enc.occpred[0].weight.detach().reshape(1, -1),
+                                      enc.sdfpred[0].weight.detach().reshape(1, -1)], 0))
+        w.nf_coarse = enc.final[0].out_channels
+        for h in range(3):
+            r, m = w.ref[h], model.refinement[h]
+            r.cin, r.c = m.nf_in, m.nf
+            r.w_in = self.conv(m.p1)
+            self.fcn(r.fcn, m.p2, m.p3)
+            r.w_up = self.conv(m.n1)
+            self.bn(r.bn_up, m.n2)
+            r.w_occ, r.b_occ = self.t(m.linear.weight.view(-1)), self.t(m.linear.bias)
+            r.w_sdf, r.b_sdf = self.t(m.linearsdf.weight.view(-1)), self.t(m.linearsdf.bias)
+        s, m = w.surf, model.surfacepred
+        s.cin, s.c = m.p1.nIn, m.p1.nOut
+        s.w_in = self.conv(m.p1)
+        self.fcn(s.fcn, m.p2, m.p3)
+        s.w_lin, s.b_lin = self.t(m.linear.weight), self.t(m.linear.bias)
+
+    @staticmethod
+    def version_key(model):
+        return tuple((t._version, t.data_ptr()) for t in model.state_dict().values())
+
+    def t(self, x):
+        x = x.detach().float().contiguous()
+        self.keep.append(x)
+        return x.data_ptr()
+
+    def conv(self, m):
+        wt = m.weight.detach()
+        if wt.dim() == 4:
+            wt = wt[:, 0]
+        return self.t(wt)
+
+    def bn(self, dst, m):
+        s, t = E.fold_bn(m)
+        self.keep += [s, t]
+        dst.scale, dst.shift = s.data_ptr(), t.data_ptr()
+
+    def res(self, dst, blk):
+        seq = blk[1]
+        self.bn(dst.bn0, seq[0])
+        dst.w0 = self.conv(seq[1])
+        self.bn(dst.bn1, seq[2])
+        dst.w1 = self.conv(seq[3])
+
+    def fcn(self, dst, fcn, p3):
+        m = fcn
+        dst.c = m[0][1][1].nOut
+        for lvl in range(3):
+            self.res(dst.blk[lvl], m[0])
+            if lvl < 2:
+                down = m[2][1]
+                self.bn(dst.bn_down[lvl], down[0])
+                dst.w_down[lvl] = self.conv(down[1])
+                m = down[2]
+        self.bn(dst.bn_join, p3)
+
+
+class NativeGenerator(object):
+    def __init__(self, model, arena_bytes=1 << 30):
+        self.model = model
+        self.weights = None
+        self.arena = None
+        self.arena_bytes = int(arena_bytes)
+        self.last = None
+
+    def _prepare(self, dev):
+        m = self.model
+        if self.weights is None or self.weights.dev != dev or self.weights.key != _Weights.version_key(m):
+            self.weights = _Weights(m)
+        if self.arena is None or self.arena.device != dev or self.arena.numel() < self.arena_bytes:
+            self.arena = None
+            self.arena = torch.empty(self.arena_bytes, dtype=torch.uint8, device=dev)
+
+    def forward(self, locs, feats, want_cand_locs=True, nb=None):
+        """locs int64/int32 [n,4] CUDA, feats fp32 [n,cin] CUDA -> raw SgnnGeneratorOut-backed tensors (clones)."""
+        dev = feats.device
+        self._prepare(dev)
+        m = self.model
+        dims = (C.c_int32 * 3)(*[int(v) for v in m.encoder.process_sparse[0].p0.spatial_size])
+        if nb is None:
+            nb = int(locs[:, 3].max().item()) + 1 if locs.shape[0] else 1
+        out = _lib.SgnnGeneratorOut()
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for _ in range(8):
+            rc = lib.sgnn_generator_forward(C.byref(self.weights.w), C.c_void_p(locs.data_ptr()),
+                                            1 if locs.dtype == torch.int64 else 0, C.c_void_p(feats.data_ptr()),
+                                            locs.shape[0], nb, dims, C.c_void_p(self.arena.data_ptr()),
+                                            self.arena.numel(), _lib.GEN_CAND_LOCS if want_cand_locs else 0,
+                                            C.byref(out), stream)
+            if rc != -6:
+                break
+            self.arena_bytes = max(int(out.arena_needed), 2 * self.arena_bytes)
+            self._prepare(dev)
+        check(rc, 'sgnn_generator_forward')
+        self.last = out
+        return out, nb
+
+    def view(self, ptr, shape, dtype):
+        """Tensor view into the arena (valid until the next forward)."""
+        n = 1
+        for s in shape:
+            n *= s
+        if n == 0:
+            return torch.empty(shape, dtype=dtype, device=self.arena.device)
+        off = ptr - self.arena.data_ptr()
+        esz = torch.empty(0, dtype=dtype).element_size()
+        return self.arena[off:off + n * esz].view(dtype).view(shape)
+
+
+def forward_native(model, x, loss_weights):
+    from .model import _dense_cell_coords
+    if model.training:
+        raise NotImplementedError('sgnn_b200 is forward-inference only: call model.eval()')
+    locs, feats = x[0], x[1]
+    if not feats.is_cuda:
+        raise RuntimeError('sgnn_b200.GenModel: features must be a CUDA tensor (no CPU fallback)')
+    dev = feats.device
+    if model._native is None:
+        model._native = NativeGenerator(model)
+    g = model._native
+    locs = locs.to(dev).contiguous()
+    if locs.dtype not in (torch.int64, torch.int32):
+        locs = locs.long()
+    feats = feats.float().contiguous()
+    ssz = [int(v) for v in model.encoder.process_sparse[0].p0.spatial_size]
+    with torch.no_grad():
+        out, nb = g.forward(locs, feats, want_cand_locs=True, nb=int(x[2]) if len(x) > 2 else None)
+        def to64(v):
+            return E.coords_to_i64(v) if model.return_long else v.clone()
+        outputs = []
+        dd = list(ssz)
+        for _ in range(3):
+            dd = [(d - 2) // 2 + 1 for d in dd]
+        outputs.append([to64(_dense_cell_coords(nb, dd, dev)), g.view(out.cand[0], (out.n_cand[0], 2), torch.float32).clone()])
+        for h in range(1, 4):
+            n = out.n_cand[h]
+            if n == 0:
+                outputs.append([[], []])
+                continue
+            outputs.append([to64(g.view(out.cand_locs[h], (n, 4), torch.int32)),
+                            g.view(out.cand[h], (n, 2), torch.float32).clone()])
+        if out.n_out == 0:
+            return [[], []], outputs
+        ol = to64(g.view(out.out_locs, (out.n_out, 4), torch.int32))
+        return [ol, g.view(out.out_sdf, (out.n_out, 1), torch.float32).clone()], outputs

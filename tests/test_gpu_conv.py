@@ -215,7 +215,8 @@ def test_error_codes():
 @pytest.mark.parametrize('transposed,c0,c1,cout,k,s,p,dims', [
     (False, 16, 0, 24, 4, 2, 1, (8, 8, 8)), (False, 24, 0, 32, 4, 2, 1, (4, 4, 4)), (False, 32, 0, 32, 1, 1, 0, (2, 2, 2)),
     (True, 32, 32, 32, 4, 2, 1, (2, 2, 2)), (True, 32, 24, 28, 4, 2, 1, (4, 6, 4)), (False, 28, 0, 16, 1, 1, 0, (8, 4, 8)),
-    (False, 16, 0, 2, 1, 1, 0, (8, 8, 8)),
+    (False, 16, 0, 2, 1, 1, 0, (8, 8, 8)), (True, 8, 0, 4, 3, 1, 1, (4, 4, 4)), (True, 6, 2, 5, 2, 2, 0, (3, 3, 3)),
+    (True, 5, 0, 3, 4, 1, 0, (3, 2, 3)), (False, 7, 3, 5, 3, 2, 1, (7, 5, 6)),
 ])
 def test_dense_unet_layers_bit_exact(transposed, c0, c1, cout, k, s, p, dims):
     """a12: the coarse dense U-Net layers (model.py:89-136) -- bit-exact vs O3, 1e-5 vs torch."""

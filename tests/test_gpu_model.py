@@ -53,7 +53,9 @@ def test_golden_fixture_from_reference_model(name):
         assert kept == int(g['kept'][i])
     assert np.array_equal(out_locs.cpu().numpy(), g['out_locs'].astype(np.int64))
     assert np.abs(out_sdf.cpu().numpy() - g['out_sdf']).max() <= TOL_SDF
-    # and the reference-shaped (module by module) path gives the SAME bits as the fused path
+    # the native one-call generator, the Python-orchestrated fused path and the reference-shaped (module by
+    # module) path give the SAME bits
+    _same_outputs(((out_locs, out_sdf), levels), m.forward_fused([locs, feats], ONES))
     _same_outputs(((out_locs, out_sdf), levels), m.forward_modules([locs, feats], ONES))
 
 
@@ -119,6 +121,7 @@ def test_baseline_config_properties():
     a = m([locs.cuda(), feats.cuda()], ONES)
     b = m([locs.cuda(), feats.cuda()], ONES)
     _same_outputs(a, b)                                             # deterministic (no atomics on the float path)
+    _same_outputs(a, m.forward_fused([locs.cuda(), feats.cuda()], ONES))
     _same_outputs(a, m.forward_modules([locs.cuda(), feats.cuda()], ONES))
     (fl, fs), lv = a
     assert lv[0][0].shape[0] == 32 * 512
