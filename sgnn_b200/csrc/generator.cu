@@ -234,8 +234,9 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       GEN(coarsen_level(c, lv, &cl, &par, &chi, l < 2));
       out->rows[l + 1] = cl.n;
       GALLOC(h, float, cl.n * ch);
-      if (cl.n)
+      if (cl.n) {
         GEN(conv(c, skip, ch, ch, chi, cl.n, 8, 0, e.w_down, ch, cl.n, nullptr, 0, epi_bn(h, ch, e.bn_down), kNoEpi));
+      }
       lv = cl;
       x = h;
       ld_x = ch;
@@ -265,12 +266,13 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
         od[i] = L.transposed ? (cur_d[i] - 1) * L.stride - 2 * L.pad + L.ksize
                              : (cur_d[i] + 2 * L.pad - L.ksize) / L.stride + 1;
       GALLOC(o, float, (int64_t)nb * L.cout * od[0] * od[1] * od[2]);
-      if (L.transposed)
+      if (L.transposed) {
         GEN(sgnn_dense_convT3d(cur, cur_c, in1, c1, nb, cur_d[0], cur_d[1], cur_d[2], L.w, L.cout, L.ksize, L.stride,
                                L.pad, L.bn.scale, L.bn.shift, 1, o, stream));
-      else
+      } else {
         GEN(sgnn_dense_conv3d(cur, cur_c, in1, c1, nb, cur_d[0], cur_d[1], cur_d[2], L.w, L.cout, L.ksize, L.stride,
                               L.pad, L.bn.scale, L.bn.shift, 1, o, stream));
+      }
       lay_out[l] = o; lay_c[l] = L.cout;
       for (int i = 0; i < 3; ++i) lay_d[l][i] = od[i];
       cur = o; cur_c = L.cout;
@@ -317,7 +319,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       ref_ok = false;
       if (m == 0) { ref_ok = true; continue; }
       const Skip& sk = skips[3 - h];
-      if (sk.n) GEN(sgnn_concat_skip(&sk.g, sk.f, sk.c, sk.c, locs, m, fts, ld_f, live_c, stream));
+      if (sk.n) { GEN(sgnn_concat_skip(&sk.g, sk.f, sk.c, sk.c, locs, m, fts, ld_f, live_c, stream)); }
       // (rows of an empty skip set keep the zeros written with the row)
       live_c += sk.c;
       if (live_c != R.cin) { rc = SGNN_E_INVALID; break; }
@@ -366,7 +368,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
     if (m > 0) {
       const SgnnSurfaceW& S = w->surf;
       const Skip& sk = skips[0];
-      if (sk.n) GEN(sgnn_concat_skip(&sk.g, sk.f, sk.c, sk.c, locs, m, fts, ld_f, live_c, stream));
+      if (sk.n) { GEN(sgnn_concat_skip(&sk.g, sk.f, sk.c, sk.c, locs, m, fts, ld_f, live_c, stream)); }
       live_c += sk.c;
       if (live_c != S.cin) { rc = SGNN_E_INVALID; break; }
       Level sl;
