@@ -229,7 +229,7 @@ def run_b200(args):
     if rank == 0:
         prof.count_rules = True
         E.PROFILER = prof
-        out = step(0)
+        out = model.forward_fused(list(resident[0]), ones)     # same arithmetic, every conv visible to the hook
         torch.cuda.synchronize()
         E.PROFILER = None
         prof.count_rules = False
@@ -241,7 +241,6 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        E.PROFILER = prof
     barrier()
     l0 = lib.sgnn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -254,8 +253,24 @@ def run_b200(args):
     barrier()
     wall = time.perf_counter() - t0
     launches = (lib.sgnn_launch_count() - l0) / max(args.steps, 1)
-    E.PROFILER = None
     dev_ms = e0.elapsed_time(e1)
+    # ---- same K steps again with a CUDA-event pair around every convolution launch (native SGNN_GEN_PROFILE):
+    # the dominant kernel's live duration.  Kept out of the bracket above because it adds one sync per step.
+    conv_ms, n_conv, prof_ms = 0.0, 0, 0.0
+    if rank == 0 and getattr(model, '_native', None) is not None:
+        model._native.profile = True
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for i in range(args.steps):
+            flush.fill_(i & 0xff)
+            step(i)
+            conv_ms += model._native.last.conv_ms
+            n_conv += model._native.last.n_conv
+        p1.record()
+        torch.cuda.synchronize()
+        prof_ms = p0.elapsed_time(p1)
+        model._native.profile = False
     ms = shard.max_over_ranks(dev_ms, dev)
     vox_timed = sum(vox[i % args.sets] for i in range(args.steps))
     total_vox = shard.sum_over_ranks(vox_timed, dev)
@@ -264,12 +279,18 @@ def run_b200(args):
     # ---- e2e: HOST buffers in, host result out, through the public API (GenModel.forward), copies inside the region
     out_host = None
 
+    pin_l = torch.empty((64 * 64 * 64 * args.blocks, 4), dtype=torch.int64).pin_memory()
+    pin_s = torch.empty((64 * 64 * 64 * args.blocks, 1), dtype=torch.float32).pin_memory()
+
     def e2e_step(i):
         hl, hf = host[i % args.sets]
         dl = hl.to(dev, non_blocking=True)
         df = hf.to(dev, non_blocking=True)
         (ol, osdf), _ = model([dl, df], ones)
-        return ol.to('cpu', non_blocking=True), osdf.to('cpu', non_blocking=True), ol.shape[0]
+        n = ol.shape[0]
+        pin_l[:n].copy_(ol, non_blocking=True)          # result coordinates + TSDF back to pinned host memory
+        pin_s[:n].copy_(osdf, non_blocking=True)
+        return pin_l, pin_s, n
 
     for w in range(2):
         e2e_step(w)
@@ -308,22 +329,26 @@ def run_b200(args):
         rec['flops'] = 2.0 * r * rec['cin'] * rec['cout']
         per_set_bytes += rec['bytes']
         per_set_flops += rec['flops']
-    conv_ms = sum(a.elapsed_time(b) for a, b, _ in prof.events)
-    n_conv = max(len(prof.events), 1)
-    convs_per_step = len(prof.events) / max(args.steps, 1)
+    n_conv = max(n_conv, 1)
+    convs_per_step = n_conv / max(args.steps, 1)
     # ledger is of set 0; all sets are statistically alike (same generator) -> scale by launches
     alg_bytes_total = per_set_bytes * args.steps
     achieved = alg_bytes_total / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0
     roofline = {
-        'kernel': 'conv_gather_f32_kernel (all %d launches per step)' % round(convs_per_step),
+        'kernel': 'conv_tile_f32_kernel / conv_gather_f32_kernel (all %d sgnn_conv_forward launches per step)'
+                  % round(convs_per_step),
         'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
         'traffic': None, 'peak_source': peak_src,
         'algorithmic_bytes_per_launch': per_set_bytes / max(convs_per_step, 1),
         'avg_launch_us': 1e3 * conv_ms / n_conv,
-        'share_of_step': conv_ms / dev_ms if dev_ms > 0 else None,
+        'share_of_step': conv_ms / prof_ms if prof_ms > 0 else None,
+        'profiled_pass_ms_per_step': prof_ms / max(args.steps, 1),
         'gflops_per_step': per_set_flops / 1e9,
         'achieved_tflops_fp32': per_set_flops * args.steps / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0,
-        'note': 'fp32 FFMA path: compute-bound above ~11 flop/B; HBM fraction reported per SURVEY 8(d)',
+        'fp32_ffma_peak_tflops': 148 * 128 * 2 * 1.965e9 / 1e12,
+        'note': 'fp32 FFMA path: activations are L2 resident and the kernel is FFMA / L2-gather bound, so the HBM '
+                'fraction (SURVEY 8(d) definition) is small by construction; achieved_tflops_fp32 vs the FFMA peak '
+                'is the meaningful ceiling for this dtype',
     }
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

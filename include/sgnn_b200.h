@@ -270,8 +270,11 @@ typedef struct SgnnGeneratorOut {
   int64_t n_cand[4];    int32_t* cand_locs[4]; float* cand[4];     /* per level: [n,4] (if requested), [n,2] */
   int64_t rows[16];     /* site counts: enc L0..L3, then per refinement/surface level its 3 FCN resolutions */
   size_t arena_used, arena_needed;
+  double conv_ms;       /* SGNN_GEN_PROFILE: sum of CUDA-event durations of the sgnn_conv_forward launches */
+  int64_t n_conv;
 } SgnnGeneratorOut;
 #define SGNN_GEN_CAND_LOCS 1        /* materialise the candidate coordinates of every level (model.py:247,336) */
+#define SGNN_GEN_PROFILE 2          /* time every convolution launch with CUDA events (adds one sync at the end) */
 int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coords, int coords_i64, const float* feats,
                            int64_t n, int32_t nb, const int32_t* dims3, void* arena, size_t arena_bytes, int flags,
                            SgnnGeneratorOut* out, void* stream);
@@ -289,6 +292,10 @@ int sgnn_coords_to_i64(const int32_t* in, int64_t n, int64_t* out, void* stream)
 
 /* Number of CUDA kernels this library has launched in the calling process (monotonic). */
 int64_t sgnn_launch_count(void);
+
+/* Test hook: choose the convolution implementation (0 = default constant-weight kernel, 1 = tile kernels,
+ * 2 = runtime-shape kernel).  All give bit-identical results. */
+void sgnn_debug_set_conv_impl(int impl);
 
 int sgnn_version(void);
 const char* sgnn_error_string(int code);

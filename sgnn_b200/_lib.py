@@ -77,10 +77,12 @@ class SgnnGeneratorW(C.Structure):
 class SgnnGeneratorOut(C.Structure):
     _fields_ = [('n_out', C.c_int64), ('out_locs', C.c_void_p), ('out_sdf', C.c_void_p),
                 ('n_cand', C.c_int64 * 4), ('cand_locs', C.c_void_p * 4), ('cand', C.c_void_p * 4),
-                ('rows', C.c_int64 * 16), ('arena_used', C.c_size_t), ('arena_needed', C.c_size_t)]
+                ('rows', C.c_int64 * 16), ('arena_used', C.c_size_t), ('arena_needed', C.c_size_t),
+                ('conv_ms', C.c_double), ('n_conv', C.c_int64)]
 
 
 GEN_CAND_LOCS = 1
+GEN_PROFILE = 2
 
 _P, _I, _L, _Z = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
 _G, _E = C.POINTER(SgnnGrid), C.POINTER(SgnnEpilogue)
@@ -116,6 +118,7 @@ SIGNATURES = {
     'sgnn_children_coords': (_I, [_P, _L, _P, _P]),
     'sgnn_concat_skip': (_I, [_G, _P, _I, _I, _P, _L, _P, _I, _I, _P]),
     'sgnn_coords_to_i64': (_I, [_P, _L, _P, _P]),
+    'sgnn_debug_set_conv_impl': (None, [_I]),
     'sgnn_launch_count': (_L, []),
     'sgnn_version': (_I, []),
     'sgnn_error_string': (C.c_char_p, [_I]),

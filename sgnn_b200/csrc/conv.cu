@@ -62,8 +62,21 @@ __device__ __forceinline__ int conv_src_row(const ConvParams& p, long long j, in
 
 // Shared epilogue: residual add, two output slots with optional affine + relu (see SgnnEpilogue).
 template <int COUT>
+__device__ __forceinline__ void conv_epilogue_rows(const ConvParams& p, const float (&acc)[TS][4],
+                                                   const long long (&rows)[TS], int cg);
+
+template <int COUT>
 __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const float (&acc)[TS][4], long long tile_base,
                                               int sg, int cg) {
+  long long rows[TS];
+#pragma unroll
+  for (int t = 0; t < TS; ++t) rows[t] = tile_base + sg + NSG * t;
+  conv_epilogue_rows<COUT>(p, acc, rows, cg);
+}
+
+template <int COUT>
+__device__ __forceinline__ void conv_epilogue_rows(const ConvParams& p, const float (&acc)[TS][4],
+                                                   const long long (&rows)[TS], int cg) {
   float4 sa = make_float4(1.f, 1.f, 1.f, 1.f), ta = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa, tb = ta;
   if (p.out_a && p.scale_a) {
     sa = __ldg(reinterpret_cast<const float4*>(p.scale_a) + cg);
@@ -75,7 +88,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const float (
   }
 #pragma unroll
   for (int t = 0; t < TS; ++t) {
-    const long long j = tile_base + sg + NSG * t;
+    const long long j = rows[t];
     if (j >= p.n_out) continue;
     float4 v = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
     if (p.residual) {
@@ -363,6 +376,170 @@ conv_tile_f32_kernel(ConvParams p) {
   conv_epilogue<COUT>(p, acc, tile_base, sg, cg);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Child-mode kernel (generative upsampling, model.py:192-207,224-225): the n1 convolution over
+// the 8 children of every site.  A tile is 16 parents = 128 outputs.  The 27 parent-neighbour rows of each
+// parent are staged in shared memory ONCE (16 x 27 rows) and serve all 8 children x 27 offsets -- 8x less
+// gather traffic than treating the 128 children as independent rows.  Only the 3 KB filter slice of the
+// current offset streams (double buffered).  Thread (g, w, cg): parents {g, g+8}, children {w, w+4},
+// channels [4cg, 4cg+4): the 8 lane groups of a warp read 8 different parents of the same (child, offset),
+// i.e. 8 rows at stride 27*XS -- conflict free.  Arithmetic order identical to the generic kernels.
+template <int COUT, int CINP>
+__global__ void __launch_bounds__(NSG * (COUT / 4), 2)
+conv_child_f32_kernel(ConvParams p) {
+  constexpr int NCG = COUT / 4;
+  constexpr int NT = NSG * NCG;
+  constexpr int PT = TM / 8;  // parents per tile
+  constexpr int XS2 = TileCfg<CINP>::XS2;
+  constexpr int CPR = CINP / 4;
+  constexpr int WT = CINP * COUT;
+  extern __shared__ __align__(16) float smem[];
+  float* X_s = smem;                             // [PT][27][XS2]
+  float* W_s = X_s + PT * 27 * XS2;              // [2][CINP][COUT]
+  int* idx_s = reinterpret_cast<int*>(W_s + 2 * WT);  // [27][PT]
+  __shared__ unsigned live_kp_s;
+  __shared__ signed char kp_tab[8][27];
+
+  const int tid = threadIdx.x;
+  const int sg = tid / NCG, cg = tid % NCG;
+  const int g = sg & 7, w = sg >> 3;
+  const long long parent_base = (long long)blockIdx.x * PT;
+  const long long n_parent = p.n_out >> 3;
+
+  if (tid == 0) live_kp_s = 0u;
+  for (int e = tid; e < 8 * 27; e += NT) {
+    const int c = e / 27, k = e % 27;
+    const int dz = k / 9 - 1, dy = (k / 3) % 3 - 1, dx = k % 3 - 1;
+    const int pz = (((c >> 2) & 1) + dz + 2) / 2 - 1;
+    const int py = (((c >> 1) & 1) + dy + 2) / 2 - 1;
+    const int px = ((c & 1) + dx + 2) / 2 - 1;
+    kp_tab[c][k] = (signed char)((pz + 1) * 9 + (py + 1) * 3 + (px + 1));
+  }
+  for (int b = 0; b < 2; ++b)
+    for (int q = p.cin * COUT + tid; q < WT; q += NT) W_s[b * WT + q] = 0.f;
+  __syncthreads();
+  unsigned my_live = 0u;
+  for (int e = tid; e < 27 * PT; e += NT) {
+    const int kp = e / PT, pl = e % PT;
+    const long long pr = parent_base + pl;
+    const int r = pr < n_parent ? __ldg(p.nbr + (long long)kp * p.nbr_stride + pr) : -1;
+    idx_s[e] = r;
+    if (r >= 0) my_live |= 1u << kp;
+  }
+  my_live = __reduce_or_sync(0xffffffffu, my_live);
+  if ((tid & 31) == 0 && my_live) atomicOr(&live_kp_s, my_live);
+  __syncthreads();
+  // stage all parent-neighbour rows of the tile
+  for (int pi = tid; pi < 27 * PT * CPR; pi += NT) {
+    const int ch = pi % CPR, e = pi / CPR;
+    const int kp = e / PT, pl = e % PT;
+    const int r = idx_s[e];
+    float* dst = X_s + (pl * 27 + kp) * XS2 + ch * 4;
+    if (r >= 0) {
+      const float* src = p.in + (long long)r * p.ld_in + ch * 4;
+      if (ch * 4 + 4 <= p.cin) {
+        cp_async16(dst, src);
+      } else {
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          if (ch * 4 + e2 < p.cin) cp_async4(dst + e2, src + e2);
+          else dst[e2] = 0.f;
+        }
+      }
+    } else {
+      *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  // offsets with at least one live (child, parent neighbour) in the tile
+  const unsigned live_kp = live_kp_s;
+  unsigned live_k = 0u;
+  for (int k = 0; k < 27; ++k) {
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) any = any || ((live_kp >> kp_tab[c][k]) & 1u);
+    if (any) live_k |= 1u << k;
+  }
+  auto issue_w = [&](int k, int buf) {
+    const float* Wk = p.weight + (size_t)k * p.cin * COUT;
+    float* Wd = W_s + buf * WT;
+    for (int q = tid; q < p.cin * NCG; q += NT) cp_async16(Wd + q * 4, Wk + q * 4);
+  };
+  unsigned issue_mask = live_k;
+  const int S = __popc(live_k);
+  if (issue_mask) {
+    issue_w(__ffs(issue_mask) - 1, 0);
+    issue_mask &= issue_mask - 1;
+  }
+  cp_async_commit();  // group 0: all X rows + first filter slice
+
+  float acc[TS][4];
+#pragma unroll
+  for (int t = 0; t < TS; ++t)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[t][c] = 0.f;
+
+  unsigned comp_mask = live_k;
+  for (int s = 0; s < S; ++s) {
+    cp_async_wait<0>();
+    __syncthreads();
+    if (issue_mask) {
+      issue_w(__ffs(issue_mask) - 1, (s + 1) & 1);
+      issue_mask &= issue_mask - 1;
+    }
+    cp_async_commit();
+    const int k = __ffs(comp_mask) - 1;
+    comp_mask &= comp_mask - 1;
+    const float* Wd = W_s + (s & 1) * WT + cg * 4;
+    const float* xr[TS];
+#pragma unroll
+    for (int t = 0; t < TS; ++t) {
+      const int pl = g + 8 * (t & 1), c = w + 4 * (t >> 1);
+      xr[t] = X_s + (pl * 27 + kp_tab[c][k]) * XS2;
+    }
+#pragma unroll
+    for (int c4 = 0; c4 < CINP; c4 += 4) {
+      float4 xv[TS];
+#pragma unroll
+      for (int t = 0; t < TS; ++t) xv[t] = *reinterpret_cast<const float4*>(xr[t] + c4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 wv = *reinterpret_cast<const float4*>(Wd + (c4 + e) * COUT);
+#pragma unroll
+        for (int t = 0; t < TS; ++t) {
+          const float x = e == 0 ? xv[t].x : e == 1 ? xv[t].y : e == 2 ? xv[t].z : xv[t].w;
+          acc[t][0] = fmaf(x, wv.x, acc[t][0]);
+          acc[t][1] = fmaf(x, wv.y, acc[t][1]);
+          acc[t][2] = fmaf(x, wv.z, acc[t][2]);
+          acc[t][3] = fmaf(x, wv.w, acc[t][3]);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  long long rows[TS];
+#pragma unroll
+  for (int t = 0; t < TS; ++t) rows[t] = (parent_base + g + 8 * (t & 1)) * 8 + w + 4 * (t >> 1);
+  conv_epilogue_rows<COUT>(p, acc, rows, cg);
+}
+
+template <int COUT, int CINP>
+static int launch_child(const ConvParams& p, cudaStream_t st) {
+  constexpr int NT = NSG * (COUT / 4);
+  constexpr int PT = TM / 8;
+  const size_t smem = ((size_t)PT * 27 * TileCfg<CINP>::XS2 + 2 * CINP * COUT) * sizeof(float) + 27 * PT * sizeof(int);
+  const long long tiles = ((p.n_out >> 3) + PT - 1) / PT;
+  if (tiles > 0x7fffffff) return SGNN_E_TOO_LARGE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SGNN_CUDA(cudaFuncSetAttribute(conv_child_f32_kernel<COUT, CINP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    attr_set = true;
+  }
+  conv_child_f32_kernel<COUT, CINP><<<(int)tiles, NT, smem, st>>>(p);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
 template <int COUT, int CINP>
 static int launch_tile(const ConvParams& p, cudaStream_t st) {
   constexpr int NT = NSG * (COUT / 4);
@@ -385,6 +562,7 @@ static int launch_tile(const ConvParams& p, cudaStream_t st) {
 static int dispatch_tile(const ConvParams& p, cudaStream_t st, bool* handled) {
   const int cinp = (p.cin + 3) & ~3;
   *handled = true;
+  if (p.child_mode && p.cout == 16 && cinp == 48 && (p.n_out & 7) == 0) return launch_child<16, 48>(p, st);
 #define SGNN_TILE_CASE(CO, CI) \
   if (p.cout == CO && cinp == CI) return launch_tile<CO, CI>(p, st);
   SGNN_TILE_CASE(8, 4)
@@ -398,6 +576,231 @@ static int dispatch_tile(const ConvParams& p, cudaStream_t st, bool* handled) {
   SGNN_TILE_CASE(16, 36)
   SGNN_TILE_CASE(16, 48)
 #undef SGNN_TILE_CASE
+  *handled = false;
+  return SGNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// v3 "constant-weight" kernel.  ncu on v2 (profiles/conv_r1b_*) showed the FFMA pipe at 39 % with the
+// shared-memory pipe saturated: the 4x4 register tile re-reads every weight through LDS.128 at 4 wavefronts
+// per instruction.  Here the filter slice lives in __constant__ memory and reaches the FFMA through the
+// UNIFORM datapath (LDCU -> FFMA R, R, UR, R): no shared-memory traffic for weights at all.  Each thread owns
+// S whole output rows (all Cout accumulators in registers), gathers ITS OWN neighbour rows with cp.async into a
+// private shared-memory ring (lane stride XW words, XW/4 odd -> conflict-free LDS.128/LDGSTS) and therefore
+// needs NO block barrier in the main loop: warps run decoupled.  Neighbour indices are prefetched one stage
+// ahead into registers (coalesced: consecutive lanes = consecutive rows).
+// Arithmetic is unchanged: k ascending, ci ascending, one fmaf chain per output element from +0 (or from the
+// exact partial sums of the previous k-range when the filter bank exceeds the 62 KB constant window).
+#define CW_FLOATS 15872
+__constant__ float c_W[CW_FLOATS];
+
+template <int CIN>
+struct CwCfg {
+  static constexpr int CPR = (CIN + 3) / 4;
+  static constexpr int XW = CPR * 4 + ((CPR % 2 == 0) ? 4 : 0);  // XW/4 odd
+};
+
+template <int COUT, int CIN, int S, int NS>
+__global__ void __launch_bounds__(128)
+conv_cw_kernel(ConvParams p, int k0, int k1, int vec, const float* acc_in, int ld_acc_in, float* acc_out,
+               int ld_acc_out) {
+  constexpr int CPR = CwCfg<CIN>::CPR;
+  constexpr int XW = CwCfg<CIN>::XW;
+  extern __shared__ __align__(16) float smem[];  // [NS][S][128][XW]
+  const int tid = threadIdx.x;
+  const long long row0 = (long long)blockIdx.x * (128 * S) + tid;
+
+  float acc[S][COUT];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const long long j = row0 + 128 * s;
+    if (acc_in && j < p.n_out) {
+#pragma unroll
+      for (int c = 0; c < COUT; c += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(acc_in + j * ld_acc_in + c);
+        acc[s][c] = v.x; acc[s][c + 1] = v.y; acc[s][c + 2] = v.z; acc[s][c + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) acc[s][c] = 0.f;
+    }
+  }
+
+  int ir[S];
+  auto load_idx = [&](int k) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const long long j = row0 + 128 * s;
+      ir[s] = j < p.n_out ? conv_src_row(p, j, k) : -1;
+    }
+  };
+  auto issue = [&](int buf) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      float* dst = smem + ((size_t)(buf * S + s) * 128 + tid) * XW;
+      const int r = ir[s];
+      if (r >= 0) {
+        const float* src = p.in + (long long)r * p.ld_in;
+        if (vec) {
+#pragma unroll
+          for (int ch = 0; ch < CPR; ++ch) {
+            if (ch * 4 + 4 <= CIN) {
+              cp_async16(dst + ch * 4, src + ch * 4);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (ch * 4 + e < CIN) cp_async4(dst + ch * 4 + e, src + ch * 4 + e);
+                else dst[ch * 4 + e] = 0.f;
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < CPR * 4; ++e) {
+            if (e < CIN) cp_async4(dst + e, src + e);
+            else dst[e] = 0.f;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int ch = 0; ch < CPR; ++ch) *reinterpret_cast<float4*>(dst + ch * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+
+  int kk = k0;
+  if (kk < k1) load_idx(kk);
+#pragma unroll
+  for (int i = 0; i < NS - 1; ++i) {
+    if (kk < k1) {
+      issue(i);
+      ++kk;
+      if (kk < k1) load_idx(kk);
+    }
+    cp_async_commit();
+  }
+  for (int k = k0; k < k1; ++k) {
+    cp_async_wait<NS - 2>();
+    const int st = (k - k0) % NS;
+    if (kk < k1) {
+      issue((k - k0 + NS - 1) % NS);
+      ++kk;
+      if (kk < k1) load_idx(kk);
+    }
+    cp_async_commit();
+    const float* W = c_W + (k - k0) * (CIN * COUT);
+    const float* X = smem + ((size_t)(st * S) * 128 + tid) * XW;
+#pragma unroll
+    for (int ch = 0; ch < CPR; ++ch) {
+      float4 xv[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) xv[s] = *reinterpret_cast<const float4*>(X + (size_t)s * 128 * XW + ch * 4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (ch * 4 + e < CIN) {
+#pragma unroll
+          for (int co = 0; co < COUT; ++co) {
+            const float wv = W[(ch * 4 + e) * COUT + co];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              const float x = e == 0 ? xv[s].x : e == 1 ? xv[s].y : e == 2 ? xv[s].z : xv[s].w;
+              acc[s][co] = fmaf(x, wv, acc[s][co]);
+            }
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue (per row: all COUT channels are in this thread)
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const long long j = row0 + 128 * s;
+    if (j >= p.n_out) continue;
+    if (acc_out) {
+#pragma unroll
+      for (int c = 0; c < COUT; c += 4)
+        *reinterpret_cast<float4*>(acc_out + j * ld_acc_out + c) =
+            make_float4(acc[s][c], acc[s][c + 1], acc[s][c + 2], acc[s][c + 3]);
+      continue;
+    }
+#pragma unroll
+    for (int c = 0; c < COUT; c += 4) {
+      float4 v = make_float4(acc[s][c], acc[s][c + 1], acc[s][c + 2], acc[s][c + 3]);
+      if (p.residual) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + j * p.ld_res + c));
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      }
+      if (p.out_a) {
+        float4 y = v;
+        if (p.scale_a) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale_a + c));
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift_a + c));
+          y.x = fmaf(v.x, sc.x, sh.x); y.y = fmaf(v.y, sc.y, sh.y); y.z = fmaf(v.z, sc.z, sh.z); y.w = fmaf(v.w, sc.w, sh.w);
+        }
+        if (p.relu_a) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+        *reinterpret_cast<float4*>(p.out_a + j * p.ld_a + c) = y;
+      }
+      if (p.out_b) {
+        float4 y = v;
+        if (p.scale_b) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale_b + c));
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift_b + c));
+          y.x = fmaf(v.x, sc.x, sh.x); y.y = fmaf(v.y, sc.y, sh.y); y.z = fmaf(v.z, sc.z, sh.z); y.w = fmaf(v.w, sc.w, sh.w);
+        }
+        if (p.relu_b) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+        *reinterpret_cast<float4*>(p.out_b + j * p.ld_b + c) = y;
+      }
+    }
+  }
+}
+
+template <int COUT, int CIN, int S>
+static int launch_cw(const ConvParams& p, bool vec, cudaStream_t st) {
+  constexpr int XW = CwCfg<CIN>::XW;
+  constexpr int NS = (3 * S * 128 * XW * 4 <= 72 * 1024) ? 3 : 2;
+  const size_t smem = (size_t)NS * S * 128 * XW * sizeof(float);
+  const long long tiles = (p.n_out + 128 * S - 1) / (128 * S);
+  if (tiles > 0x7fffffff) return SGNN_E_TOO_LARGE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SGNN_CUDA(cudaFuncSetAttribute(conv_cw_kernel<COUT, CIN, S, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    attr_set = true;
+  }
+  const int per_k = CIN * COUT;
+  const int kmax = CW_FLOATS / per_k;
+  float* accbuf = p.out_a ? p.out_a : p.out_b;
+  const int ld_acc = p.out_a ? p.ld_a : p.ld_b;
+  for (int k0 = 0; k0 < p.K; k0 += kmax) {
+    const int k1 = k0 + kmax < p.K ? k0 + kmax : p.K;
+    SGNN_CUDA(cudaMemcpyToSymbolAsync(c_W, p.weight + (size_t)k0 * per_k, (size_t)(k1 - k0) * per_k * sizeof(float), 0,
+                                      cudaMemcpyDeviceToDevice, st));
+    const bool first = k0 == 0, last = k1 == p.K;
+    conv_cw_kernel<COUT, CIN, S, NS><<<(int)tiles, 128, smem, st>>>(p, k0, k1, vec ? 1 : 0, first ? nullptr : accbuf,
+                                                                    ld_acc, last ? nullptr : accbuf, ld_acc);
+    SGNN_CHECK_LAUNCH();
+  }
+  return SGNN_OK;
+}
+
+// exact (cin, cout) pairs of the SG-NN channel plan
+static int dispatch_cw(const ConvParams& p, bool vec, cudaStream_t st, bool* handled) {
+  *handled = true;
+#define SGNN_CW_CASE(CO, CI, SS) \
+  if (p.cout == CO && p.cin == CI) return launch_cw<CO, CI, SS>(p, vec, st);
+  SGNN_CW_CASE(8, 1, 4)
+  SGNN_CW_CASE(8, 8, 4)
+  SGNN_CW_CASE(12, 8, 2)
+  SGNN_CW_CASE(12, 12, 2)
+  SGNN_CW_CASE(16, 12, 2)
+  SGNN_CW_CASE(16, 16, 2)
+  SGNN_CW_CASE(16, 26, 2)
+  SGNN_CW_CASE(16, 30, 2)
+  SGNN_CW_CASE(16, 34, 2)
+  SGNN_CW_CASE(16, 48, 2)
+#undef SGNN_CW_CASE
   *handled = false;
   return SGNN_OK;
 }
@@ -433,6 +836,10 @@ __global__ void conv_gather_f32_generic_kernel(ConvParams p) {
     }
   }
 }
+
+// 0: v3 constant-weight kernel (default); 1: v2 tile kernels; 2: v1 runtime-shape kernel.  Test hook.
+int g_sgnn_conv_impl = 0;
+extern "C" void sgnn_debug_set_conv_impl(int v) { g_sgnn_conv_impl = v; }
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
@@ -490,10 +897,16 @@ extern "C" int sgnn_conv_forward(const SgnnConvArgs* a, void* stream) {
     if (!aligned16(a->weight)) return SGNN_E_ALIGN;
     if (a->residual && (!aligned16(a->residual) || (a->ld_res & 3))) return SGNN_E_ALIGN;
     const bool vec = aligned16(a->in) && (a->ld_in & 3) == 0;
-    if (vec) {
+    {
       bool handled = false;
-      rc = dispatch_tile(p, st, &handled);
-      if (handled) return rc;
+      if (g_sgnn_conv_impl == 0) {
+        rc = dispatch_cw(p, vec, st, &handled);
+        if (handled) return rc;
+      }
+      if (vec && g_sgnn_conv_impl <= 1) {
+        rc = dispatch_tile(p, st, &handled);
+        if (handled) return rc;
+      }
     }
     switch (a->cout) {
       case 4: return launch_conv<4>(p, vec, st);

@@ -28,7 +28,13 @@ struct Ctx {
   Arena ar;
   cudaStream_t st;
   void* stream;
+  bool profile;
+  int n_ev;
 };
+
+// event pool for SGNN_GEN_PROFILE (pairs around every sgnn_conv_forward of the pass)
+static cudaEvent_t g_ev[512];
+static int g_ev_made = 0;
 
 struct Epi {
   float* out; int ld; const float* scale; const float* shift; int relu;
@@ -134,7 +140,17 @@ static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr,
   x.child_mode = child; x.weight = w; x.cin = cin; x.cout = cout; x.n_out = n_out; x.residual = res; x.ld_res = ld_res;
   x.a.out = a.out; x.a.ld = a.ld; x.a.relu = a.relu; x.a.scale = a.scale; x.a.shift = a.shift;
   x.b.out = b.out; x.b.ld = b.ld; x.b.relu = b.relu; x.b.scale = b.scale; x.b.shift = b.shift;
-  return sgnn_conv_forward(&x, c.stream);
+  const bool prof = c.profile && c.n_ev + 2 <= 512;
+  if (prof) {
+    while (g_ev_made < c.n_ev + 2) SGNN_CUDA(cudaEventCreate(&g_ev[g_ev_made++]));
+    SGNN_CUDA(cudaEventRecord(g_ev[c.n_ev], c.st));
+  }
+  const int rc = sgnn_conv_forward(&x, c.stream);
+  if (prof) {
+    SGNN_CUDA(cudaEventRecord(g_ev[c.n_ev + 1], c.st));
+    c.n_ev += 2;
+  }
+  return rc;
 }
 
 // y = SMC(BNReLU(SMC(x_bn))) + x_raw   with x_bn = BNReLU_0(x_raw) supplied by the producer of x_raw
@@ -202,6 +218,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
   Ctx c;
   c.ar.base = (char*)arena; c.ar.cap = arena_bytes; c.ar.off = 0; c.ar.high = 0; c.ar.oom = false;
   c.st = (cudaStream_t)stream; c.stream = stream;
+  c.profile = (flags & SGNN_GEN_PROFILE) != 0; c.n_ev = 0;
   int rc = SGNN_OK;
   do {
 #define GEN(call)                 \
@@ -385,6 +402,17 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       out->out_sdf = sdf;
     }
   } while (0);
+  if (c.profile && c.n_ev > 0 && rc == SGNN_OK) {
+    SGNN_CUDA(cudaStreamSynchronize(c.st));
+    double ms = 0;
+    for (int i = 0; i < c.n_ev; i += 2) {
+      float t = 0.f;
+      SGNN_CUDA(cudaEventElapsedTime(&t, g_ev[i], g_ev[i + 1]));
+      ms += t;
+    }
+    out->conv_ms = ms;
+    out->n_conv = c.n_ev / 2;
+  }
   out->arena_used = c.ar.off;
   out->arena_needed = c.ar.high > arena_bytes ? 2 * c.ar.high : c.ar.high;
   if (c.ar.oom && rc == SGNN_OK) rc = SGNN_E_NOMEM;

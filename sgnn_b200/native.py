@@ -113,6 +113,7 @@ class NativeGenerator(object):
         self.arena = None
         self.arena_bytes = int(arena_bytes)
         self.last = None
+        self.profile = False
 
     def _prepare(self, dev):
         m = self.model
@@ -136,7 +137,8 @@ class NativeGenerator(object):
             rc = lib.sgnn_generator_forward(C.byref(self.weights.w), C.c_void_p(locs.data_ptr()),
                                             1 if locs.dtype == torch.int64 else 0, C.c_void_p(feats.data_ptr()),
                                             locs.shape[0], nb, dims, C.c_void_p(self.arena.data_ptr()),
-                                            self.arena.numel(), _lib.GEN_CAND_LOCS if want_cand_locs else 0,
+                                            self.arena.numel(), (_lib.GEN_CAND_LOCS if want_cand_locs else 0) |
+                                            (_lib.GEN_PROFILE if self.profile else 0),
                                             C.byref(out), stream)
             if rc != -6:
                 break
