@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--cpu-reps', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ledger', default='', help='write the per-layer ledger JSON here')
+    ap.add_argument('--conv-impl', type=int, default=0, help='sgnn_debug_set_conv_impl (kernel A/B runs)')
     return ap.parse_args()
 
 
@@ -194,6 +195,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     ones = np.ones(5, dtype=np.float32)
+    lib.sgnn_debug_set_conv_impl(args.conv_impl)
 
     model = sgnn_b200.GenModel(8, 64, 1, 16, 16, 4, True, True, 1, 1)
     if rank == 0:

@@ -562,7 +562,6 @@ static int launch_tile(const ConvParams& p, cudaStream_t st) {
 static int dispatch_tile(const ConvParams& p, cudaStream_t st, bool* handled) {
   const int cinp = (p.cin + 3) & ~3;
   *handled = true;
-  if (p.child_mode && p.cout == 16 && cinp == 48 && (p.n_out & 7) == 0) return launch_child<16, 48>(p, st);
 #define SGNN_TILE_CASE(CO, CI) \
   if (p.cout == CO && cinp == CI) return launch_tile<CO, CI>(p, st);
   SGNN_TILE_CASE(8, 4)
@@ -581,50 +580,75 @@ static int dispatch_tile(const ConvParams& p, cudaStream_t st, bool* handled) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// v3 "constant-weight" kernel.  ncu on v2 (profiles/conv_r1b_*) showed the FFMA pipe at 39 % with the
-// shared-memory pipe saturated: the 4x4 register tile re-reads every weight through LDS.128 at 4 wavefronts
-// per instruction.  Here the filter slice lives in __constant__ memory and reaches the FFMA through the
-// UNIFORM datapath (LDCU -> FFMA R, R, UR, R): no shared-memory traffic for weights at all.  Each thread owns
-// S whole output rows (all Cout accumulators in registers), gathers ITS OWN neighbour rows with cp.async into a
-// private shared-memory ring (lane stride XW words, XW/4 odd -> conflict-free LDS.128/LDGSTS) and therefore
-// needs NO block barrier in the main loop: warps run decoupled.  Neighbour indices are prefetched one stage
-// ahead into registers (coalesced: consecutive lanes = consecutive rows).
-// Arithmetic is unchanged: k ascending, ci ascending, one fmaf chain per output element from +0 (or from the
-// exact partial sums of the previous k-range when the filter bank exceeds the 62 KB constant window).
-#define CW_FLOATS 15872
-__constant__ float c_W[CW_FLOATS];
-
-template <int CIN>
-struct CwCfg {
-  static constexpr int CPR = (CIN + 3) / 4;
-  static constexpr int XW = CPR * 4 + ((CPR % 2 == 0) ? 4 : 0);  // XW/4 odd
+// v4 "row-owner" kernel (default).  History, with the ncu evidence under profiles/:
+//   v2 (4x4 register tile, weights re-read by every lane group through LDS.128): shared-memory pipe saturated,
+//      FFMA pipe 39 %;  v3 (weights in __constant__, LDCU -> FFMA R,R,UR,R): no smem traffic for weights but every
+//      stage touches a fresh 1-3 KB constant slice -> constant-cache MISS latency chain, ~3.3 us per stage, a
+//      90 us floor per launch.
+// v4: each thread owns S whole output rows (all COUT accumulators in registers).  A stage = (filter offset k,
+// 16-channel slice of Cin).  Per stage a WARP gathers its 32*S neighbour-row slices cooperatively (CPR lanes per
+// row, coalesced) into the owners' private slots of a shared-memory ring and its own copy of the W[k] slice
+// (<= 1 KB); the owner then reads its rows with conflict-free LDS.128 (XOR chunk swizzle) and the weights with
+// warp-UNIFORM LDS.128 (one broadcast wavefront).  Only __syncwarp is needed -- no block barrier, warps run
+// decoupled.  Neighbour indices are prefetched one stage ahead (coalesced).  Arithmetic unchanged: k ascending,
+// ci ascending, one fmaf chain per output element from +0.
+template <int CH>
+struct RoCfg {
+  static constexpr int CPR = CH / 4;  // 16-byte chunks per row slice
+  static constexpr int TZ = (CPR % 8 == 0) ? 3 : (CPR % 4 == 0) ? 2 : (CPR % 2 == 0) ? 1 : 0;
 };
+// chunk swizzle of the slice owned by lane l (slices are CPR chunks apart; for even CPR XOR the low TZ bits)
+template <int CH>
+__device__ __forceinline__ int ro_swz(int l) {
+  return (l >> (3 - RoCfg<CH>::TZ)) & ((1 << RoCfg<CH>::TZ) - 1);
+}
 
-template <int COUT, int CIN, int S, int NS>
+template <int COUT, int S, int W>   // one compute step over a W-channel slice (W multiple of 4, compile time)
+__device__ __forceinline__ void ro_compute(float (&acc)[S][COUT], const float* __restrict__ X, int xs_stride,
+                                           int my_sw, const float* __restrict__ Wst) {
+#pragma unroll
+  for (int ch = 0; ch < W / 4; ++ch) {
+    float4 xv[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) xv[s] = *reinterpret_cast<const float4*>(X + (size_t)s * xs_stride + ((ch * 4) ^ my_sw));
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+#pragma unroll
+      for (int co = 0; co < COUT; co += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(Wst + (ch * 4 + e) * COUT + co);  // warp-uniform
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const float x = e == 0 ? xv[s].x : e == 1 ? xv[s].y : e == 2 ? xv[s].z : xv[s].w;
+          acc[s][co] = fmaf(x, wv.x, acc[s][co]);
+          acc[s][co + 1] = fmaf(x, wv.y, acc[s][co + 1]);
+          acc[s][co + 2] = fmaf(x, wv.z, acc[s][co + 2]);
+          acc[s][co + 3] = fmaf(x, wv.w, acc[s][co + 3]);
+        }
+      }
+    }
+  }
+}
+
+// CIN: exact input channels; CH: channels per stage (CINP when CIN <= 16, else 16); S rows per thread; NS ring depth
+template <int COUT, int CIN, int CH, int S, int NS>
 __global__ void __launch_bounds__(128)
-conv_cw_kernel(ConvParams p, int k0, int k1, int vec, const float* acc_in, int ld_acc_in, float* acc_out,
-               int ld_acc_out) {
-  constexpr int CPR = CwCfg<CIN>::CPR;
-  constexpr int XW = CwCfg<CIN>::XW;
-  extern __shared__ __align__(16) float smem[];  // [NS][S][128][XW]
-  const int tid = threadIdx.x;
+conv_ro_kernel(ConvParams p, int vec) {
+  constexpr int CINP = (CIN + 3) & ~3;
+  constexpr int NSUB = (CINP + CH - 1) / CH;          // stages per filter offset
+  constexpr int TAIL = CINP - (NSUB - 1) * CH;         // channels (padded to 4) of the last slice
+  constexpr int CPR = CH / 4;
+  constexpr int XSL = S * 128 * CH;                    // floats: X slots of one stage (whole CTA)
+  constexpr int WSL = 4 * CH * COUT;                   // floats: per-warp W slices of one stage
+  extern __shared__ __align__(16) float smem[];        // [NS][ X: [S][128][CH] | W: [4 warps][CH][COUT] ]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wbase = tid & ~31;
   const long long row0 = (long long)blockIdx.x * (128 * S) + tid;
+  const int my_sw = ro_swz<CH>(lane) << 2;
 
   float acc[S][COUT];
 #pragma unroll
-  for (int s = 0; s < S; ++s) {
-    const long long j = row0 + 128 * s;
-    if (acc_in && j < p.n_out) {
+  for (int s = 0; s < S; ++s)
 #pragma unroll
-      for (int c = 0; c < COUT; c += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(acc_in + j * ld_acc_in + c);
-        acc[s][c] = v.x; acc[s][c + 1] = v.y; acc[s][c + 2] = v.z; acc[s][c + 3] = v.w;
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < COUT; ++c) acc[s][c] = 0.f;
-    }
-  }
+    for (int c = 0; c < COUT; ++c) acc[s][c] = 0.f;
 
   int ir[S];
   auto load_idx = [&](int k) {
@@ -634,82 +658,90 @@ conv_cw_kernel(ConvParams p, int k0, int k1, int vec, const float* acc_in, int l
       ir[s] = j < p.n_out ? conv_src_row(p, j, k) : -1;
     }
   };
-  auto issue = [&](int buf) {
+  // gather of stage (k, sub) into ring slot `buf`; ir[] holds the row indices of offset k
+  auto issue = [&](int k, int sub, int buf) {
+    float* Xb = smem + (size_t)buf * (XSL + WSL);
+    const int c0 = sub * CH;
+    if (vec) {
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-      float* dst = smem + ((size_t)(buf * S + s) * 128 + tid) * XW;
-      const int r = ir[s];
-      if (r >= 0) {
-        const float* src = p.in + (long long)r * p.ld_in;
-        if (vec) {
+      for (int s = 0; s < S; ++s) {
+        float* slot = Xb + ((size_t)s * 128 + wbase) * CH;
 #pragma unroll
-          for (int ch = 0; ch < CPR; ++ch) {
-            if (ch * 4 + 4 <= CIN) {
-              cp_async16(dst + ch * 4, src + ch * 4);
+        for (int it = 0; it < CPR; ++it) {
+          const int q = lane + 32 * it;
+          const int rl = q / CPR, ch = q % CPR;
+          const int r = __shfl_sync(0xffffffffu, ir[s], rl);
+          float* dst = slot + rl * CH + ((ch ^ ro_swz<CH>(rl)) * 4);
+          const int cb = c0 + ch * 4;
+          if (r >= 0 && cb < CIN) {
+            const float* src = p.in + (long long)r * p.ld_in + cb;
+            if (cb + 4 <= CIN) {
+              cp_async16(dst, src);
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                if (ch * 4 + e < CIN) cp_async4(dst + ch * 4 + e, src + ch * 4 + e);
-                else dst[ch * 4 + e] = 0.f;
+                if (cb + e < CIN) cp_async4(dst + e, src + e);
+                else dst[e] = 0.f;
               }
             }
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < CPR * 4; ++e) {
-            if (e < CIN) cp_async4(dst + e, src + e);
-            else dst[e] = 0.f;
+          } else {
+            *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-      } else {
+      }
+    } else {
 #pragma unroll
-        for (int ch = 0; ch < CPR; ++ch) *reinterpret_cast<float4*>(dst + ch * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < S; ++s) {
+        float* dst = Xb + ((size_t)s * 128 + tid) * CH;
+        const int r = ir[s];
+        const int sw = ro_swz<CH>(lane);
+#pragma unroll
+        for (int e = 0; e < CH; ++e) {
+          float* d = dst + (((e >> 2) ^ sw) << 2) + (e & 3);
+          if (r >= 0 && c0 + e < CIN) cp_async4(d, p.in + (long long)r * p.ld_in + c0 + e);
+          else *d = 0.f;
+        }
       }
     }
+    // this warp's copy of the filter slice W[k][c0 .. c0+CH) (contiguous in global memory)
+    float* Wd = Xb + XSL + warp * (CH * COUT);
+    const int wn = min(CH, CIN - c0) * COUT / 4;  // 16-byte chunks (COUT % 4 == 0)
+    const float* Wk = p.weight + ((size_t)k * CIN + c0) * COUT;
+    for (int q = lane; q < wn; q += 32) cp_async16(Wd + q * 4, Wk + q * 4);
+    if (CINP != CIN && sub == NSUB - 1)   // weight rows of the channel padding (ring slots are reused: zero each time)
+      for (int q = (CIN - (NSUB - 1) * CH) * COUT + lane; q < TAIL * COUT; q += 32) Wd[q] = 0.f;
   };
 
-  int kk = k0;
-  if (kk < k1) load_idx(kk);
+  const int total = p.K * NSUB;
+  int ik = 0, isub = 0, issued = 0;   // next stage to issue
+  load_idx(0);
 #pragma unroll
   for (int i = 0; i < NS - 1; ++i) {
-    if (kk < k1) {
-      issue(i);
-      ++kk;
-      if (kk < k1) load_idx(kk);
+    if (issued < total) {
+      issue(ik, isub, i);
+      ++issued;
+      if (++isub == NSUB) { isub = 0; ++ik; if (ik < p.K) load_idx(ik); }
     }
     cp_async_commit();
   }
-  for (int k = k0; k < k1; ++k) {
+  int st = 0, fill = NS - 1, csub = 0;
+  for (int t = 0; t < total; ++t) {
     cp_async_wait<NS - 2>();
-    const int st = (k - k0) % NS;
-    if (kk < k1) {
-      issue((k - k0 + NS - 1) % NS);
-      ++kk;
-      if (kk < k1) load_idx(kk);
+    __syncwarp();  // stage t landed for every lane of this warp; all lanes are done with the slot refilled below
+    if (issued < total) {
+      issue(ik, isub, fill);
+      ++issued;
+      if (++isub == NSUB) { isub = 0; ++ik; if (ik < p.K) load_idx(ik); }
     }
     cp_async_commit();
-    const float* W = c_W + (k - k0) * (CIN * COUT);
-    const float* X = smem + ((size_t)(st * S) * 128 + tid) * XW;
-#pragma unroll
-    for (int ch = 0; ch < CPR; ++ch) {
-      float4 xv[S];
-#pragma unroll
-      for (int s = 0; s < S; ++s) xv[s] = *reinterpret_cast<const float4*>(X + (size_t)s * 128 * XW + ch * 4);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (ch * 4 + e < CIN) {
-#pragma unroll
-          for (int co = 0; co < COUT; ++co) {
-            const float wv = W[(ch * 4 + e) * COUT + co];
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              const float x = e == 0 ? xv[s].x : e == 1 ? xv[s].y : e == 2 ? xv[s].z : xv[s].w;
-              acc[s][co] = fmaf(x, wv, acc[s][co]);
-            }
-          }
-        }
-      }
-    }
+    const float* Xb = smem + (size_t)st * (XSL + WSL);
+    const float* X = Xb + (size_t)tid * CH;
+    const float* Wst = Xb + XSL + warp * (CH * COUT);
+    if (csub < NSUB - 1) ro_compute<COUT, S, CH>(acc, X, 128 * CH, my_sw, Wst);
+    else ro_compute<COUT, S, TAIL>(acc, X, 128 * CH, my_sw, Wst);
+    if (++csub == NSUB) csub = 0;
+    st = st + 1 == NS ? 0 : st + 1;
+    fill = fill + 1 == NS ? 0 : fill + 1;
   }
   cp_async_wait<0>();
 
@@ -718,13 +750,6 @@ conv_cw_kernel(ConvParams p, int k0, int k1, int vec, const float* acc_in, int l
   for (int s = 0; s < S; ++s) {
     const long long j = row0 + 128 * s;
     if (j >= p.n_out) continue;
-    if (acc_out) {
-#pragma unroll
-      for (int c = 0; c < COUT; c += 4)
-        *reinterpret_cast<float4*>(acc_out + j * ld_acc_out + c) =
-            make_float4(acc[s][c], acc[s][c + 1], acc[s][c + 2], acc[s][c + 3]);
-      continue;
-    }
 #pragma unroll
     for (int c = 0; c < COUT; c += 4) {
       float4 v = make_float4(acc[s][c], acc[s][c + 1], acc[s][c + 2], acc[s][c + 3]);
@@ -756,51 +781,46 @@ conv_cw_kernel(ConvParams p, int k0, int k1, int vec, const float* acc_in, int l
   }
 }
 
-template <int COUT, int CIN, int S>
-static int launch_cw(const ConvParams& p, bool vec, cudaStream_t st) {
-  constexpr int XW = CwCfg<CIN>::XW;
-  constexpr int NS = (3 * S * 128 * XW * 4 <= 72 * 1024) ? 3 : 2;
-  const size_t smem = (size_t)NS * S * 128 * XW * sizeof(float);
+template <int COUT, int CIN, int S, int CH>
+static int launch_ro(const ConvParams& p, bool vec, cudaStream_t st) {
+  constexpr int STAGE = (S * 128 * CH + 4 * CH * COUT) * 4;
+  constexpr int NS = (3 * STAGE <= 60 * 1024) ? 3 : 2;
+  const size_t smem = (size_t)NS * STAGE;
   const long long tiles = (p.n_out + 128 * S - 1) / (128 * S);
   if (tiles > 0x7fffffff) return SGNN_E_TOO_LARGE;
   static bool attr_set = false;
   if (!attr_set) {
-    SGNN_CUDA(cudaFuncSetAttribute(conv_cw_kernel<COUT, CIN, S, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SGNN_CUDA(cudaFuncSetAttribute(conv_ro_kernel<COUT, CIN, CH, S, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
     attr_set = true;
   }
-  const int per_k = CIN * COUT;
-  const int kmax = CW_FLOATS / per_k;
-  float* accbuf = p.out_a ? p.out_a : p.out_b;
-  const int ld_acc = p.out_a ? p.ld_a : p.ld_b;
-  for (int k0 = 0; k0 < p.K; k0 += kmax) {
-    const int k1 = k0 + kmax < p.K ? k0 + kmax : p.K;
-    SGNN_CUDA(cudaMemcpyToSymbolAsync(c_W, p.weight + (size_t)k0 * per_k, (size_t)(k1 - k0) * per_k * sizeof(float), 0,
-                                      cudaMemcpyDeviceToDevice, st));
-    const bool first = k0 == 0, last = k1 == p.K;
-    conv_cw_kernel<COUT, CIN, S, NS><<<(int)tiles, 128, smem, st>>>(p, k0, k1, vec ? 1 : 0, first ? nullptr : accbuf,
-                                                                    ld_acc, last ? nullptr : accbuf, ld_acc);
-    SGNN_CHECK_LAUNCH();
-  }
+  conv_ro_kernel<COUT, CIN, CH, S, NS><<<(int)tiles, 128, smem, st>>>(p, vec ? 1 : 0);
+  SGNN_CHECK_LAUNCH();
   return SGNN_OK;
 }
 
 // exact (cin, cout) pairs of the SG-NN channel plan
-static int dispatch_cw(const ConvParams& p, bool vec, cudaStream_t st, bool* handled) {
+static int dispatch_ro(const ConvParams& p, bool vec, cudaStream_t st, bool* handled, int alt) {
   *handled = true;
-#define SGNN_CW_CASE(CO, CI, SS) \
-  if (p.cout == CO && p.cin == CI) return launch_cw<CO, CI, SS>(p, vec, st);
-  SGNN_CW_CASE(8, 1, 4)
-  SGNN_CW_CASE(8, 8, 4)
-  SGNN_CW_CASE(12, 8, 2)
-  SGNN_CW_CASE(12, 12, 2)
-  SGNN_CW_CASE(16, 12, 2)
-  SGNN_CW_CASE(16, 16, 2)
-  SGNN_CW_CASE(16, 26, 2)
-  SGNN_CW_CASE(16, 30, 2)
-  SGNN_CW_CASE(16, 34, 2)
-  SGNN_CW_CASE(16, 48, 2)
-#undef SGNN_CW_CASE
+#define SGNN_RO_CASE(CO, CI, SS, CHH) \
+  if (p.cout == CO && p.cin == CI) return launch_ro<CO, CI, SS, CHH>(p, vec, st);
+  SGNN_RO_CASE(8, 1, 4, 4)
+  SGNN_RO_CASE(8, 8, 4, 8)
+  SGNN_RO_CASE(12, 8, 4, 8)
+  SGNN_RO_CASE(12, 12, 4, 12)
+  SGNN_RO_CASE(16, 12, 4, 12)
+  SGNN_RO_CASE(16, 16, 4, 16)
+  if (alt) {   // wide inputs: one stage per offset (whole padded row), 2 rows per thread
+    SGNN_RO_CASE(16, 26, 2, 28)
+    SGNN_RO_CASE(16, 30, 2, 32)
+    SGNN_RO_CASE(16, 34, 2, 36)
+    SGNN_RO_CASE(16, 48, 2, 24)
+  }
+  SGNN_RO_CASE(16, 26, 4, 16)
+  SGNN_RO_CASE(16, 30, 4, 16)
+  SGNN_RO_CASE(16, 34, 4, 16)
+  SGNN_RO_CASE(16, 48, 4, 16)
+#undef SGNN_RO_CASE
   *handled = false;
   return SGNN_OK;
 }
@@ -837,7 +857,9 @@ __global__ void conv_gather_f32_generic_kernel(ConvParams p) {
   }
 }
 
-// 0: v3 constant-weight kernel (default); 1: v2 tile kernels; 2: v1 runtime-shape kernel.  Test hook.
+// 0 (default): v4 row-owner kernel, whole-row stages for wide inputs, parent-staged kernel for child mode;
+// 1: v2 tile kernels; 2: v1 runtime-shape kernel; 3: v4 only (whole-row stages for wide inputs); 4: v4 with
+// 16-channel sub-stages + child kernel; 5: v4 with 16-channel sub-stages only.  Tuning hook, all bit-identical.
 int g_sgnn_conv_impl = 0;
 extern "C" void sgnn_debug_set_conv_impl(int v) { g_sgnn_conv_impl = v; }
 
@@ -899,8 +921,11 @@ extern "C" int sgnn_conv_forward(const SgnnConvArgs* a, void* stream) {
     const bool vec = aligned16(a->in) && (a->ld_in & 3) == 0;
     {
       bool handled = false;
-      if (g_sgnn_conv_impl == 0) {
-        rc = dispatch_cw(p, vec, st, &handled);
+      if ((g_sgnn_conv_impl == 0 || g_sgnn_conv_impl == 4) && vec && p.child_mode && p.cout == 16 && p.cin == 48 &&
+          (p.n_out & 7) == 0)
+        return launch_child<16, 48>(p, st);
+      if (g_sgnn_conv_impl == 0 || g_sgnn_conv_impl >= 3) {
+        rc = dispatch_ro(p, vec, st, &handled, g_sgnn_conv_impl == 0 || g_sgnn_conv_impl == 3);
         if (handled) return rc;
       }
       if (vec && g_sgnn_conv_impl <= 1) {
