@@ -46,25 +46,34 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------ reference arm
+def cpu_threads():
+    """Threads for the CPU arm: all host cores up to 16 -- beyond that the restated scn path (many small torch ops)
+    gets SLOWER from intra-op oversubscription (69 s per block with 128 threads on the GPU box vs 0.5 s with 8)."""
+    return max(1, min(os.cpu_count() or 1, 16))
+
+
 def cpu_forward_rate(n_blocks, reps, seed, first_block=0):
     """Times the oracle port of the reference CPU path (oracle/genmodel.py on oracle/sparseconvnet).
     This is the ONE place bench.py executes oracle code: as the thing the B200 arm is compared with."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     from genmodel import OracleGenModel
     from sgnn_b200.synth import fill_parameters, synthetic_batch
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     m = OracleGenModel()
     fill_parameters(m, seed)
     m.eval()
     locs, feats = synthetic_batch(n_blocks, 64, 0.05, first=first_block)
     times = []
+    t_start = time.perf_counter()
     with torch.no_grad():
         m(locs, feats)                      # warm-up (allocator, thread pool)
         for _ in range(reps):
             t0 = time.perf_counter()
             m(locs, feats)
             times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_start > 45:      # bounded sample: stop after ~45 s of CPU work
+                break
     t = float(np.median(times))
     return locs.shape[0] / t, t, cores, locs.shape[0]
 
@@ -77,7 +86,7 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     from genmodel import OracleGenModel
     from sgnn_b200.synth import fill_parameters, synthetic_batch
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     m = OracleGenModel()
     fill_parameters(m, args.param_seed)

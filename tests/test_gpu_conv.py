@@ -238,3 +238,31 @@ def test_dense_unet_layers_bit_exact(transposed, c0, c1, cout, k, s, p, dims):
     assert torch.allclose(got.cpu(), ref, atol=2e-5, rtol=1e-5)
     raw = E.dense_conv(x0.cuda(), x1.cuda() if c1 else None, w.cuda(), cout, k, s, p, transposed=transposed)
     assert torch.equal(raw.cpu(), o3.dense_conv(xcat, w, k, s, p, transposed=transposed))
+
+
+@pytest.mark.parametrize('impl', [0, 1, 2, 3, 4, 5])
+def test_all_conv_implementations_bit_identical(impl):
+    """Every convolution kernel generation (v1 runtime-shape, v2 tile, v4 row-owner, child-mode) computes the SAME
+    fmaf chains: results are bit-identical to O3 whichever the dispatcher picks."""
+    E = _E()
+    from sgnn_b200._lib import lib
+    rng, c, dims, nb = _site_case(77, dims=(9, 8, 11), occ=0.45)
+    n = c.shape[0]
+    nbr = torch.from_numpy(nbr_table(c))
+    try:
+        lib.sgnn_debug_set_conv_impl(impl)
+        for cin, cout, child in [(16, 16, False), (34, 16, False), (26, 16, False), (48, 16, True), (8, 12, False)]:
+            ld = (cin + 3) // 4 * 4
+            xb = torch.zeros((n, ld))
+            xb[:, :cin] = torch.from_numpy(rng.standard_normal((n, cin)).astype(np.float32))
+            w = torch.from_numpy((rng.standard_normal((27, cin, cout)) * 0.1).astype(np.float32))
+            r = torch.from_numpy(rng.standard_normal(((8 if child else 1) * n, cout)).astype(np.float32))
+            s_, t_ = torch.rand(cout) + 0.5, torch.rand(cout) - 0.5
+            no = 8 * n if child else n
+            want = o3.conv(xb[:, :cin], nbr, w, no, child_mode=child, residual=r, scale=s_, shift=t_, relu=True)
+            out = torch.empty((no, cout), device='cuda')
+            E.conv(xb.cuda()[:, :cin], nbr.cuda(), w.cuda(), no, out, child_mode=child, residual=r.cuda(),
+                   scale_a=s_.cuda(), shift_a=t_.cuda(), relu_a=True)
+            assert torch.equal(out.cpu(), want), (impl, cin, cout, child)
+    finally:
+        lib.sgnn_debug_set_conv_impl(0)

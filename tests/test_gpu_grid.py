@@ -108,3 +108,59 @@ def test_rulebook_properties_at_baseline_size():
         assert torch.equal(nbr[26 - k][i].long(), j)
     r = int((nbr >= 0).sum().item())
     assert 2.0 * n < r < 2.7 * n                      # 1 + 26 * 0.05 rules per site
+
+
+def test_rulebook_microbench_size_properties():
+    """BASELINE.json configs[4]: ~10 M active sites (763 blocks of 64^3 @5 %), 3^3 submanifold rulebook.
+    Size-independent properties: centre offset is the identity, the table is symmetric, rule count ~ 1 + 26*0.05."""
+    E = _E()
+    nb = 763
+    g = torch.Generator(device='cuda').manual_seed(1234)
+    mask = torch.rand((nb, 64, 64, 64), device='cuda', generator=g) < 0.05
+    coords = torch.nonzero(mask)[:, [1, 2, 3, 0]].contiguous()         # (z,y,x,b), batch-major raster order
+    n = coords.shape[0]
+    assert 9.5e6 < n < 10.5e6
+    del mask
+    grid = E.build_grid(coords, nb, (64, 64, 64))
+    assert int(grid.prefix[grid.n_words].item()) == n
+    nbr = E.rulebook_submanifold(grid)
+    assert torch.equal(nbr[13], torch.arange(n, device='cuda', dtype=torch.int32))
+    for k in (0, 4, 12):
+        j = torch.nonzero(nbr[k] >= 0).view(-1)
+        i = nbr[k][j].long()
+        assert torch.equal(nbr[26 - k][i].long(), j)
+    r = int((nbr >= 0).sum().item())
+    assert 2.2 * n < r < 2.4 * n
+    # coarse set: every site has exactly one parent, children tables invert the parent table
+    cg = E.coarsen(grid)
+    parent, children = E.rulebook_strided(grid, cg)
+    assert int((parent < 0).sum().item()) == 0
+    k = (parent & 7).long()
+    row = (parent >> 3).long()
+    assert torch.equal(children[k, row].long(), torch.arange(n, device='cuda'))
+
+
+def test_config2_block_128_conv_deconv_pair():
+    """BASELINE.json configs[2] geometry: one 128^3 block @3 %, C=16 stride-2 Convolution then Deconvolution back to
+    the fine set (fp32 here; the bf16 tensor-core variant is round-2 work).  Checked against the dense identities."""
+    import dense_equiv as o1
+    E = _E()
+    rng = np.random.default_rng(1234)
+    mask = rng.random((128, 128, 128)) < 0.03
+    c = np.ascontiguousarray(np.concatenate([np.argwhere(mask), np.zeros((int(mask.sum()), 1), dtype=np.int64)], 1))
+    n = c.shape[0]
+    x = torch.from_numpy(rng.standard_normal((n, 16)).astype(np.float32))
+    wc = torch.from_numpy((rng.standard_normal((8, 16, 16)) * 0.2).astype(np.float32))
+    wd = torch.from_numpy((rng.standard_normal((8, 16, 16)) * 0.2).astype(np.float32))
+    g = E.build_grid(torch.from_numpy(c).cuda(), 1, (128, 128, 128))
+    cg = E.coarsen(g)
+    parent, children = E.rulebook_strided(g, cg)
+    y = torch.empty((cg.n, 16), device='cuda')
+    E.conv(x.cuda(), children, wc.cuda(), cg.n, y)
+    z = torch.empty((n, 16), device='cuda')
+    E.deconv(y, parent, wd.cuda(), z)
+    cc = cg.coords.cpu().long()
+    want_y = o1.strided_conv(torch.from_numpy(c), x, wc, 1, (128, 128, 128), cc)
+    assert torch.allclose(y.cpu(), want_y, atol=1e-4, rtol=1e-4)
+    want_z = o1.strided_deconv(cc, want_y, wd, 1, (64, 64, 64), torch.from_numpy(c))
+    assert torch.allclose(z.cpu(), want_z, atol=1e-4, rtol=1e-4)
