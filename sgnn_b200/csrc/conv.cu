@@ -894,8 +894,16 @@ static int check_epilogue(const SgnnEpilogue& e, bool need_vec) {
   return SGNN_OK;
 }
 
+int sgnn_conv_tc_bf16(const void* in, int ld_in, const int* tbl, long long tbl_stride, int K, int mode, const void* w,
+                      int cin, int cout, long long n_out, const SgnnEpilogue* ep, cudaStream_t st);  // conv_tc.cu
+
 extern "C" int sgnn_conv_forward(const SgnnConvArgs* a, void* stream) {
   if (!a || a->n_out < 0 || a->cin <= 0 || a->cout <= 0 || !a->weight) return SGNN_E_INVALID;
+  if (a->dtype == SGNN_BF16) {   // tcgen05 path (conv_tc.cu): bf16 features/weights/outputs, fp32 accumulation in TMEM
+    if (a->child_mode || a->residual || a->b.out) return SGNN_E_UNSUPPORTED;
+    return sgnn_conv_tc_bf16(a->in, a->ld_in, a->nbr, a->nbr_stride, a->K, 0, a->weight, a->cin, a->cout, a->n_out,
+                             &a->a, (cudaStream_t)stream);
+  }
   if (a->dtype != SGNN_F32) return SGNN_E_UNSUPPORTED;
   if (a->K != 27 && a->K != 8) return SGNN_E_UNSUPPORTED;
   if (a->child_mode && a->K != 27) return SGNN_E_INVALID;
@@ -976,6 +984,8 @@ extern "C" int sgnn_deconv_forward(const void* in, int32_t ld_in, int32_t dtype,
                                    const void* weight, int32_t cin, int32_t cout, int64_t n_fine,
                                    const SgnnEpilogue* ep, void* stream) {
   if (n_fine < 0 || cin <= 0 || cout <= 0 || !ep || !ep->out || !weight) return SGNN_E_INVALID;
+  if (dtype == SGNN_BF16)
+    return sgnn_conv_tc_bf16(in, ld_in, parent, 0, 8, 1, weight, cin, cout, n_fine, ep, (cudaStream_t)stream);
   if (dtype != SGNN_F32) return SGNN_E_UNSUPPORTED;
   if ((ep->scale == nullptr) != (ep->shift == nullptr)) return SGNN_E_INVALID;
   if (n_fine == 0) return SGNN_OK;

@@ -137,7 +137,7 @@ def _epilogue(out, scale=None, shift=None, relu=False):
         e.out, e.ld, e.relu, e.scale, e.shift = None, 0, 0, None, None
         return e
     _need_cuda(out, scale, shift)
-    assert out.dtype == torch.float32 and out.stride(-1) == 1
+    assert out.dtype in (torch.float32, torch.bfloat16) and out.stride(-1) == 1
     e.out = out.data_ptr()
     e.ld = out.stride(0) if out.dim() == 2 else 1
     e.relu = 1 if relu else 0
@@ -152,13 +152,13 @@ def conv(x, nbr, weight, n_out, out_a, child_mode=False, residual=None, scale_a=
     x / out_* may be column views of wider row-major buffers (stride(1) == 1)."""
     _need_cuda(x, nbr, weight, out_a, residual, out_b)
     K, cin, cout = weight.shape
-    assert weight.is_contiguous() and weight.dtype == torch.float32
-    assert x.dtype == torch.float32 and x.stride(1) == 1 and x.shape[1] == cin
+    assert weight.is_contiguous() and weight.dtype in (torch.float32, torch.bfloat16)
+    assert x.dtype == weight.dtype == out_a.dtype and x.stride(1) == 1 and x.shape[1] == cin
     assert nbr.dtype == torch.int32 and nbr.shape[0] == K and nbr.stride(1) == 1
     a = SgnnConvArgs()
     a.in_ = x.data_ptr()
     a.ld_in = x.stride(0)
-    a.dtype = _lib.SGNN_F32
+    a.dtype = _lib.SGNN_BF16 if x.dtype == torch.bfloat16 else _lib.SGNN_F32
     a.nbr = nbr.data_ptr()
     a.nbr_stride = nbr.stride(0)
     a.K = K
@@ -188,7 +188,9 @@ def deconv(x, parent, weight, out, scale=None, shift=None, relu=False):
     K, cin, cout = weight.shape
     assert K == 8 and x.stride(1) == 1
     e = _epilogue(out, scale, shift, relu)
-    check(lib.sgnn_deconv_forward(_ptr(x), x.stride(0), _lib.SGNN_F32, _ptr(parent), _ptr(weight), cin, cout,
+    dt = _lib.SGNN_BF16 if x.dtype == torch.bfloat16 else _lib.SGNN_F32
+    assert x.dtype == weight.dtype == out.dtype
+    check(lib.sgnn_deconv_forward(_ptr(x), x.stride(0), dt, _ptr(parent), _ptr(weight), cin, cout,
                                   parent.shape[0], C.byref(e), _stream()), 'sgnn_deconv_forward')
     return out
 
