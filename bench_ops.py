@@ -1,0 +1,125 @@
+#!/usr/bin/env python
+"""Operator microbenchmarks for the non-headline BASELINE.json configs (one JSON line each, CUDA-event timed):
+
+  configs[4]  rulebook build, ~10 M active voxels (763 blocks of 64^3 @5 %), 3^3 submanifold:
+              grid build (bitmask + popcount ranks) + neighbour table, GB/s against the HBM roofline
+  configs[2]  one 128^3 block @3 % (and a 32-block batch for stable timing), bf16 features, C=16
+              Convolution(k2,s2) + Deconvolution(k2,s2) on the tcgen05 path
+  ffma        sustained 3-register FFMA rate (roofline denominator of the fp32 convolution)
+
+The headline metric lives in bench.py; this file feeds DESIGN.md §5 and the ncu captures under profiles/.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def timed(fn, reps, flush):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ms = []
+    for i in range(reps):
+        flush.fill_(i & 0xff)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    ms.sort()
+    return ms[len(ms) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--which', default='all')
+    ap.add_argument('--reps', type=int, default=10)
+    args = ap.parse_args()
+    import sgnn_b200.engine as E
+    from sgnn_b200._lib import lib
+    dev = torch.device('cuda', 0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm = float(peaks.get('hbm_gbs', 6650.0))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    if args.which in ('all', 'ffma'):
+        t = C.c_double(0)
+        lib.sgnn_debug_ffma_peak(20000, C.byref(t), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        print(json.dumps({'bench': 'ffma_peak', 'tflops_measured': t.value,
+                          'tflops_nominal': 148 * 128 * 2 * 1.965e9 / 1e12}))
+
+    if args.which in ('all', 'rulebook'):
+        nb = 763
+        g = torch.Generator(device=dev).manual_seed(1234)
+        mask = torch.rand((nb, 64, 64, 64), device=dev, generator=g) < 0.05
+        coords = torch.nonzero(mask)[:, [1, 2, 3, 0]].contiguous().int()
+        del mask
+        n = coords.shape[0]
+        state = {}
+
+        def build():
+            state['g'] = E.build_grid(coords, nb, (64, 64, 64))
+
+        def rules():
+            state['nbr'] = E.rulebook_submanifold(state['g'])
+        t_build = timed(build, args.reps, flush)
+        t_rules = timed(rules, args.reps, flush)
+        r = int((state['nbr'] >= 0).sum().item())
+        # SURVEY 8(d) algorithmic bytes (hash design): 16N in + 12N slots + 26*8N probes + 8R pairs
+        alg = 16 * n + 12 * n + 208 * n + 8 * r
+        # bytes this design must move: coords 16N (in) + 16N (int32 copy) + 4N (rank->row) + mask/prefix, table 108N
+        mine = 16 * n + 16 * n + 4 * n + state['g'].n_words * 12 + 108 * n
+        t = t_build + t_rules
+        print(json.dumps({'bench': 'configs[4] rulebook build', 'sites': n, 'rules': r,
+                          'ms_grid_build': t_build, 'ms_neighbour_table': t_rules, 'sites_per_s': n / (t * 1e-3),
+                          'algorithmic_GBps_survey_formula': alg / (t * 1e-3) / 1e9,
+                          'frac_of_hbm_survey_formula': alg / (t * 1e-3) / 1e9 / hbm,
+                          'design_bytes_GBps': mine / (t * 1e-3) / 1e9, 'frac_of_hbm_design_bytes': mine / (t * 1e-3) / 1e9 / hbm,
+                          'hbm_peak_GBps': hbm}))
+        del state, coords
+
+    if args.which in ('all', 'config2'):
+        for nblk in (1, 32):
+            g = torch.Generator(device=dev).manual_seed(1234)
+            mask = torch.rand((nblk, 128, 128, 128), device=dev, generator=g) < 0.03
+            coords = torch.nonzero(mask)[:, [1, 2, 3, 0]].contiguous().int()
+            del mask
+            n = coords.shape[0]
+            grid = E.build_grid(coords, nblk, (128, 128, 128))
+            cg = E.coarsen(grid)
+            parent, children = E.rulebook_strided(grid, cg)
+            x = torch.randn((n, 16), device=dev).bfloat16()
+            wc = (torch.randn((8, 16, 16), device=dev) * 0.2).bfloat16()
+            wd = (torch.randn((8, 16, 16), device=dev) * 0.2).bfloat16()
+            y = torch.empty((cg.n, 16), dtype=torch.bfloat16, device=dev)
+            z = torch.empty((n, 16), dtype=torch.bfloat16, device=dev)
+            t_conv = timed(lambda: E.conv(x, children, wc, cg.n, y), args.reps, flush)
+            t_dec = timed(lambda: E.deconv(y, parent, wd, z), args.reps, flush)
+            b_conv = (n * 16 + cg.n * 16) * 2 + 8 * n + 8 * 16 * 16 * 2
+            b_dec = (cg.n * 16 + n * 16) * 2 + 8 * n + 8 * 16 * 16 * 2
+            # fp32 FFMA path on the same geometry for comparison
+            xf, wcf, yf = x.float(), wc.float(), torch.empty((cg.n, 16), device=dev)
+            t_f32 = timed(lambda: E.conv(xf, children, wcf, cg.n, yf), args.reps, flush)
+            print(json.dumps({'bench': 'configs[2] bf16 tcgen05 conv+deconv', 'blocks_128cubed': nblk, 'fine_sites': n,
+                              'coarse_sites': cg.n, 'ms_conv': t_conv, 'ms_deconv': t_dec,
+                              'conv_GBps': b_conv / (t_conv * 1e-3) / 1e9, 'deconv_GBps': b_dec / (t_dec * 1e-3) / 1e9,
+                              'conv_frac_of_hbm': b_conv / (t_conv * 1e-3) / 1e9 / hbm,
+                              'deconv_frac_of_hbm': b_dec / (t_dec * 1e-3) / 1e9 / hbm,
+                              'conv_tflops': 2.0 * n * 256 / (t_conv * 1e-3) / 1e12,
+                              'ms_conv_fp32_ffma_same_geometry': t_f32, 'hbm_peak_GBps': hbm}))
+
+
+if __name__ == '__main__':
+    main()

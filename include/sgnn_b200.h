@@ -297,6 +297,9 @@ int64_t sgnn_launch_count(void);
  * 2 = runtime-shape kernel).  All give bit-identical results. */
 void sgnn_debug_set_conv_impl(int impl);
 
+/* Measures the sustained 3-register FFMA rate of the device (TFLOP/s): roofline denominator of the fp32 kernels. */
+int sgnn_debug_ffma_peak(int iters, double* tflops, void* stream);
+
 int sgnn_version(void);
 const char* sgnn_error_string(int code);
 int sgnn_last_cuda_error(void);

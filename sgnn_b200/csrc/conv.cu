@@ -802,24 +802,42 @@ static int launch_ro(const ConvParams& p, bool vec, cudaStream_t st) {
 // exact (cin, cout) pairs of the SG-NN channel plan
 static int dispatch_ro(const ConvParams& p, bool vec, cudaStream_t st, bool* handled, int alt) {
   *handled = true;
+  // Rows per thread by launch size: S=4 amortises the weight reads best but makes 512-row CTAs; a launch that cannot
+  // fill the chip (148 SMs x 3 CTAs) with those is latency bound (ncu: 45-80 us floors on the coarse levels), so
+  // mid-size launches use S=2 and small ones S=1 (4x more, 4x shorter CTAs).
+  const int sz = p.n_out >= 300000 ? 4 : (p.n_out >= 90000 ? 2 : 1);
 #define SGNN_RO_CASE(CO, CI, SS, CHH) \
   if (p.cout == CO && p.cin == CI) return launch_ro<CO, CI, SS, CHH>(p, vec, st);
-  SGNN_RO_CASE(8, 1, 4, 4)
-  SGNN_RO_CASE(8, 8, 4, 8)
-  SGNN_RO_CASE(12, 8, 4, 8)
-  SGNN_RO_CASE(12, 12, 4, 12)
-  SGNN_RO_CASE(16, 12, 4, 12)
-  SGNN_RO_CASE(16, 16, 4, 16)
-  if (alt) {   // wide inputs: one stage per offset (whole padded row), 2 rows per thread
-    SGNN_RO_CASE(16, 26, 2, 28)
-    SGNN_RO_CASE(16, 30, 2, 32)
-    SGNN_RO_CASE(16, 34, 2, 36)
-    SGNN_RO_CASE(16, 48, 2, 24)
+#define SGNN_RO_SIZED(CO, CI, CHH)              \
+  if (p.cout == CO && p.cin == CI) {            \
+    if (sz == 4) return launch_ro<CO, CI, 4, CHH>(p, vec, st); \
+    if (sz == 2) return launch_ro<CO, CI, 2, CHH>(p, vec, st); \
+    return launch_ro<CO, CI, 1, CHH>(p, vec, st);              \
+  }
+  SGNN_RO_SIZED(8, 1, 4)
+  SGNN_RO_SIZED(8, 8, 8)
+  SGNN_RO_SIZED(12, 8, 8)
+  SGNN_RO_SIZED(12, 12, 12)
+  SGNN_RO_SIZED(16, 12, 12)
+  SGNN_RO_SIZED(16, 16, 16)
+  if (alt) {   // wide inputs: one stage per offset (whole padded row)
+    if (sz >= 2) {
+      SGNN_RO_CASE(16, 26, 2, 28)
+      SGNN_RO_CASE(16, 30, 2, 32)
+      SGNN_RO_CASE(16, 34, 2, 36)
+      SGNN_RO_CASE(16, 48, 2, 24)
+    } else {
+      SGNN_RO_CASE(16, 26, 1, 28)
+      SGNN_RO_CASE(16, 30, 1, 32)
+      SGNN_RO_CASE(16, 34, 1, 36)
+      SGNN_RO_CASE(16, 48, 1, 24)
+    }
   }
   SGNN_RO_CASE(16, 26, 4, 16)
   SGNN_RO_CASE(16, 30, 4, 16)
   SGNN_RO_CASE(16, 34, 4, 16)
   SGNN_RO_CASE(16, 48, 4, 16)
+#undef SGNN_RO_SIZED
 #undef SGNN_RO_CASE
   *handled = false;
   return SGNN_OK;

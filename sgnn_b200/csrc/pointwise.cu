@@ -131,3 +131,49 @@ extern "C" int sgnn_sparse_to_dense(const float* feats, int32_t ld, const int32_
   SGNN_CHECK_LAUNCH();
   return SGNN_OK;
 }
+
+// ------------------------------------------------------------ measured FFMA ceiling (bench.py roofline denominator)
+// 3-register FFMAs, 16 independent chains per thread, operands in registers: what the fp32 pipe of this part
+// actually sustains (the fp32 convolution is FFMA bound, not HBM bound -- DESIGN.md §5).
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float a, float b) {
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = (float)(threadIdx.x + i);
+  float x = a + threadIdx.x * 1e-9f, y = b;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], x, y);
+      x += 1e-9f;
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  if (s == 123.456f) out[0] = s;
+}
+
+extern "C" int sgnn_debug_ffma_peak(int iters, double* tflops, void* stream) {
+  if (!tflops || iters <= 0) return SGNN_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* d = nullptr;
+  SGNN_CUDA(cudaMalloc(&d, 4));
+  cudaEvent_t e0, e1;
+  SGNN_CUDA(cudaEventCreate(&e0));
+  SGNN_CUDA(cudaEventCreate(&e1));
+  const int blocks = 148 * 8;
+  ffma_peak_kernel<<<blocks, 256, 0, st>>>(d, 16, 1.0001f, 0.5f);   // warm-up
+  SGNN_CUDA(cudaEventRecord(e0, st));
+  ffma_peak_kernel<<<blocks, 256, 0, st>>>(d, iters, 1.0001f, 0.5f);
+  SGNN_CHECK_LAUNCH();
+  SGNN_CUDA(cudaEventRecord(e1, st));
+  SGNN_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  SGNN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *tflops = 2.0 * 128.0 * (double)iters * blocks * 256 / (ms * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return SGNN_OK;
+}
