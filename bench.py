@@ -326,6 +326,10 @@ def run_b200(args):
     sampler.join(2)
 
     # ---- roofline of the dominant kernel (conv_gather_f32_kernel, all shapes): algorithmic bytes / measured time
+    import ctypes
+    _t = ctypes.c_double(0)
+    lib.sgnn_debug_ffma_peak(5000, ctypes.byref(_t), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    ffma_meas = _t.value
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -346,7 +350,7 @@ def run_b200(args):
     alg_bytes_total = per_set_bytes * args.steps
     achieved = alg_bytes_total / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0
     roofline = {
-        'kernel': 'conv_tile_f32_kernel / conv_gather_f32_kernel (all %d sgnn_conv_forward launches per step)'
+        'kernel': 'sgnn_conv_forward = conv_ro_kernel<COUT,CIN,..> + conv_child_f32_kernel (all %d launches per step)'
                   % round(convs_per_step),
         'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
         'traffic': None, 'peak_source': peak_src,
@@ -357,6 +361,7 @@ def run_b200(args):
         'gflops_per_step': per_set_flops / 1e9,
         'achieved_tflops_fp32': per_set_flops * args.steps / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0,
         'fp32_ffma_peak_tflops': 148 * 128 * 2 * 1.965e9 / 1e12,
+        'fp32_ffma_peak_tflops_measured': ffma_meas,
         'note': 'fp32 FFMA path: activations are L2 resident and the kernel is FFMA / L2-gather bound, so the HBM '
                 'fraction (SURVEY 8(d) definition) is small by construction; achieved_tflops_fp32 vs the FFMA peak '
                 'is the meaningful ceiling for this dtype',

@@ -98,8 +98,11 @@ static int build_level(Ctx& c, const void* coords, int is64, int64_t n, int nb, 
   return sgnn_rulebook_submanifold(&L->g, ci32, n, nbr, c.stream);
 }
 
-// a4: stride-2 coarse set of `f` (raster rows) + strided rulebook (+ its own 27-neighbour table)
-static int coarsen_level(Ctx& c, const Level& f, Level* L, int32_t** parent, int32_t** children, bool want_nbr) {
+// a4: stride-2 coarse set of `f` (raster rows) + strided rulebook (+ its own 27-neighbour table), in two phases so
+// that a whole pyramid of coarse sets costs ONE host read: begin() enqueues mask + rank scan (depends only on the
+// finer mask), the caller reads all counts with a single synchronisation, finish() allocates exactly and enqueues
+// coordinate enumeration and rulebooks.
+static int coarsen_begin(Ctx& c, const Level& f, Level* L) {
   int dims[3];
   for (int i = 0; i < 3; ++i) dims[i] = f.dims[i] >= 2 ? (f.dims[i] - 2) / 2 + 1 : 0;  // scn output size
   grid_shape(&L->g, f.g.nb, dims);
@@ -107,24 +110,37 @@ static int coarsen_level(Ctx& c, const Level& f, Level* L, int32_t** parent, int
   ALLOC(mask, uint64_t, L->g.n_words);
   ALLOC(prefix, int32_t, L->g.n_words + 1);
   L->g.mask = mask; L->g.prefix = prefix; L->g.row_of_rank = nullptr;
+  L->n = -1; L->coords = nullptr; L->nbr = nullptr;
   const size_t mark = c.ar.off;
   const size_t sb = sgnn_scan_scratch_bytes(L->g.n_words);
   ALLOC(scr, char, sb);
   RC(sgnn_grid_coarsen(&f.g, &L->g, scr, sb, c.stream));
   c.ar.off = mark;
-  int32_t cnt = 0;
-  RC(read_i32(c, prefix + L->g.n_words, &cnt));
-  L->n = cnt;
-  ALLOC(cc, int32_t, (int64_t)cnt * 4);
+  return SGNN_OK;
+}
+
+// one synchronisation for up to 4 pending levels
+static int read_counts(Ctx& c, Level** lv, int n) {
+  int32_t cnt[4] = {0, 0, 0, 0};
+  for (int i = 0; i < n; ++i)
+    SGNN_CUDA(cudaMemcpyAsync(&cnt[i], lv[i]->g.prefix + lv[i]->g.n_words, 4, cudaMemcpyDeviceToHost, c.st));
+  SGNN_CUDA(cudaStreamSynchronize(c.st));
+  for (int i = 0; i < n; ++i) lv[i]->n = cnt[i];
+  return SGNN_OK;
+}
+
+static int coarsen_finish(Ctx& c, const Level& f, Level* L, int32_t** parent, int32_t** children, bool want_nbr) {
+  const int64_t cnt = L->n;
+  ALLOC(cc, int32_t, cnt * 4);
   L->coords = cc;
   if (cnt) RC(sgnn_grid_enumerate(&L->g, cc, c.stream));
   ALLOC(par, int32_t, f.n);
-  ALLOC(chi, int32_t, (int64_t)cnt * 8);
+  ALLOC(chi, int32_t, cnt * 8);
   *parent = par; *children = chi;
   RC(sgnn_rulebook_strided(&L->g, f.coords, f.n, par, chi, cnt, c.stream));
   L->nbr = nullptr;
   if (want_nbr) {
-    ALLOC(nbr, int32_t, (int64_t)cnt * 27);
+    ALLOC(nbr, int32_t, cnt * 27);
     L->nbr = nbr;
     RC(sgnn_rulebook_submanifold(&L->g, cc, cnt, nbr, c.stream));
   }
@@ -169,12 +185,21 @@ static int fcn(Ctx& c, const Level& lv0, const SgnnFcnW& f, const float* x_raw, 
   *out = J0;
   rows[0] = lv0.n; rows[1] = rows[2] = 0;
   if (lv0.n == 0) return SGNN_OK;
+  // both coarse site sets + rulebooks of the U first (one host read), then the convolutions back to back
+  Level lv1, lv2;
+  int32_t *par01, *chi01, *par12 = nullptr, *chi12 = nullptr;
+  RC(coarsen_begin(c, lv0, &lv1));
+  RC(coarsen_begin(c, lv1, &lv2));
+  {
+    Level* pend[2] = {&lv1, &lv2};
+    RC(read_counts(c, pend, 2));
+  }
+  RC(coarsen_finish(c, lv0, &lv1, &par01, &chi01, true));
+  RC(coarsen_finish(c, lv1, &lv2, &par12, &chi12, true));
+  rows[1] = lv1.n;
+  rows[2] = lv2.n;
   ALLOC(y0_bn, float, lv0.n * ch);
   RC(res_block(c, lv0, f.blk[0], ch, x_raw, x_bn, epi_bn(J0, 3 * ch, f.bn_join), epi_bn(y0_bn, ch, f.bn_down[0])));
-  Level lv1;
-  int32_t *par01, *chi01;
-  RC(coarsen_level(c, lv0, &lv1, &par01, &chi01, true));
-  rows[1] = lv1.n;
   ALLOC(J1, float, lv1.n * 2 * ch);
   if (lv1.n) {
     ALLOC(z1_raw, float, lv1.n * ch);
@@ -183,10 +208,6 @@ static int fcn(Ctx& c, const Level& lv0, const SgnnFcnW& f, const float* x_raw, 
             epi_bn(z1_bn, ch, f.blk[1].bn0)));
     ALLOC(y1_bn, float, lv1.n * ch);
     RC(res_block(c, lv1, f.blk[1], ch, z1_raw, z1_bn, epi(J1, 2 * ch), epi_bn(y1_bn, ch, f.bn_down[1])));
-    Level lv2;
-    int32_t *par12, *chi12;
-    RC(coarsen_level(c, lv1, &lv2, &par12, &chi12, true));
-    rows[2] = lv2.n;
     ALLOC(y2, float, lv2.n * ch);
     if (lv2.n) {
       ALLOC(z2_raw, float, lv2.n * ch);
@@ -234,6 +255,20 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
     Skip skips[4];
     const float* x = feats;
     int ld_x = w->enc[0].cin;
+    // the whole encoder pyramid (3 coarse site sets + rulebooks) up front: one host read instead of three mid-stream
+    Level enc_lv[4];
+    int32_t *enc_par[3], *enc_chi[3];
+    enc_lv[0] = lv;
+    GEN(coarsen_begin(c, enc_lv[0], &enc_lv[1]));
+    GEN(coarsen_begin(c, enc_lv[1], &enc_lv[2]));
+    GEN(coarsen_begin(c, enc_lv[2], &enc_lv[3]));
+    {
+      Level* pend[3] = {&enc_lv[1], &enc_lv[2], &enc_lv[3]};
+      GEN(read_counts(c, pend, 3));
+    }
+    GEN(coarsen_finish(c, enc_lv[0], &enc_lv[1], &enc_par[0], &enc_chi[0], true));
+    GEN(coarsen_finish(c, enc_lv[1], &enc_lv[2], &enc_par[1], &enc_chi[1], true));
+    GEN(coarsen_finish(c, enc_lv[2], &enc_lv[3], &enc_par[2], &enc_chi[2], false));
     bool enc_ok = true;
     for (int l = 0; l < 3 && enc_ok; ++l) {
       const SgnnEncLevelW& e = w->enc[l];
@@ -246,9 +281,8 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       GALLOC(skip, float, lv.n * ch);
       GEN(res_block(c, lv, e.res, ch, a_raw, a_bn, epi_bn(skip, ch, e.bn_out), kNoEpi));
       skips[l].g = lv.g; skips[l].f = skip; skips[l].c = ch; skips[l].n = lv.n;
-      Level cl;
-      int32_t *par, *chi;
-      GEN(coarsen_level(c, lv, &cl, &par, &chi, l < 2));
+      Level cl = enc_lv[l + 1];
+      int32_t* chi = enc_chi[l];
       out->rows[l + 1] = cl.n;
       GALLOC(h, float, cl.n * ch);
       if (cl.n) {
