@@ -250,7 +250,9 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
     int dims[3] = {dims3[0], dims3[1], dims3[2]};
     // ------------------------------------------------------------ encoder (model.py:145-150)
     Level lv;
-    GEN(build_level(c, coords, coords_i64, n, nb, dims, nullptr, &lv));
+    GALLOC(status, int32_t, 1);
+    if ((rc = (cudaMemsetAsync(status, 0, 4, c.st) == cudaSuccess ? SGNN_OK : SGNN_E_CUDA)) != SGNN_OK) break;
+    GEN(build_level(c, coords, coords_i64, n, nb, dims, status, &lv));
     out->rows[0] = n;
     Skip skips[4];
     const float* x = feats;
@@ -262,10 +264,15 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
     GEN(coarsen_begin(c, enc_lv[0], &enc_lv[1]));
     GEN(coarsen_begin(c, enc_lv[1], &enc_lv[2]));
     GEN(coarsen_begin(c, enc_lv[2], &enc_lv[3]));
+    int32_t bad = 0;
+    if ((rc = (cudaMemcpyAsync(&bad, status, 4, cudaMemcpyDeviceToHost, c.st) == cudaSuccess ? SGNN_OK : SGNN_E_CUDA)) !=
+        SGNN_OK)
+      break;
     {
       Level* pend[3] = {&enc_lv[1], &enc_lv[2], &enc_lv[3]};
       GEN(read_counts(c, pend, 3));
     }
+    if (bad) { rc = SGNN_E_INVALID; break; }   // a coordinate outside [0, dims) x [0, nb): scn raises here too
     GEN(coarsen_finish(c, enc_lv[0], &enc_lv[1], &enc_par[0], &enc_chi[0], true));
     GEN(coarsen_finish(c, enc_lv[1], &enc_lv[2], &enc_par[1], &enc_chi[1], true));
     GEN(coarsen_finish(c, enc_lv[2], &enc_lv[3], &enc_par[2], &enc_chi[2], false));

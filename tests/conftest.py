@@ -14,6 +14,12 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+    # the CPU oracles are many small torch ops: on a 128-core GPU box the default thread count makes them ~100x slower
+    try:
+        import torch
+        torch.set_num_threads(max(1, min(os.cpu_count() or 1, 16)))
+    except Exception:
+        pass
 
 
 def pytest_collection_modifyitems(config, items):

@@ -168,3 +168,45 @@ def test_dropin_sparseconvnet_modules_against_oracle():
         assert db.shape == da.shape and torch.allclose(db.cpu(), da, atol=1e-4, rtol=1e-4)
     with pytest.raises(NotImplementedError):
         b.train()(scn.InputLayer(3, dims, mode=0)([c, f.cuda()]))
+
+
+def test_native_generator_rejects_out_of_range_coordinates():
+    from sgnn_b200.synth import synthetic_batch
+    from sgnn_b200._lib import SgnnError
+    m = _model((32, 32, 32), 0)
+    locs, feats = synthetic_batch(1, [32, 32, 32], 0.08)
+    bad = locs.clone()
+    bad[5, 1] = 40                                   # y beyond the declared 32^3 input size
+    with pytest.raises(SgnnError):
+        m([bad.cuda(), feats.cuda()], ONES)
+    out = m([locs.cuda(), feats.cuda()], ONES)       # the engine stays usable afterwards
+    assert out[0][1].shape[0] > 0
+
+
+def test_whole_scene_shape_batch1_update_sizes():
+    """the test_scene.py call pattern -- batch 1, non-cubic scene padded to /32, update_sizes() before the
+    forward (test_scene.py:77-82), coordinates left on the CPU -- against the live oracle generator."""
+    from genmodel import OracleGenModel
+    from sgnn_b200.synth import fill_parameters, synthetic_batch
+    dims = (64, 96, 32)
+    locs, feats = synthetic_batch(1, list(dims), 0.04, seed0=77)
+    ora = OracleGenModel(input_dim=64)
+    fill_parameters(ora, 4)
+    ora.eval()
+    ora.set_sizes(dims)
+    with torch.no_grad():
+        (wl, ws), wlv = ora(locs, feats)
+    import sgnn_b200
+    m = sgnn_b200.GenModel(8, 64, 1, 16, 16, 4, True, True, 1, 1)
+    m.load_state_dict(ora.state_dict())
+    m = m.cuda().eval()
+    m.update_sizes(np.array(dims), np.array(dims) // 8)
+    (gl, gs), glv = m([locs, feats.cuda()], ONES)
+    for i, (w, gg) in enumerate(zip(wlv, glv)):
+        assert torch.equal(w[0], gg[0].cpu()), 'level %d' % i
+        assert (w[1] - gg[1].cpu()).abs().max() <= TOL_LOGIT
+        flips = (torch.sigmoid(w[1][:, 0]) > 0.5) != (torch.sigmoid(gg[1][:, 0].cpu()) > 0.5)
+        assert bool((w[1][:, 0][flips].abs() < 1e-5).all())
+        if bool(flips.any()):
+            return
+    assert torch.equal(wl, gl.cpu()) and (ws - gs.cpu()).abs().max() <= TOL_SDF
