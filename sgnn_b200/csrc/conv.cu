@@ -17,6 +17,8 @@
 #define CHUNK 16       // input channels per stage
 #define XS (CHUNK + 4) // X tile row stride (floats)
 
+int g_sgnn_conv_impl = 0;  // tuning hook, see sgnn_debug_set_conv_impl
+
 struct ConvParams {
   const float* in;
   int ld_in;
@@ -629,10 +631,45 @@ __device__ __forceinline__ void ro_compute(float (&acc)[S][COUT], const float* _
   }
 }
 
+// epilogue of one output row held entirely by one thread: residual add, two slots with optional affine + relu
+template <int COUT>
+__device__ __forceinline__ void ro_epilogue_row(const ConvParams& p, const float (&acc)[COUT], long long j) {
+  if (j >= p.n_out) return;
+#pragma unroll
+  for (int c = 0; c < COUT; c += 4) {
+    float4 v = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+    if (p.residual) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + j * p.ld_res + c));
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (p.out_a) {
+      float4 y = v;
+      if (p.scale_a) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale_a + c));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift_a + c));
+        y.x = fmaf(v.x, sc.x, sh.x); y.y = fmaf(v.y, sc.y, sh.y); y.z = fmaf(v.z, sc.z, sh.z); y.w = fmaf(v.w, sc.w, sh.w);
+      }
+      if (p.relu_a) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+      *reinterpret_cast<float4*>(p.out_a + j * p.ld_a + c) = y;
+    }
+    if (p.out_b) {
+      float4 y = v;
+      if (p.scale_b) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale_b + c));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift_b + c));
+        y.x = fmaf(v.x, sc.x, sh.x); y.y = fmaf(v.y, sc.y, sh.y); y.z = fmaf(v.z, sc.z, sh.z); y.w = fmaf(v.w, sc.w, sh.w);
+      }
+      if (p.relu_b) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+      *reinterpret_cast<float4*>(p.out_b + j * p.ld_b + c) = y;
+    }
+  }
+}
+
 // CIN: exact input channels; CH: channels per stage (CINP when CIN <= 16, else 16); S rows per thread; NS ring depth
-template <int COUT, int CIN, int CH, int S, int NS>
+template <int COUT, int CIN, int CH, int S, int NS, bool VEC, bool CHILD>
 __global__ void __launch_bounds__(128)
-conv_ro_kernel(ConvParams p, int vec) {
+conv_ro_kernel(ConvParams p) {
+  constexpr bool vec = VEC;
   constexpr int CINP = (CIN + 3) & ~3;
   constexpr int NSUB = (CINP + CH - 1) / CH;          // stages per filter offset
   constexpr int TAIL = CINP - (NSUB - 1) * CH;         // channels (padded to 4) of the last slice
@@ -655,7 +692,8 @@ conv_ro_kernel(ConvParams p, int vec) {
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       const long long j = row0 + 128 * s;
-      ir[s] = j < p.n_out ? conv_src_row(p, j, k) : -1;
+      if (CHILD) ir[s] = j < p.n_out ? conv_src_row(p, j, k) : -1;
+      else ir[s] = j < p.n_out ? __ldg(p.nbr + (long long)k * p.nbr_stride + j) : -1;
     }
   };
   // gather of stage (k, sub) into ring slot `buf`; ir[] holds the row indices of offset k
@@ -747,38 +785,7 @@ conv_ro_kernel(ConvParams p, int vec) {
 
   // ---- epilogue (per row: all COUT channels are in this thread)
 #pragma unroll
-  for (int s = 0; s < S; ++s) {
-    const long long j = row0 + 128 * s;
-    if (j >= p.n_out) continue;
-#pragma unroll
-    for (int c = 0; c < COUT; c += 4) {
-      float4 v = make_float4(acc[s][c], acc[s][c + 1], acc[s][c + 2], acc[s][c + 3]);
-      if (p.residual) {
-        const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + j * p.ld_res + c));
-        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-      }
-      if (p.out_a) {
-        float4 y = v;
-        if (p.scale_a) {
-          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale_a + c));
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift_a + c));
-          y.x = fmaf(v.x, sc.x, sh.x); y.y = fmaf(v.y, sc.y, sh.y); y.z = fmaf(v.z, sc.z, sh.z); y.w = fmaf(v.w, sc.w, sh.w);
-        }
-        if (p.relu_a) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-        *reinterpret_cast<float4*>(p.out_a + j * p.ld_a + c) = y;
-      }
-      if (p.out_b) {
-        float4 y = v;
-        if (p.scale_b) {
-          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale_b + c));
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift_b + c));
-          y.x = fmaf(v.x, sc.x, sh.x); y.y = fmaf(v.y, sc.y, sh.y); y.z = fmaf(v.z, sc.z, sh.z); y.w = fmaf(v.w, sc.w, sh.w);
-        }
-        if (p.relu_b) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-        *reinterpret_cast<float4*>(p.out_b + j * p.ld_b + c) = y;
-      }
-    }
-  }
+  for (int s = 0; s < S; ++s) ro_epilogue_row<COUT>(p, acc[s], row0 + 128 * s);
 }
 
 template <int COUT, int CIN, int S, int CH>
@@ -790,11 +797,22 @@ static int launch_ro(const ConvParams& p, bool vec, cudaStream_t st) {
   if (tiles > 0x7fffffff) return SGNN_E_TOO_LARGE;
   static bool attr_set = false;
   if (!attr_set) {
-    SGNN_CUDA(cudaFuncSetAttribute(conv_ro_kernel<COUT, CIN, CH, S, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
+    SGNN_CUDA(cudaFuncSetAttribute(conv_ro_kernel<COUT, CIN, CH, S, NS, true, false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGNN_CUDA(cudaFuncSetAttribute(conv_ro_kernel<COUT, CIN, CH, S, NS, false, false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGNN_CUDA(cudaFuncSetAttribute(conv_ro_kernel<COUT, CIN, CH, S, NS, true, true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  conv_ro_kernel<COUT, CIN, CH, S, NS><<<(int)tiles, 128, smem, st>>>(p, vec ? 1 : 0);
+  if (p.child_mode) {
+    if (!vec) return SGNN_E_ALIGN;
+    conv_ro_kernel<COUT, CIN, CH, S, NS, true, true><<<(int)tiles, 128, smem, st>>>(p);
+  } else if (vec) {
+    conv_ro_kernel<COUT, CIN, CH, S, NS, true, false><<<(int)tiles, 128, smem, st>>>(p);
+  } else {
+    conv_ro_kernel<COUT, CIN, CH, S, NS, false, false><<<(int)tiles, 128, smem, st>>>(p);
+  }
   SGNN_CHECK_LAUNCH();
   return SGNN_OK;
 }
@@ -805,7 +823,10 @@ static int dispatch_ro(const ConvParams& p, bool vec, cudaStream_t st, bool* han
   // Rows per thread by launch size: S=4 amortises the weight reads best but makes 512-row CTAs; a launch that cannot
   // fill the chip (148 SMs x 3 CTAs) with those is latency bound (ncu: 45-80 us floors on the coarse levels), so
   // mid-size launches use S=2 and small ones S=1 (4x more, 4x shorter CTAs).
-  const int sz = p.n_out >= 300000 ? 4 : (p.n_out >= 90000 ? 2 : 1);
+  if (p.child_mode && !vec) { *handled = false; return SGNN_OK; }
+  int sz = p.n_out >= 300000 ? 4 : (p.n_out >= 90000 ? 2 : 1);
+  if (g_sgnn_conv_impl == 6 && sz == 4) sz = 2;   // A/B: never 4 rows per thread
+  if (g_sgnn_conv_impl == 7 && sz == 1) sz = 2;   // A/B: never 1 row per thread
 #define SGNN_RO_CASE(CO, CI, SS, CHH) \
   if (p.cout == CO && p.cin == CI) return launch_ro<CO, CI, SS, CHH>(p, vec, st);
 #define SGNN_RO_SIZED(CO, CI, CHH)              \
@@ -875,10 +896,9 @@ __global__ void conv_gather_f32_generic_kernel(ConvParams p) {
   }
 }
 
-// 0 (default): v4 row-owner kernel, whole-row stages for wide inputs, parent-staged kernel for child mode;
+// (declared near the top of the file) 0 (default): v4 row-owner kernel, whole-row stages for wide inputs, parent-staged kernel for child mode;
 // 1: v2 tile kernels; 2: v1 runtime-shape kernel; 3: v4 only (whole-row stages for wide inputs); 4: v4 with
 // 16-channel sub-stages + child kernel; 5: v4 with 16-channel sub-stages only.  Tuning hook, all bit-identical.
-int g_sgnn_conv_impl = 0;
 extern "C" void sgnn_debug_set_conv_impl(int v) { g_sgnn_conv_impl = v; }
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -947,11 +967,11 @@ extern "C" int sgnn_conv_forward(const SgnnConvArgs* a, void* stream) {
     const bool vec = aligned16(a->in) && (a->ld_in & 3) == 0;
     {
       bool handled = false;
-      if ((g_sgnn_conv_impl == 0 || g_sgnn_conv_impl == 4) && vec && p.child_mode && p.cout == 16 && p.cin == 48 &&
-          (p.n_out & 7) == 0)
+      if (vec && p.child_mode && p.cout == 16 && p.cin == 48 && (p.n_out & 7) == 0 &&
+          (g_sgnn_conv_impl == 0 || g_sgnn_conv_impl == 4 || g_sgnn_conv_impl >= 6))
         return launch_child<16, 48>(p, st);
       if (g_sgnn_conv_impl == 0 || g_sgnn_conv_impl >= 3) {
-        rc = dispatch_ro(p, vec, st, &handled, g_sgnn_conv_impl == 0 || g_sgnn_conv_impl == 3);
+        rc = dispatch_ro(p, vec, st, &handled, g_sgnn_conv_impl == 0 || g_sgnn_conv_impl == 3 || g_sgnn_conv_impl >= 6);
         if (handled) return rc;
       }
       if (vec && g_sgnn_conv_impl <= 1) {

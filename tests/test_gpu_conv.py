@@ -240,7 +240,7 @@ def test_dense_unet_layers_bit_exact(transposed, c0, c1, cout, k, s, p, dims):
     assert torch.equal(raw.cpu(), o3.dense_conv(xcat, w, k, s, p, transposed=transposed))
 
 
-@pytest.mark.parametrize('impl', [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize('impl', [0, 1, 2, 3, 4, 5, 6, 7])
 def test_all_conv_implementations_bit_identical(impl):
     """Every convolution kernel generation (v1 runtime-shape, v2 tile, v4 row-owner, child-mode) computes the SAME
     fmaf chains: results are bit-identical to O3 whichever the dispatcher picks."""
