@@ -3,8 +3,9 @@
 // stays on the bit-reproducible FFMA kernels (conv.cu); this is the north_star's "tcgen05 tiles only for the
 // per-offset dense (Nactive x Cin).(Cin x Cout) contraction".
 //
-// One CTA = one tile of 128 output rows (UMMA M = 128), N = Cout = 16, and per filter offset k one
-// tcgen05.mma.cta_group::1.kind::f16 with K = Cin = 16 (bf16 UMMA_K).  Per group of <= 9 offsets:
+// Work item = (tile of 128 output rows (UMMA M = 128), group of <= 9 filter offsets); N = Cout = 16, and per offset k
+// one tcgen05.mma.cta_group::1.kind::f16 with K = Cin = 16 (bf16 UMMA_K).  CTAs are persistent (a few per SM) and
+// double buffer the A tiles, so the gather of the next item overlaps the MMAs + epilogue of the current one.  Per item:
 //   1. all 128 threads gather the neighbour rows (32 B each) with cp.async straight into the canonical
 //      K-major / no-swizzle core-matrix layout the UMMA shared-memory descriptor expects
 //        row r, 16-byte chunk c  ->  (r/8)*256 + c*128 + (r%8)*16      (SBO = 256 B, LBO = 128 B)
@@ -48,16 +49,20 @@ __device__ __forceinline__ void cp16(void* smem, const void* g) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(g));
 }
 
+// Persistent, software-pipelined version: a CTA walks work items (tile, offset group) with stride gridDim.x.  The
+// whole filter bank is staged once per CTA; A tiles are double buffered, so the cp.async gather of item j+1 is in
+// flight while the MMAs of item j complete and its epilogue (TMEM -> registers -> bf16 rows) runs.
 __global__ void __launch_bounds__(128)
-conv_tc_bf16_kernel(TcParams p) {
+conv_tc_bf16_kernel(TcParams p, int kg_max, long long n_tiles) {
   extern __shared__ __align__(1024) unsigned char sm[];
-  unsigned char* A = sm;                              // [TC_KG][4096]
-  unsigned char* B = sm + TC_KG * TC_A_BYTES;         // [TC_KG][512]
+  const int ngroups = (p.K + kg_max - 1) / kg_max;
+  unsigned char* B = sm;                                   // [K][512]
+  unsigned char* A0 = sm + ((p.K * TC_B_BYTES + 1023) & ~1023);
+  const int a_buf = kg_max * TC_A_BYTES;                   // A0 + buf * a_buf : [kg_max][4096]
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ unsigned tmem_ptr_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long tile_base = (long long)blockIdx.x * TC_M;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr_s)), "r"(32));
@@ -67,46 +72,77 @@ conv_tc_bf16_kernel(TcParams p) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::);
   }
+  // filter bank once per CTA: W[k][ci][co] -> element (n = co, kdim = ci) of the canonical K-major layout
+  for (int idx = tid; idx < p.K * 256; idx += 128) {
+    const int kk = idx >> 8, e = idx & 255, ci = e >> 4, co = e & 15;
+    *reinterpret_cast<__nv_bfloat16*>(B + kk * TC_B_BYTES + (co >> 3) * 256 + (ci >> 3) * 128 + (co & 7) * 16 + (ci & 7) * 2) =
+        p.w[(size_t)kk * 256 + e];
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::);
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::);
   const unsigned tmem = tmem_ptr_s;
   unsigned phase = 0;
 
-  for (int k0 = 0; k0 < p.K; k0 += TC_KG) {
-    const int kg = min(TC_KG, p.K - k0);
-    // ---- gather A: kg x 128 rows x 2 chunks
-    for (int idx = tid; idx < kg * TC_M * 2; idx += 128) {
-      const int kk = idx >> 8, rem = idx & 255, r = rem >> 1, c = rem & 1;
-      const long long j = tile_base + r;
-      int src = -1;
-      if (j < p.n_out) {
-        if (p.mode == 0) {
-          src = __ldg(p.tbl + (long long)(k0 + kk) * p.tbl_stride + j);
-        } else {
-          const int pk = __ldg(p.tbl + j);
-          src = (pk >= 0 && (pk & 7) == k0 + kk) ? (pk >> 3) : -1;
+  // gather of work item (tile, group g) into A buffer `buf`.  Thread t copies chunk c = t&1 of rows {t>>1, 64 + (t>>1)} for
+  // every offset of the group: ALL neighbour indices are loaded first (independent loads in flight together), then the
+  // dependent cp.async copies are issued -- a naive loop exposes one index-load latency per copied chunk.
+  auto gather = [&](long long tile, int g, int buf) {
+    const long long tile_base = tile * TC_M;
+    const int k0 = g * kg_max, kg = min(kg_max, p.K - k0);
+    unsigned char* A = A0 + buf * a_buf;
+    const int c = tid & 1;
+    int src[TC_KG][2];
+    if (p.mode == 0) {
+#pragma unroll
+      for (int kk = 0; kk < TC_KG; ++kk)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const long long j = tile_base + (tid >> 1) + 64 * h;
+          src[kk][h] = (kk < kg && j < p.n_out) ? __ldg(p.tbl + (long long)(k0 + kk) * p.tbl_stride + j) : -1;
+        }
+    } else {
+      int pk[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const long long j = tile_base + (tid >> 1) + 64 * h;
+        pk[h] = j < p.n_out ? __ldg(p.tbl + j) : -1;
+      }
+#pragma unroll
+      for (int kk = 0; kk < TC_KG; ++kk)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) src[kk][h] = (kk < kg && pk[h] >= 0 && (pk[h] & 7) == k0 + kk) ? (pk[h] >> 3) : -1;
+    }
+#pragma unroll
+    for (int kk = 0; kk < TC_KG; ++kk)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (kk < kg) {
+          const int r = (tid >> 1) + 64 * h;
+          unsigned char* dst = A + kk * TC_A_BYTES + (r >> 3) * 256 + c * 128 + (r & 7) * 16;
+          if (src[kk][h] >= 0) cp16(dst, p.in + (long long)src[kk][h] * p.ld_in + c * 8);
+          else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
         }
       }
-      unsigned char* dst = A + kk * TC_A_BYTES + (r >> 3) * 256 + c * 128 + (r & 7) * 16;
-      if (src >= 0) cp16(dst, p.in + (long long)src * p.ld_in + c * 8);
-      else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-    }
-    // ---- stage B: W[k][ci][co] -> element (n = co, kdim = ci) of the canonical K-major layout
-    for (int idx = tid; idx < kg * 256; idx += 128) {
-      const int kk = idx >> 8, e = idx & 255, ci = e >> 4, co = e & 15;
-      const __nv_bfloat16 v = p.w[(size_t)(k0 + kk) * 256 + e];
-      *reinterpret_cast<__nv_bfloat16*>(B + kk * TC_B_BYTES + (co >> 3) * 256 + (ci >> 3) * 128 + (co & 7) * 16 + (ci & 7) * 2) = v;
-    }
-    asm volatile("cp.async.commit_group;\n" ::);
+  };
+
+  const long long my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const long long n_items = my_tiles * ngroups;
+  if (n_items > 0) gather(blockIdx.x, 0, 0);
+  asm volatile("cp.async.commit_group;\n" ::);
+  for (long long it = 0; it < n_items; ++it) {
+    const long long tile = blockIdx.x + (it / ngroups) * gridDim.x;
+    const int g = (int)(it % ngroups);
+    const int buf = (int)(it & 1);
     asm volatile("cp.async.wait_group 0;\n" ::);
     asm volatile("fence.proxy.async.shared::cta;" ::);   // generic-proxy writes -> visible to the tensor-core (async) proxy
-    __syncthreads();
+    __syncthreads();                                      // item `it` staged; previous epilogue's TMEM loads retired
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::);
+      const int k0 = g * kg_max, kg = min(kg_max, p.K - k0);
       for (int kk = 0; kk < kg; ++kk) {
-        const unsigned long long da = umma_desc(smem_u32(A + kk * TC_A_BYTES));
-        const unsigned long long db = umma_desc(smem_u32(B + kk * TC_B_BYTES));
+        const unsigned long long da = umma_desc(smem_u32(A0 + buf * a_buf + kk * TC_A_BYTES));
+        const unsigned long long db = umma_desc(smem_u32(B + (k0 + kk) * TC_B_BYTES));
         const unsigned accumulate = (k0 + kk) > 0 ? 1u : 0u;
         asm volatile(
             "{\n\t"
@@ -118,7 +154,13 @@ conv_tc_bf16_kernel(TcParams p) {
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar))
                    : "memory");
     }
-    // ---- wait until the MMAs of this group have completed (shared memory may then be overwritten)
+    // prefetch the next item into the other buffer (its previous reader, item it-1, completed: we waited on its commit)
+    if (it + 1 < n_items) {
+      const long long nt = blockIdx.x + ((it + 1) / ngroups) * gridDim.x;
+      gather(nt, (int)((it + 1) % ngroups), buf ^ 1);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    // wait until the MMAs of this item have completed
     {
       const unsigned addr = smem_u32(&mbar);
       asm volatile(
@@ -134,31 +176,34 @@ conv_tc_bf16_kernel(TcParams p) {
     }
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::);
-  }
-
-  // ---- epilogue: TMEM -> registers -> bf16 rows
-  unsigned v[16];
-  const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-  const long long j = tile_base + warp * 32 + lane;
-  if (j < p.n_out) {
-    __nv_bfloat16 o[16];
+    if (g == ngroups - 1) {
+      // ---- epilogue of the tile: TMEM -> registers -> bf16 rows
+      unsigned v[16];
+      const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      const long long j = tile * TC_M + warp * 32 + lane;
+      if (j < p.n_out) {
+        __nv_bfloat16 o[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      float y = __uint_as_float(v[c]);
-      if (p.scale) y = fmaf(y, __ldg(p.scale + c), __ldg(p.shift + c));
-      if (p.relu) y = fmaxf(y, 0.f);
-      o[c] = __float2bfloat16_rn(y);
+        for (int c = 0; c < 16; ++c) {
+          float y = __uint_as_float(v[c]);
+          if (p.scale) y = fmaf(y, __ldg(p.scale + c), __ldg(p.shift + c));
+          if (p.relu) y = fmaxf(y, 0.f);
+          o[c] = __float2bfloat16_rn(y);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(p.out + j * p.ld_out);
+        dst[0] = *reinterpret_cast<uint4*>(&o[0]);
+        dst[1] = *reinterpret_cast<uint4*>(&o[8]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::);
     }
-    uint4* dst = reinterpret_cast<uint4*>(p.out + j * p.ld_out);
-    dst[0] = *reinterpret_cast<uint4*>(&o[0]);
-    dst[1] = *reinterpret_cast<uint4*>(&o[8]);
   }
+  asm volatile("cp.async.wait_group 0;\n" ::);
   asm volatile("tcgen05.fence::before_thread_sync;" ::);
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32));
@@ -179,15 +224,18 @@ int sgnn_conv_tc_bf16(const void* in, int ld_in, const int* tbl, long long tbl_s
   p.in = (const __nv_bfloat16*)in; p.ld_in = ld_in; p.tbl = tbl; p.tbl_stride = tbl_stride; p.K = K; p.mode = mode;
   p.w = (const __nv_bfloat16*)w; p.n_out = n_out; p.out = (__nv_bfloat16*)ep->out; p.ld_out = ep->ld;
   p.scale = ep->scale; p.shift = ep->shift; p.relu = ep->relu;
-  const size_t smem = (size_t)TC_KG * (TC_A_BYTES + TC_B_BYTES) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  const int kg_max = K < TC_KG ? K : TC_KG;
+  const size_t smem = (((size_t)K * TC_B_BYTES + 1023) & ~(size_t)1023) + 2 * (size_t)kg_max * TC_A_BYTES + 1024;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
     SGNN_CUDA(cudaFuncSetAttribute(conv_tc_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_smem = smem;
   }
   const long long tiles = (n_out + TC_M - 1) / TC_M;
-  if (tiles > 0x7fffffff) return SGNN_E_TOO_LARGE;
-  conv_tc_bf16_kernel<<<(int)tiles, 128, smem, st>>>(p);
+  const int per_sm = (int)((220 * 1024) / (smem + 2048));
+  long long grid = (long long)148 * (per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm));
+  if (grid > tiles) grid = tiles;
+  conv_tc_bf16_kernel<<<(int)grid, 128, smem, st>>>(p, kg_max, tiles);
   SGNN_CHECK_LAUNCH();
   return SGNN_OK;
 }
