@@ -64,9 +64,20 @@ struct Level {
   type* var = (type*)c.ar.get((size_t)(count) * sizeof(type));    \
   if (!var) return SGNN_E_NOMEM
 
+// pinned landing zone for the 4-byte count reads (pageable destinations are staged by the driver)
+static int32_t* g_pinned = nullptr;
+static int pinned_slots(int32_t** p) {
+  if (!g_pinned) SGNN_CUDA(cudaHostAlloc((void**)&g_pinned, 64, cudaHostAllocDefault));
+  *p = g_pinned;
+  return SGNN_OK;
+}
+
 static int read_i32(Ctx& c, const int32_t* dev, int32_t* host) {
-  SGNN_CUDA(cudaMemcpyAsync(host, dev, 4, cudaMemcpyDeviceToHost, c.st));
+  int32_t* pin;
+  RC(pinned_slots(&pin));
+  SGNN_CUDA(cudaMemcpyAsync(pin, dev, 4, cudaMemcpyDeviceToHost, c.st));
   SGNN_CUDA(cudaStreamSynchronize(c.st));
+  *host = pin[0];
   return SGNN_OK;
 }
 
@@ -121,11 +132,12 @@ static int coarsen_begin(Ctx& c, const Level& f, Level* L) {
 
 // one synchronisation for up to 4 pending levels
 static int read_counts(Ctx& c, Level** lv, int n) {
-  int32_t cnt[4] = {0, 0, 0, 0};
+  int32_t* pin;
+  RC(pinned_slots(&pin));
   for (int i = 0; i < n; ++i)
-    SGNN_CUDA(cudaMemcpyAsync(&cnt[i], lv[i]->g.prefix + lv[i]->g.n_words, 4, cudaMemcpyDeviceToHost, c.st));
+    SGNN_CUDA(cudaMemcpyAsync(pin + 1 + i, lv[i]->g.prefix + lv[i]->g.n_words, 4, cudaMemcpyDeviceToHost, c.st));
   SGNN_CUDA(cudaStreamSynchronize(c.st));
-  for (int i = 0; i < n; ++i) lv[i]->n = cnt[i];
+  for (int i = 0; i < n; ++i) lv[i]->n = pin[1 + i];
   return SGNN_OK;
 }
 
@@ -264,15 +276,16 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
     GEN(coarsen_begin(c, enc_lv[0], &enc_lv[1]));
     GEN(coarsen_begin(c, enc_lv[1], &enc_lv[2]));
     GEN(coarsen_begin(c, enc_lv[2], &enc_lv[3]));
-    int32_t bad = 0;
-    if ((rc = (cudaMemcpyAsync(&bad, status, 4, cudaMemcpyDeviceToHost, c.st) == cudaSuccess ? SGNN_OK : SGNN_E_CUDA)) !=
+    int32_t* pinb = nullptr;
+    GEN(pinned_slots(&pinb));
+    if ((rc = (cudaMemcpyAsync(pinb + 8, status, 4, cudaMemcpyDeviceToHost, c.st) == cudaSuccess ? SGNN_OK : SGNN_E_CUDA)) !=
         SGNN_OK)
       break;
     {
       Level* pend[3] = {&enc_lv[1], &enc_lv[2], &enc_lv[3]};
       GEN(read_counts(c, pend, 3));
     }
-    if (bad) { rc = SGNN_E_INVALID; break; }   // a coordinate outside [0, dims) x [0, nb): scn raises here too
+    if (pinb[8]) { rc = SGNN_E_INVALID; break; }   // a coordinate outside [0, dims) x [0, nb): scn raises here too
     GEN(coarsen_finish(c, enc_lv[0], &enc_lv[1], &enc_par[0], &enc_chi[0], true));
     GEN(coarsen_finish(c, enc_lv[1], &enc_lv[2], &enc_par[1], &enc_chi[1], true));
     GEN(coarsen_finish(c, enc_lv[2], &enc_lv[3], &enc_par[2], &enc_chi[2], false));

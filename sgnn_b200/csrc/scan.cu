@@ -59,6 +59,59 @@ scan_block_kernel(const void* __restrict__ in, int mode, int* __restrict__ out, 
   }
 }
 
+// Small inputs (the per-level grids and candidate lists of a 32-block batch): ONE CTA walks the tiles carrying the
+// running prefix, instead of the 3-launch hierarchy -- these scans sit on the critical path between two host reads.
+#define SCAN_SINGLE_MAX (SCAN_TILE * 16)
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_single_kernel(const void* __restrict__ in, int mode, int* __restrict__ out, long long n) {
+  __shared__ int warp_tot[SCAN_THREADS / 32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (long long tile0 = 0; tile0 < n; tile0 += SCAN_TILE) {
+    const long long base = tile0 + (long long)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int tsum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+      const long long idx = base + i;
+      v[i] = idx < n ? scan_load(in, mode, idx) : 0;
+      tsum += v[i];
+    }
+    int inc = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      int w = lane < SCAN_THREADS / 32 ? warp_tot[lane] : 0;
+#pragma unroll
+      for (int d = 1; d < SCAN_THREADS / 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += t;
+      }
+      if (lane < SCAN_THREADS / 32) warp_tot[lane] = w;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    int excl = carry + inc - tsum + (wid ? warp_tot[wid - 1] : 0);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+      const long long idx = base + i;
+      if (idx < n) out[idx] = excl;
+      excl += v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == SCAN_THREADS - 1) carry_s = excl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = carry_s;
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_add_kernel(int* __restrict__ out, long long n, const int* __restrict__ sums_ex, int nb) {
   const int off = sums_ex[blockIdx.x];
@@ -88,6 +141,11 @@ int sgnn_scan_exclusive(const void* in, int mode, int* out, int64_t n, void* scr
                         size_t scratch_bytes, cudaStream_t st) {
   if (n < 0 || !out || (!in && n > 0) || !scratch) return SGNN_E_INVALID;
   if (scratch_bytes < sgnn_scan_scratch_bytes(n)) return SGNN_E_INVALID;
+  if (n <= SCAN_SINGLE_MAX) {
+    scan_single_kernel<<<1, SCAN_THREADS, 0, st>>>(in, mode, out, (long long)n);
+    SGNN_CHECK_LAUNCH();
+    return SGNN_OK;
+  }
   int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
   if (nb < 1) nb = 1;
   if (nb > 0x7fffffff) return SGNN_E_TOO_LARGE;
