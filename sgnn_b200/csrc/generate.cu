@@ -113,27 +113,34 @@ __global__ void heads_flag_kernel(const float* __restrict__ x, int ld_x, int c, 
   }
 }
 
+// 8 lanes per candidate row: the kept row (c features + occ + sdf + zeroed spare columns) is written as 16-byte /
+// 4-byte pieces by neighbouring lanes instead of one thread striding through a 112-byte row.
 __global__ void heads_write_kernel(const float* __restrict__ x, int ld_x, int c, const float* __restrict__ cand_out,
                                    const int* __restrict__ parent_coords, long long n_cand,
                                    const unsigned char* __restrict__ flags, const int* __restrict__ offs,
                                    int* __restrict__ locs, float* __restrict__ feats, int ld,
                                    int* __restrict__ count) {
   if (count && blockIdx.x == 0 && threadIdx.x == 0) *count = offs[n_cand];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_cand;
-       i += (long long)gridDim.x * blockDim.x) {
+  const int sub = threadIdx.x & 7;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3; i < n_cand;
+       i += ((long long)gridDim.x * blockDim.x) >> 3) {
     if (!flags[i]) continue;
     const int pos = offs[i];
-    const int4 p = __ldg(reinterpret_cast<const int4*>(parent_coords) + (i >> 3));
-    const int ch8 = (int)(i & 7);
-    reinterpret_cast<int4*>(locs)[pos] =
-        make_int4(2 * p.x + ((ch8 >> 2) & 1), 2 * p.y + ((ch8 >> 1) & 1), 2 * p.z + (ch8 & 1), p.w);
+    if (sub == 0) {
+      const int4 p = __ldg(reinterpret_cast<const int4*>(parent_coords) + (i >> 3));
+      const int ch8 = (int)(i & 7);
+      reinterpret_cast<int4*>(locs)[pos] =
+          make_int4(2 * p.x + ((ch8 >> 2) & 1), 2 * p.y + ((ch8 >> 1) & 1), 2 * p.z + (ch8 & 1), p.w);
+    }
     float* f = feats + (long long)pos * ld;
     const float* xr = x + i * ld_x;
-    for (int ch = 0; ch < c; ++ch) f[ch] = xr[ch];
-    const float2 os = reinterpret_cast<const float2*>(cand_out)[i];
-    f[c] = os.x;
-    f[c + 1] = os.y;
-    for (int ch = c + 2; ch < ld; ++ch) f[ch] = 0.f;       // spare columns for the skip join
+    for (int ch = sub; ch < ld; ch += 8) {
+      float v = 0.f;                                         // spare columns for the skip join
+      if (ch < c) v = xr[ch];
+      else if (ch == c) v = cand_out[2 * i];
+      else if (ch == c + 1) v = cand_out[2 * i + 1];
+      f[ch] = v;
+    }
   }
 }
 
@@ -160,7 +167,7 @@ extern "C" int sgnn_heads_compact(const float* x, int32_t ld_x, int32_t c, const
   SGNN_CHECK_LAUNCH();
   rc = sgnn_scan_exclusive(cs.flags, SCAN_U8, cs.offs, n_cand, cs.scan, cs.scan_bytes, st);
   if (rc) return rc;
-  heads_write_kernel<<<sgnn_blocks(n_cand, 256), 256, 0, st>>>(x, ld_x, c, cand_out, parent_coords, n_cand,
+  heads_write_kernel<<<sgnn_blocks(n_cand * 8, 256), 256, 0, st>>>(x, ld_x, c, cand_out, parent_coords, n_cand,
                                                                cs.flags, cs.offs, locs, feats, ld_feats, count);
   SGNN_CHECK_LAUNCH();
   return SGNN_OK;
@@ -191,7 +198,7 @@ extern "C" int sgnn_heads_write(const float* x, int32_t ld_x, int32_t c, const f
   if (n_cand < 0 || c <= 0 || ld_feats < c + 2) return SGNN_E_INVALID;
   if (n_cand == 0) return SGNN_OK;
   if (!x || !cand_out || !parent_coords || !flags || !offs || !locs || !feats) return SGNN_E_INVALID;
-  heads_write_kernel<<<sgnn_blocks(n_cand, 256), 256, 0, (cudaStream_t)stream>>>(
+  heads_write_kernel<<<sgnn_blocks(n_cand * 8, 256), 256, 0, (cudaStream_t)stream>>>(
       x, ld_x, c, cand_out, parent_coords, n_cand, flags, offs, locs, feats, ld_feats, nullptr);
   SGNN_CHECK_LAUNCH();
   return SGNN_OK;

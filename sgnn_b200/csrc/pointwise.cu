@@ -91,11 +91,47 @@ __global__ void linear_kernel(const float* __restrict__ x, int ld_x, const float
   }
 }
 
+// cout == 1 (TSDF head, model.py:258,271): 4 lanes per row read the row coalesced and hand the SAME sequential fmaf
+// chain from lane to lane (lane q continues with channels [q*cin/4, (q+1)*cin/4)) -- identical bits, 4x fewer
+// uncoalesced 192-byte row walks.
+__global__ void linear1_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ w,
+                               const float* __restrict__ b, float* __restrict__ y, int ld_y, long long n, int cin) {
+  const int q = threadIdx.x & 3;
+  const int per = cin >> 2;
+  for (long long i0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 2; ; i0 += ((long long)gridDim.x * blockDim.x) >> 2) {
+    const long long base = i0 - (i0 & 7);   // rows handled by this warp iteration: keep the warp converged for shuffles
+    if (base >= n) break;
+    const bool live = i0 < n;
+    const float* xr = x + (live ? i0 : 0) * ld_x + q * per;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = (live && c < per) ? xr[c] : 0.f;
+    float acc = 0.f;
+#pragma unroll
+    for (int step = 0; step < 4; ++step) {
+      if (q == step) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (c < per) acc = fmaf(v[c], __ldg(w + step * per + c), acc);
+      }
+      const float nxt = __shfl_sync(0xffffffffu, acc, (threadIdx.x & 28) | step, 32);
+      if (q == step + 1) acc = nxt;
+      if (step == 3 && q == 0) acc = nxt;
+    }
+    if (live && q == 0) y[i0 * ld_y] = b ? acc + __ldg(b) : acc;
+  }
+}
+
 extern "C" int sgnn_linear(const float* x, int32_t ld_x, const float* w, const float* b, float* y, int32_t ld_y,
                            int64_t n, int32_t cin, int32_t cout, void* stream) {
   if (n < 0 || cin <= 0 || cout <= 0 || !w) return SGNN_E_INVALID;
   if (n == 0) return SGNN_OK;
   if (!x || !y) return SGNN_E_INVALID;
+  if (cout == 1 && (cin & 3) == 0 && cin <= 64) {
+    linear1_kernel<<<sgnn_blocks(n * 4, 256), 256, 0, (cudaStream_t)stream>>>(x, ld_x, w, b, y, ld_y, (long long)n, cin);
+    SGNN_CHECK_LAUNCH();
+    return SGNN_OK;
+  }
   linear_kernel<<<sgnn_blocks(n * cout, 256), 256, 0, (cudaStream_t)stream>>>(x, ld_x, w, b, y, ld_y, (long long)n,
                                                                               cin, cout);
   SGNN_CHECK_LAUNCH();
