@@ -33,8 +33,8 @@ struct Ctx {
 };
 
 // event pool for SGNN_GEN_PROFILE (pairs around every sgnn_conv_forward of the pass)
-static cudaEvent_t g_ev[512];
-static int g_ev_made = 0;
+static thread_local cudaEvent_t g_ev[512];
+static thread_local int g_ev_made = 0;
 
 struct Epi {
   float* out; int ld; const float* scale; const float* shift; int relu;
@@ -65,7 +65,7 @@ struct Level {
   if (!var) return SGNN_E_NOMEM
 
 // pinned landing zone for the 4-byte count reads (pageable destinations are staged by the driver)
-static int32_t* g_pinned = nullptr;
+static thread_local int32_t* g_pinned = nullptr;   // per host thread: concurrent forwards on different streams
 static int pinned_slots(int32_t** p) {
   if (!g_pinned) SGNN_CUDA(cudaHostAlloc((void**)&g_pinned, 64, cudaHostAllocDefault));
   *p = g_pinned;
