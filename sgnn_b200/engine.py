@@ -89,8 +89,9 @@ def build_grid(coords, nb, dims, status=None):
 
 
 def coarsen(fine, dims_cap=None):
-    """a4: stride-2 coarse site set (raster row order).  One host read of the row count."""
-    d = [(v + 1) // 2 for v in fine.d]
+    """a4: stride-2 coarse site set (raster row order).  One host read of the row count.
+    Extent = scn's Convolution output size (S-2)//2+1 per axis (fine cells beyond it are dropped, App. A.5)."""
+    d = [((v - 2) // 2 + 1) if v >= 2 else 0 for v in fine.d]
     if dims_cap is not None:
         d = [min(a, int(b)) for a, b in zip(d, dims_cap)]
     g = Grid(fine.nb, d, fine.device, False)

@@ -139,12 +139,17 @@ def forward_fused(model, x, loss_weights):
     enc = model.encoder
     with torch.no_grad():
         outputs = []
-        # ---------------- encoder: level-0 grid from caller coordinates (a1, a2)
+        # ---------------- encoder: level-0 grid from caller coordinates (a1, a2), declared extent like the native path
         il = enc.process_sparse[0].p0
-        sp = il(([locs_in, feats_in]))
-        g = sp.metadata.grid(sp.spatial_size)
-        nb = sp.metadata.batch_size
-        feats = sp.features
+        locs_dev = locs_in.to(dev).contiguous()
+        if locs_dev.dtype not in (torch.int64, torch.int32):
+            locs_dev = locs_dev.long()
+        nb = int(x[2]) if len(x) > 2 else (int(locs_dev[:, 3].max().item()) + 1 if locs_dev.shape[0] else 1)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        g = E.build_grid(locs_dev, nb, [int(v) for v in il.spatial_size], status=status)
+        if int(status.item()):
+            raise ValueError('coordinate outside spatial_size %s' % il.spatial_size.tolist())
+        feats = feats_in.float().contiguous()
         skips = []
         for li, layer in enumerate(enc.process_sparse):
             lv = _Level(g)

@@ -186,7 +186,13 @@ class InputLayer(nn.Module):
         if n and any(mx[a] >= ssz[a] for a in range(3)):
             raise ValueError('coordinate %s outside spatial_size %s' % (mx[:3], ssz))
         bs = int(input[2]) if len(input) > 2 else mx[3] + 1
-        dims = [max(1, min(ssz[a], mx[a] + 1)) for a in range(3)]
+        # Grid extent: the declared spatial_size (scn semantics for the strided output sizes) whenever the bitmask
+        # stays small; the reference's update_sizes quirk (App. C.2) declares absurd bounds at test time, then the
+        # data extent rounded up to a multiple of 64 is used (identical results for <= 6 stride-2 levels).
+        if max(bs, 1) * ssz[0] * ssz[1] * ssz[2] <= (1 << 31):
+            dims = list(ssz)
+        else:
+            dims = [max(1, min(ssz[a], (mx[a] + 64) // 64 * 64)) for a in range(3)]
         coords = coords.to(dev).contiguous()
         md = Metadata(self.dimension)
         md.batch_size = bs
