@@ -824,7 +824,10 @@ static int dispatch_ro(const ConvParams& p, bool vec, cudaStream_t st, bool* han
   // fill the chip (148 SMs x 3 CTAs) with those is latency bound (ncu: 45-80 us floors on the coarse levels), so
   // mid-size launches use S=2 and small ones S=1 (4x more, 4x shorter CTAs).
   if (p.child_mode && !vec) { *handled = false; return SGNN_OK; }
-  int sz = p.n_out >= 300000 ? 4 : (p.n_out >= 90000 ? 2 : 1);
+  long long t4 = 300000, t2 = 90000;
+  if (g_sgnn_conv_impl == 10) { t4 = 150000; t2 = 40000; }     // A/B: thresholds of the rows-per-thread policy
+  if (g_sgnn_conv_impl == 11) { t4 = 600000; t2 = 200000; }
+  int sz = p.n_out >= t4 ? 4 : (p.n_out >= t2 ? 2 : 1);
   if (g_sgnn_conv_impl == 6 && sz == 4) sz = 2;   // A/B: never 4 rows per thread
   if (g_sgnn_conv_impl == 7 && sz == 1) sz = 2;   // A/B: never 1 row per thread
 #define SGNN_RO_CASE(CO, CI, SS, CHH) \

@@ -58,11 +58,8 @@ def _fcn_bn(fcn, p3, lv0, x_raw, x_bn, dev):
     """FullyConvolutionalNet(reps=1, [c,c,c], residual) followed by BatchNormReLU(3c) (model.py:180-181,
     255-256).  Returns [n,3c].  x_raw is the p1 output, x_bn = BNReLU_{block0.bn0}(x_raw)."""
     s3, t3 = E.fold_bn(p3)
-    levels = [lv0]
-    mods = [fcn]
     # walk the nesting: U = Seq(ConcatTable(Id, resSeq), AddTable, ConcatTable(Id, Seq(BN, Conv, U', UnPool)), Join)
-    c = mods[0][0][1][1].nOut
-    width = 0
+    c = fcn[0][1][1].nOut
     m = fcn
     depth = 1
     while len(m) > 2:

@@ -218,7 +218,6 @@ class GenModel(nn.Module):
         nf_in += nf if pass_feats else 0
         self.surfacepred = SurfacePrediction(nf_in, nf, 1, self.refine_sizes[-1])
         self.return_long = True      # LongTensor coordinates at the boundary, like the reference
-        self._plan = None
         self._native = None
 
     # model.py:357-369.  The sizes are upper bounds of mode-0 InputLayers; the reference doubles
@@ -233,18 +232,6 @@ class GenModel(nn.Module):
                 refine_max_dim = refine_max_dim * 2
                 self.refinement[h].n0.spatial_size[k] = int(refine_max_dim[k])
             self.surfacepred.p0.spatial_size[k] = int(refine_max_dim[k])
-
-    def train(self, mode=True):
-        self._plan = None
-        return nn.Module.train(self, mode)
-
-    def _apply(self, fn, *a, **kw):
-        self._plan = None
-        return nn.Module._apply(self, fn, *a, **kw)
-
-    def load_state_dict(self, *a, **kw):
-        self._plan = None
-        return nn.Module.load_state_dict(self, *a, **kw)
 
     # ------------------------------------------------------------------ helpers
     def _locs_out(self, locs):

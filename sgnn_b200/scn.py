@@ -150,7 +150,8 @@ class JoinTable(nn.Module):
 class InputLayer(nn.Module):
     """scn.InputLayer(dimension, spatial_size, mode) -- model.py:31,178,185,253.  mode 0 only (the mode the
     reference uses): coordinates unique, rows keep caller order.  `spatial_size` stays an assignable
-    LongTensor(3) (model.py:364-369); it is an upper bound -- the grid is sized by the data extent."""
+    LongTensor(3) (model.py:364-369).  The bitmask grid covers the declared size (or, when update_sizes' quirk
+    declares an absurd bound, the data extent rounded up to 64 cells)."""
 
     def __init__(self, dimension, spatial_size, mode=3):
         nn.Module.__init__(self)
