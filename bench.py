@@ -224,7 +224,7 @@ def run_b200(args):
 
     def step(i):
         locs, feats = resident[i % args.sets]
-        return model([locs, feats], ones)
+        return model([locs, feats, args.blocks], ones)      # scn's [coords, features, batch_size] input form
 
     def barrier():
         if world > 1:
@@ -297,7 +297,7 @@ def run_b200(args):
         hl, hf = host[i % args.sets]
         dl = hl.to(dev, non_blocking=True)
         df = hf.to(dev, non_blocking=True)
-        (ol, osdf), _ = model([dl, df], ones)
+        (ol, osdf), _ = model([dl, df, args.blocks], ones)
         n = ol.shape[0]
         pin_l[:n].copy_(ol, non_blocking=True)          # result coordinates + TSDF back to pinned host memory
         pin_s[:n].copy_(osdf, non_blocking=True)
