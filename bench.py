@@ -295,7 +295,7 @@ def run_b200(args):
 
     def e2e_run(k, count):
         d2h = 0
-        tickets = []
+        prev = None
         runner.submit(host[0][0], host[0][1], args.blocks)
         for i in range(k):
             flush.fill_(i & 0xff)
@@ -303,17 +303,17 @@ def run_b200(args):
                 nl, nf = host[(i + 1) % args.sets]
                 runner.submit(nl, nf, args.blocks)             # H2D of step i+1 overlaps the compute of step i
             t = runner.step(ones)
-            tickets.append(t)
-            if len(tickets) > 1:
-                hl, hs = runner.result(tickets[-2])            # host-side result of step i-1 is complete
+            if prev is not None:
+                hl, hs = runner.result(prev)                   # host-side result of step i-1 is complete
                 if count:
                     d2h += hl.numel() * 8 + hs.numel() * 4
-        hl, hs = runner.result(tickets[-1])
+            prev = t
+        hl, hs = runner.result(prev)
         if count:
             d2h += hl.numel() * 8 + hs.numel() * 4
         return d2h
 
-    e2e_run(2, False)
+    e2e_run(4, False)
     barrier()
     e0.record()
     d2h = e2e_run(args.steps, True)

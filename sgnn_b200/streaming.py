@@ -15,12 +15,13 @@ import torch
 
 
 class StreamingRunner(object):
-    def __init__(self, model, depth=2, max_rows_out=None):
+    def __init__(self, model, depth=2, overlap_in=True, overlap_out=True):
         self.model = model
         self.dev = next(model.parameters()).device
         self.depth = depth
-        self.s_in = torch.cuda.Stream(device=self.dev)
-        self.s_out = torch.cuda.Stream(device=self.dev)
+        cur = torch.cuda.current_stream(self.dev)
+        self.s_in = torch.cuda.Stream(device=self.dev) if overlap_in else cur
+        self.s_out = torch.cuda.Stream(device=self.dev) if overlap_out else cur
         self.slots = [dict(locs=None, feats=None, ev=None) for _ in range(depth)]
         self.pins = [dict(locs=None, sdf=None) for _ in range(depth)]
         self.pending = collections.deque()     # submitted, H2D enqueued, not yet computed
@@ -75,8 +76,12 @@ class StreamingRunner(object):
             if m:
                 p['locs'][:m].copy_(ol, non_blocking=True)
                 p['sdf'][:m].copy_(osdf, non_blocking=True)
+                ol.record_stream(self.s_out)       # the caching allocator may recycle them once the copies are done
+                osdf.record_stream(self.s_out)
             out_ev.record(self.s_out)
-        return dict(slot=slot, m=m, ev=out_ev, keep=(ol, osdf), levels=levels)
+        # NOTE for callers: `levels` (per-hierarchy device outputs) and every live ticket pin device memory; holding
+        # many of them forces the allocator into fresh cudaMallocs each step.  Drop tickets once consumed.
+        return dict(slot=slot, m=m, ev=out_ev, levels=levels)
 
     def result(self, ticket):
         """Host tensors (views of the pinned result buffers, valid until `depth` more steps) of a finished step."""

@@ -219,14 +219,14 @@ def test_streaming_runner_matches_direct_calls():
     from sgnn_b200.streaming import StreamingRunner
     from sgnn_b200.synth import synthetic_batch
     dims = (32, 32, 32)
-    m = _model(dims, 2)
+    m = _model(dims, 0)
     batches = [synthetic_batch(nb, list(dims), occ, seed0=s) for nb, occ, s in
                [(2, 0.08, 1), (3, 0.05, 2), (1, 0.12, 3), (2, 0.03, 4), (3, 0.10, 5)]]
     nbs = [2, 3, 1, 2, 3]
     direct = []
     for (l, f), nb in zip(batches, nbs):
         (ol, os_), _ = m([l.cuda(), f.cuda(), nb], ONES)
-        direct.append((ol.cpu().clone(), os_.cpu().clone()))
+        direct.append(([], []) if isinstance(ol, list) else (ol.cpu().clone(), os_.cpu().clone()))
     pinned = [(l.pin_memory(), f.pin_memory()) for l, f in batches]
     r = StreamingRunner(m, depth=2)
     r.submit(pinned[0][0], pinned[0][1], nbs[0])
@@ -236,8 +236,14 @@ def test_streaming_runner_matches_direct_calls():
             r.submit(pinned[i + 1][0], pinned[i + 1][1], nbs[i + 1])
         t = r.step(ONES)
         if prev is not None:
-            hl, hs = r.result(prev[1])
-            assert torch.equal(hl, direct[prev[0]][0]) and torch.equal(hs, direct[prev[0]][1])
+            _check_host_result(r.result(prev[1]), direct[prev[0]])
         prev = (i, t)
-    hl, hs = r.result(prev[1])
-    assert torch.equal(hl, direct[prev[0]][0]) and torch.equal(hs, direct[prev[0]][1])
+    _check_host_result(r.result(prev[1]), direct[prev[0]])
+    assert sum(0 if isinstance(d[0], list) else d[0].shape[0] for d in direct) > 0
+
+
+def _check_host_result(got, want):
+    if isinstance(want[0], list):
+        assert isinstance(got[0], list)
+    else:
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
