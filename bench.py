@@ -42,6 +42,8 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ledger', default='', help='write the per-layer ledger JSON here')
     ap.add_argument('--conv-impl', type=int, default=0, help='sgnn_debug_set_conv_impl (kernel A/B runs)')
+    ap.add_argument('--conv-mode', default='exact', choices=['exact', 'tc32'],
+                    help="exact: fixed-order FFMA convolutions; tc32: Cout=16 convolutions on tcgen05 (3-way bf16 split)")
     return ap.parse_args()
 
 
@@ -212,6 +214,7 @@ def run_b200(args):
     model = model.to(dev).eval()
     shard.broadcast_parameters(model, src=0)          # the one collective of the path (2.57 MB)
     model.return_long = True
+    model.conv_mode = args.conv_mode
 
     # inputs: `sets` distinct batches per rank (global block id = (set*world + rank)*blocks + i), resident in HBM
     host, resident = [], []
@@ -268,6 +271,7 @@ def run_b200(args):
     # ---- same K steps again with a CUDA-event pair around every convolution launch (native SGNN_GEN_PROFILE):
     # the dominant kernel's live duration.  Kept out of the bracket above because it adds one sync per step.
     conv_ms, n_conv, prof_ms = 0.0, 0, 0.0
+    conv_table = []
     if rank == 0 and getattr(model, '_native', None) is not None:
         model._native.profile = True
         torch.cuda.synchronize()
@@ -279,6 +283,13 @@ def run_b200(args):
             conv_ms += model._native.last.conv_ms
             n_conv += model._native.last.n_conv
         p1.record()
+        import ctypes as _C
+        rec6, rms = (_C.c_int64 * 6)(), _C.c_float(0)
+        for ci in range(int(model._native.last.n_conv)):     # per-convolution times of the last profiled step
+            if lib.sgnn_generator_profile_entry(ci, rec6, _C.byref(rms)) != 0:
+                break
+            conv_table.append({'n_out': rec6[0], 'cin': rec6[1], 'cout': rec6[2], 'K': rec6[3], 'child': rec6[4],
+                               'tc': rec6[5], 'us': round(rms.value * 1e3, 2)})
         torch.cuda.synchronize()
         prof_ms = p0.elapsed_time(p1)
         model._native.profile = False
@@ -355,7 +366,9 @@ def run_b200(args):
     alg_bytes_total = per_set_bytes * args.steps
     achieved = alg_bytes_total / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0
     roofline = {
-        'kernel': 'sgnn_conv_forward = conv_ro_kernel<COUT,CIN,..> + conv_child_f32_kernel (all %d launches per step)'
+        'kernel': ('sgnn_conv_forward_tc32 = conv_tc32_kernel<Q,KG> + conv_tc32_child_kernel (tcgen05) for Cout=16, '
+                   'conv_ro_kernel (FFMA) for the rest (all %d convolutions per step)' if args.conv_mode == 'tc32' else
+                   'sgnn_conv_forward = conv_ro_kernel<COUT,CIN,..> + conv_child_f32_kernel (all %d launches per step)')
                   % round(convs_per_step),
         'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
         'traffic': None, 'peak_source': peak_src,
@@ -367,9 +380,11 @@ def run_b200(args):
         'achieved_tflops_fp32': per_set_flops * args.steps / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0,
         'fp32_ffma_peak_tflops': 148 * 128 * 2 * 1.965e9 / 1e12,
         'fp32_ffma_peak_tflops_measured': ffma_meas,
-        'note': 'fp32 FFMA path: activations are L2 resident and the kernel is FFMA / L2-gather bound, so the HBM '
-                'fraction (SURVEY 8(d) definition) is small by construction; achieved_tflops_fp32 vs the FFMA peak '
-                'is the meaningful ceiling for this dtype',
+        'note': ('tc32: fp32 features on tcgen05 via an exact 3-way bf16 split; activations are L2 resident, the kernel is '
+                 'L2-gather / shared-memory-store bound' if args.conv_mode == 'tc32' else
+                 'fp32 FFMA path: activations are L2 resident and the kernel is FFMA / L2-gather bound, so the HBM '
+                 'fraction (SURVEY 8(d) definition) is small by construction; achieved_tflops_fp32 vs the FFMA peak '
+                 'is the meaningful ceiling for this dtype'),
     }
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -389,7 +404,8 @@ def run_b200(args):
                    'parallelism': 'independent blocks, rank = block mod %d, one NCCL weight broadcast' % world,
                    'l2': '256 MiB flush before every step (inside the timed bracket); %d rotating input sets'
                          % args.sets,
-                   'params': 'deterministic hash fill seed %d (643735 params)' % args.param_seed},
+                   'params': 'deterministic hash fill seed %d (643735 params)' % args.param_seed,
+                   'conv_mode': args.conv_mode},
         'roofline': roofline, 'cpu_baseline': cpu,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d // args.steps,
                 'd2h_bytes_per_step': d2h // max(args.steps, 1), 'ms_per_step': e2e_ms / args.steps},
@@ -397,7 +413,8 @@ def run_b200(args):
     }
     if args.ledger:
         with open(args.ledger, 'w') as f:
-            json.dump({'ledger_set0': ledger, 'bytes': per_set_bytes, 'flops': per_set_flops}, f, indent=1)
+            json.dump({'ledger_set0': ledger, 'bytes': per_set_bytes, 'flops': per_set_flops,
+                       'conv_times_last_profiled_step': conv_table}, f, indent=1)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -144,6 +144,17 @@ typedef struct SgnnConvArgs {
 } SgnnConvArgs;
 int sgnn_conv_forward(const SgnnConvArgs* args, void* stream);
 
+/* ---- a3 / a4 / a9 on the tensor cores: the same operation as sgnn_conv_forward for fp32 features with Cout = 16
+ * and Cin <= 48 (every wide layer of the generator: model.py:179,186,254 and the FullyConvolutionalNet blocks),
+ * evaluated with tcgen05.mma on an exact 3-way bf16 split of features and filters (six bf16 partial products per
+ * fp32 product, fp32 accumulation in TMEM; csrc/conv_tc32.cu).  fp32 accuracy (relative ~1e-6 of the row magnitude),
+ * but NOT the fixed fmaf order of sgnn_conv_forward -- results are not bit-identical to it.  In child mode the 27
+ * filter offsets of each child collapse onto its 8 parent neighbours (filters pre-summed per child and parent
+ * offset).  `workspace`: dev scratch of sgnn_conv_tc32_workspace_bytes(K, cin, child_mode) bytes for the prepared
+ * filter bank (written by the call, on `stream`).  SGNN_E_UNSUPPORTED for shapes outside the above. */
+size_t sgnn_conv_tc32_workspace_bytes(int32_t K, int32_t cin, int32_t child_mode);
+int sgnn_conv_forward_tc32(const SgnnConvArgs* args, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- scn.Deconvolution(3,Cin,Cout,2,2) (north_star operator surface; upstream Deconvolution_updateOutput)
  *   out[i] = in[parent[i] >> 3] @ W[parent[i] & 7]          (rows with parent < 0 get zeros) */
 int sgnn_deconv_forward(const void* in, int32_t ld_in, int32_t dtype, const int32_t* parent,
@@ -275,9 +286,14 @@ typedef struct SgnnGeneratorOut {
 } SgnnGeneratorOut;
 #define SGNN_GEN_CAND_LOCS 1        /* materialise the candidate coordinates of every level (model.py:247,336) */
 #define SGNN_GEN_PROFILE 2          /* time every convolution launch with CUDA events (adds one sync at the end) */
+#define SGNN_GEN_TC32 4             /* run the Cout = 16 convolutions through sgnn_conv_forward_tc32 (tensor cores) */
 int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coords, int coords_i64, const float* feats,
                            int64_t n, int32_t nb, const int32_t* dims3, void* arena, size_t arena_bytes, int flags,
                            SgnnGeneratorOut* out, void* stream);
+
+/* Per-convolution record of the calling thread's last SGNN_GEN_PROFILE pass (i = 0 .. n_conv-1, launch order):
+ * rec6 = {n_out, cin, cout, K, child_mode, ran on tensor cores}, *ms = CUDA-event duration.  SGNN_E_INVALID past the end. */
+int sgnn_generator_profile_entry(int32_t i, int64_t* rec6, float* ms);
 
 /* Candidate coordinates of model.py:192-207: out dev [8*n_parent,4]. */
 int sgnn_children_coords(const int32_t* parent_coords, int64_t n_parent, int32_t* out, void* stream);

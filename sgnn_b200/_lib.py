@@ -83,6 +83,7 @@ class SgnnGeneratorOut(C.Structure):
 
 GEN_CAND_LOCS = 1
 GEN_PROFILE = 2
+GEN_TC32 = 4
 
 _P, _I, _L, _Z = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
 _G, _E = C.POINTER(SgnnGrid), C.POINTER(SgnnEpilogue)
@@ -98,6 +99,8 @@ SIGNATURES = {
     'sgnn_rulebook_submanifold': (_I, [_G, _P, _L, _P, _P]),
     'sgnn_rulebook_strided': (_I, [_G, _P, _L, _P, _P, _L, _P]),
     'sgnn_conv_forward': (_I, [C.POINTER(SgnnConvArgs), _P]),
+    'sgnn_conv_tc32_workspace_bytes': (_Z, [_I, _I, _I]),
+    'sgnn_conv_forward_tc32': (_I, [C.POINTER(SgnnConvArgs), _P, _Z, _P]),
     'sgnn_deconv_forward': (_I, [_P, _I, _I, _P, _P, _I, _I, _L, _E, _P]),
     'sgnn_unpool': (_I, [_P, _I, _P, _I, _L, _E, _P]),
     'sgnn_affine_relu': (_I, [_P, _I, _P, _I, _L, _I, _P, _P, _I, _P]),
@@ -115,6 +118,7 @@ SIGNATURES = {
     'sgnn_dense_write': (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     'sgnn_generator_forward': (_I, [C.POINTER(SgnnGeneratorW), _P, _I, _P, _L, _I, C.POINTER(C.c_int32), _P, _Z, _I,
                                     C.POINTER(SgnnGeneratorOut), _P]),
+    'sgnn_generator_profile_entry': (_I, [_I, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     'sgnn_children_coords': (_I, [_P, _L, _P, _P]),
     'sgnn_concat_skip': (_I, [_G, _P, _I, _I, _P, _L, _P, _I, _I, _P]),
     'sgnn_coords_to_i64': (_I, [_P, _L, _P, _P]),

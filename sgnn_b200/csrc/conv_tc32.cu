@@ -1,0 +1,592 @@
+// conv_tc32.cu -- fp32 sparse convolution on the 5th-generation tensor cores (tcgen05 + TMEM) by a 3-way bf16 split,
+// SURVEY §8 rows a3 / a4 / a9 for the fp32 generator (BASELINE.json configs[1]); the north_star's "tcgen05 tiles only
+// for the per-offset dense (Nactive x Cin).(Cin x Cout) contraction".
+//
+// Arithmetic.  Every fp32 value v is cut EXACTLY into three bf16 pieces v = v0 + v1 + v2 (8 + 8 + 8 significant bits,
+// by truncation: v0 = top 16 bits of v, v1 = top 16 bits of v - v0, v2 = v - v0 - v1, all differences exact in fp32).
+// The product x*w is evaluated as the six partial products x_i*w_j with i + j <= 2 (each exact in the fp32 accumulator;
+// the three dropped ones are below 2^-24 |x w|), accumulated in fp32 in TMEM (leading products and corrections in
+// separate accumulators, added in the epilogue).  The result has fp32 accuracy but the
+// tensor-core summation order is not the fmaf chain of conv.cu / oracle/o3.c, so this path is NOT bit-identical to the
+// FFMA path: it is selected explicitly (SGNN_GEN_TC32 / sgnn_conv_forward_tc32) and tested to 4e-6 of sum |x||w|.
+//
+// Layout.  Everything the tensor core reads is in the canonical K-major / no-swizzle core-matrix layout validated by
+// conv_tc.cu:  row r, 8-element (16-byte) K chunk c  ->  (r/8)*256 + c*128 + (r%8)*16   (SBO = 256 B, LBO = 128 B).
+// An "A block" is 128 rows x 16 bf16 (4096 B), a "B block" 16 (Cout) x 16 (Cin slice) bf16 (512 B).  A filter offset
+// with Cin = 16 Q channels uses Q x 3 A blocks (Q slices x 3 split planes), Q x 3 B blocks and 6 Q MMAs
+// (tcgen05.mma.cta_group::1.kind::f16, M128 N16 K16).
+//
+// Regular kernel (submanifold K = 27, strided K = 8): CTA = 128 threads = the 128 output rows of a tile; thread t
+// gathers ITS row's neighbour at every filter offset of the current group (one index, 32-byte vector loads), cuts it
+// into the three planes in registers and writes 16-byte chunks (8 consecutive lanes = 8 consecutive rows = 128
+// contiguous bytes: conflict free).  The rows of the NEXT work item are prefetched into registers while the MMAs of
+// the current one run; several CTAs per SM cover the rest of the latency.  Thread 0 issues the MMAs, commit ->
+// mbarrier; epilogue tcgen05.ld 32x32b.x16: thread t owns accumulator row t (residual, two affine+ReLU slots).
+//
+// Child-mode kernel (generative upsampling, model.py:192-207,224-225).  All 8 children of every parent exist, so for
+// child position c and filter offset d the neighbour is a child of parent-neighbour e = floor((c+d)/2) and
+//   out[8p+c] = sum_d x[p+e(c,d)] W[d] = sum_e x[p+e] W'_c[e],   W'_c[e] = sum_{d: e(c,d)=e} W[d]:
+// a 2x2x2 stencil per child over PARENT rows -- 64 (e,c) pairs instead of 216 (d,c) pairs.  A tile is 128 parents
+// (M = 128), the accumulators 2 x [128 x (8 children x 16)] fp32 = 256 TMEM columns; per parent offset e the 128 neighbour
+// rows (48 channels) are gathered ONCE and multiplied with the pre-summed filter of every child that uses e.
+#include "common.cuh"
+
+#define T32_M 128
+#define T32_ABLK 4096
+#define T32_BBLK 512
+
+extern int g_sgnn_conv_impl;
+
+struct Tc32Params {
+  const float* in; int ld_in; int cin;
+  const int* nbr; long long nbr_stride; int K;
+  const unsigned char* wsplit;
+  long long n_rows;     // output rows (regular) / parent rows (child mode)
+  const float* residual; int ld_res;
+  float* out_a; int ld_a; int relu_a; const float* scale_a; const float* shift_a;
+  float* out_b; int ld_b; int relu_b; const float* scale_b; const float* shift_b;
+};
+
+namespace {
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30) = 128 B, SBO>>4 [32,46) = 256 B, version 1 [46,48), no swizzle
+__device__ __forceinline__ unsigned long long umma_desc(unsigned saddr) {
+  return (unsigned long long)((saddr & 0x3FFFFu) >> 4) | (8ull << 16) | (16ull << 32) | (1ull << 46);
+}
+// InstrDescriptor: D fp32 (1<<4), A/B bf16 (1<<7, 1<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+#define T32_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24))
+
+__device__ __forceinline__ void cp16(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(g));
+}
+
+__device__ __forceinline__ void mma_bf16(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(T32_IDESC), "r"(acc));
+}
+
+__device__ __forceinline__ void mma_commit(unsigned long long* mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long* mbar, unsigned phase) {
+  const unsigned addr = smem_u32(mbar);
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(phase), "r"(0x989680)
+        : "memory");
+  } while (!ok);
+}
+
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// exact 3-way bf16 split of two fp32 values; element a goes to the low half (lower address), b to the high half
+__device__ __forceinline__ void split2(float a, float b, unsigned& p0, unsigned& p1, unsigned& p2) {
+  const unsigned ua = __float_as_uint(a), ub = __float_as_uint(b);
+  const float ra = a - __uint_as_float(ua & 0xffff0000u), rb = b - __uint_as_float(ub & 0xffff0000u);
+  const unsigned va = __float_as_uint(ra), vb = __float_as_uint(rb);
+  const float sa = ra - __uint_as_float(va & 0xffff0000u), sb = rb - __uint_as_float(vb & 0xffff0000u);
+  p0 = __byte_perm(ua, ub, 0x7632);
+  p1 = __byte_perm(va, vb, 0x7632);
+  p2 = __byte_perm(__float_as_uint(sa), __float_as_uint(sb), 0x7632);
+}
+
+// 8 consecutive channels of one row -> one 16-byte chunk in each of the three planes
+__device__ __forceinline__ void split8_store(const float (&x)[8], unsigned char* dst0, int plane_stride) {
+  uint4 h, m, l;
+  split2(x[0], x[1], h.x, m.x, l.x);
+  split2(x[2], x[3], h.y, m.y, l.y);
+  split2(x[4], x[5], h.z, m.z, l.z);
+  split2(x[6], x[7], h.w, m.w, l.w);
+  *reinterpret_cast<uint4*>(dst0) = h;
+  *reinterpret_cast<uint4*>(dst0 + plane_stride) = m;
+  *reinterpret_cast<uint4*>(dst0 + 2 * plane_stride) = l;
+}
+
+__device__ __forceinline__ void zero_store(unsigned char* dst0, int plane_stride) {
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(dst0) = z;
+  *reinterpret_cast<uint4*>(dst0 + plane_stride) = z;
+  *reinterpret_cast<uint4*>(dst0 + 2 * plane_stride) = z;
+}
+
+// 8 channels [c0, c0+8) of row `src` (channels >= cin read as 0).  A32: 32-byte aligned rows, one 256-bit load.
+template <bool A32>
+__device__ __forceinline__ void load8(const float* __restrict__ src, int c0, int cin, float (&x)[8]) {
+  if (A32) {
+    if (c0 + 8 <= cin) {
+      asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]), "=f"(x[4]), "=f"(x[5]), "=f"(x[6]), "=f"(x[7])
+                   : "l"(src + c0));
+      return;
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int cb = c0 + 4 * h;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cb < cin) {   // ld_in is a multiple of 4 >= cin, so the 16-byte load stays inside the row
+      v = __ldg(reinterpret_cast<const float4*>(src + cb));
+      if (cb + 1 >= cin) v.y = 0.f;
+      if (cb + 2 >= cin) v.z = 0.f;
+      if (cb + 3 >= cin) v.w = 0.f;
+    }
+    x[4 * h] = v.x; x[4 * h + 1] = v.y; x[4 * h + 2] = v.z; x[4 * h + 3] = v.w;
+  }
+}
+
+// accumulator row -> residual add, two output slots with optional affine + relu (SgnnEpilogue semantics)
+__device__ __forceinline__ void epilogue_row16(const Tc32Params& p, const unsigned (&v)[16], long long j) {
+#pragma unroll
+  for (int c = 0; c < 16; c += 4) {
+    float4 a = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]),
+                           __uint_as_float(v[c + 3]));
+    if (p.residual) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + j * p.ld_res + c));
+      a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+    }
+    if (p.out_a) {
+      float4 y = a;
+      if (p.scale_a) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale_a + c));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift_a + c));
+        y.x = fmaf(a.x, sc.x, sh.x); y.y = fmaf(a.y, sc.y, sh.y); y.z = fmaf(a.z, sc.z, sh.z); y.w = fmaf(a.w, sc.w, sh.w);
+      }
+      if (p.relu_a) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+      *reinterpret_cast<float4*>(p.out_a + j * p.ld_a + c) = y;
+    }
+    if (p.out_b) {
+      float4 y = a;
+      if (p.scale_b) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale_b + c));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift_b + c));
+        y.x = fmaf(a.x, sc.x, sh.x); y.y = fmaf(a.y, sc.y, sh.y); y.z = fmaf(a.z, sc.z, sh.z); y.w = fmaf(a.w, sc.w, sh.w);
+      }
+      if (p.relu_b) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+      *reinterpret_cast<float4*>(p.out_b + j * p.ld_b + c) = y;
+    }
+  }
+}
+
+// the six partial products of one (A slice, B slice) pair: planes (i, j), i + j <= 2.  The leading product x0*w0 goes
+// to the MAIN accumulator, the five correction products (2^-8 .. 2^-16 of it) to a separate CORRECTION accumulator;
+// the epilogue adds the two.  The tensor core rounds each accumulate step on its own (not round-to-nearest-even), so
+// keeping the small terms out of the main accumulator leaves it one rounding per (offset, slice) instead of six.
+__device__ __forceinline__ void mma_split6(unsigned tmem_main, unsigned tmem_corr, unsigned a_base, unsigned b_base,
+                                           unsigned first_acc) {
+  const int pi[5] = {2, 1, 0, 1, 0};
+  const int pj[5] = {0, 1, 2, 0, 1};
+#pragma unroll
+  for (int t = 0; t < 5; ++t)
+    mma_bf16(tmem_corr, umma_desc(a_base + pi[t] * T32_ABLK), umma_desc(b_base + pj[t] * T32_BBLK), t == 0 ? first_acc : 1u);
+  mma_bf16(tmem_main, umma_desc(a_base), umma_desc(b_base), first_acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// filter preparation: fp32 [K][cin][16] -> split planes in the canonical B layout, [K][Q][3][512 B]
+__device__ __forceinline__ void store_w_split(unsigned char* blk3, int co, int cil, float w) {
+  const unsigned u = __float_as_uint(w);
+  const float r = w - __uint_as_float(u & 0xffff0000u);
+  const unsigned v = __float_as_uint(r);
+  const float s = r - __uint_as_float(v & 0xffff0000u);
+  const int off = (co >> 3) * 256 + (cil >> 3) * 128 + (co & 7) * 16 + (cil & 7) * 2;
+  *reinterpret_cast<unsigned short*>(blk3 + off) = (unsigned short)(u >> 16);
+  *reinterpret_cast<unsigned short*>(blk3 + T32_BBLK + off) = (unsigned short)(v >> 16);
+  *reinterpret_cast<unsigned short*>(blk3 + 2 * T32_BBLK + off) = (unsigned short)(__float_as_uint(s) >> 16);
+}
+
+__global__ void tc32_prep_kernel(const float* __restrict__ w, int K, int cin, int Q, unsigned char* __restrict__ out) {
+  const int total = K * Q * 256;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int co = idx & 15, cil = (idx >> 4) & 15, kq = idx >> 8, qc = kq % Q, k = kq / Q;
+    const int ci = qc * 16 + cil;
+    const float v = ci < cin ? __ldg(w + ((size_t)k * cin + ci) * 16 + co) : 0.f;
+    store_w_split(out + (size_t)kq * 3 * T32_BBLK, co, cil, v);
+  }
+}
+
+// child mode: parent offset reached from child c (z-major bit order) by filter offset d -- same arithmetic as
+// conv_src_row() in conv.cu
+__device__ __forceinline__ int child_parent_offset(int c, int d) {
+  const int dz = d / 9 - 1, dy = (d / 3) % 3 - 1, dx = d % 3 - 1;
+  const int pz = (((c >> 2) & 1) + dz + 2) / 2 - 1;
+  const int py = (((c >> 1) & 1) + dy + 2) / 2 - 1;
+  const int px = ((c & 1) + dx + 2) / 2 - 1;
+  return (pz + 1) * 9 + (py + 1) * 3 + (px + 1);
+}
+// does child c read parent offset e at all?  (axis value -1 needs child bit 0, +1 needs child bit 1)
+__device__ __forceinline__ bool child_uses(int c, int e) {
+  const int ez = e / 9 - 1, ey = (e / 3) % 3 - 1, ex = e % 3 - 1;
+  const int cz = (c >> 2) & 1, cy = (c >> 1) & 1, cx = c & 1;
+  return (ez == 0 || ez == 2 * cz - 1) && (ey == 0 || ey == 2 * cy - 1) && (ex == 0 || ex == 2 * cx - 1);
+}
+
+// pre-summed child filters W'_c[e], pairs ordered by e then c: [64 pairs][3 slices][3 planes][512 B]
+__global__ void tc32_prep_child_kernel(const float* __restrict__ w, int cin, unsigned char* __restrict__ out) {
+  const int total = 64 * 3 * 256;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int co = idx & 15, cil = (idx >> 4) & 15, pq = idx >> 8, qc = pq % 3, pair = pq / 3;
+    int e = 0, c = 0, cnt = 0;
+    bool found = false;
+    for (int ee = 0; ee < 27 && !found; ++ee)
+      for (int cc = 0; cc < 8; ++cc)
+        if (child_uses(cc, ee)) {
+          if (cnt == pair) { e = ee; c = cc; found = true; break; }
+          ++cnt;
+        }
+    const int ci = qc * 16 + cil;
+    double s = 0.0;
+    if (ci < cin)
+      for (int d = 0; d < 27; ++d)
+        if (child_parent_offset(c, d) == e) s += (double)__ldg(w + ((size_t)d * cin + ci) * 16 + co);
+    store_w_split(out + (size_t)pq * 3 * T32_BBLK, co, cil, (float)s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int Q, int KG, bool A32>
+__global__ void __launch_bounds__(128)
+conv_tc32_kernel(Tc32Params p, long long n_tiles) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  constexpr int A_OFF = Q * 3 * T32_ABLK;   // bytes of A per filter offset
+  constexpr int B_OFF = Q * 3 * T32_BBLK;   // bytes of B per filter offset
+  unsigned char* As = sm;                   // [KG][Q][3][4096]
+  unsigned char* Bs = sm + KG * A_OFF;      // [KG][Q][3][512]
+  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ unsigned tmem_ptr_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr_s)), "r"(32));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::);
+  const unsigned tmem = tmem_ptr_s;
+  unsigned phase = 0;
+
+  const int ngroups = (p.K + KG - 1) / KG;
+  const long long my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const long long n_items = my_tiles * ngroups;
+
+  float x[KG][2 * Q][8];
+  int idx[KG], idx_next[KG];
+  const int row_off = (tid >> 3) * 256 + (tid & 7) * 16;   // this thread's row inside an A block
+
+  auto load_idx = [&](long long item, int (&dst)[KG]) {
+    const long long tile = blockIdx.x + (item / ngroups) * gridDim.x;
+    const int k0 = (int)(item % ngroups) * KG;
+    const long long j = tile * T32_M + tid;
+#pragma unroll
+    for (int kk = 0; kk < KG; ++kk)
+      dst[kk] = (k0 + kk < p.K && j < p.n_rows) ? __ldg(p.nbr + (long long)(k0 + kk) * p.nbr_stride + j) : -1;
+  };
+  auto load_rows = [&]() {
+#pragma unroll
+    for (int kk = 0; kk < KG; ++kk)
+      if (idx[kk] >= 0) {
+        const float* src = p.in + (long long)idx[kk] * p.ld_in;
+#pragma unroll
+        for (int u = 0; u < 2 * Q; ++u) load8<A32>(src, 8 * u, p.cin, x[kk][u]);
+      }
+  };
+
+  if (n_items > 0) {
+    load_idx(0, idx);
+    load_rows();
+    if (n_items > 1) load_idx(1, idx_next);
+  }
+  for (long long it = 0; it < n_items; ++it) {
+    const long long tile = blockIdx.x + (it / ngroups) * gridDim.x;
+    const int g = (int)(it % ngroups);
+    const int k0 = g * KG, kg = min(KG, p.K - k0);
+    // ---- stage item `it`: split the prefetched rows into the three planes, copy the prepared filter slices
+#pragma unroll
+    for (int kk = 0; kk < KG; ++kk)
+      if (kk < kg) {
+#pragma unroll
+        for (int u = 0; u < 2 * Q; ++u) {
+          unsigned char* dst = As + kk * A_OFF + (u >> 1) * (3 * T32_ABLK) + (u & 1) * 128 + row_off;
+          if (idx[kk] >= 0) split8_store(x[kk][u], dst, T32_ABLK);
+          else zero_store(dst, T32_ABLK);
+        }
+      }
+    {
+      const unsigned char* wsrc = p.wsplit + (size_t)k0 * B_OFF;
+      for (int i = tid; i < kg * (B_OFF / 16); i += 128) cp16(Bs + i * 16, wsrc + i * 16);
+      asm volatile("cp.async.commit_group;\n" ::);
+      asm volatile("cp.async.wait_group 0;\n" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::);   // generic-proxy writes -> visible to the tensor-core proxy
+    __syncthreads();                                      // item staged; previous epilogue's TMEM loads retired
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::);
+      for (int kk = 0; kk < kg; ++kk)
+#pragma unroll
+        for (int qc = 0; qc < Q; ++qc)
+          mma_split6(tmem, tmem + 16u, smem_u32(As + kk * A_OFF + qc * 3 * T32_ABLK),
+                     smem_u32(Bs + kk * B_OFF + qc * 3 * T32_BBLK), (k0 + kk == 0 && qc == 0) ? 0u : 1u);
+      mma_commit(&mbar);
+    }
+    // ---- prefetch the rows of item it+1 (and the indices of it+2) while the tensor core works
+    if (it + 1 < n_items) {
+#pragma unroll
+      for (int kk = 0; kk < KG; ++kk) idx[kk] = idx_next[kk];
+      load_rows();
+      if (it + 2 < n_items) load_idx(it + 2, idx_next);
+    }
+    mbar_wait(&mbar, phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::);
+    if (g == ngroups - 1) {
+      unsigned v[16], vc[16];
+      tmem_ld16(tmem + ((unsigned)(warp * 32) << 16), v);
+      tmem_ld16(tmem + ((unsigned)(warp * 32) << 16) + 16u, vc);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(vc[c]));
+      const long long j = tile * T32_M + tid;
+      if (j < p.n_rows) epilogue_row16(p, v, j);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// child mode: Cin = 48 (Q = 3), Cout = 16; p.n_rows = parent rows, output row 8 p + c
+__global__ void __launch_bounds__(128)
+conv_tc32_child_kernel(Tc32Params p, long long n_tiles) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  constexpr int Q = 3;
+  constexpr int A_BYTES = Q * 3 * T32_ABLK;     // 36864
+  constexpr int PAIR_BYTES = Q * 3 * T32_BBLK;  // 4608
+  unsigned char* As = sm;                       // [Q][3][4096]
+  unsigned char* Bs = sm + A_BYTES;             // [<= 8 pairs][Q][3][512]
+  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ unsigned tmem_ptr_s;
+  __shared__ int pair_start[28];
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr_s)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::);
+    int cnt = 0;
+    for (int e = 0; e < 27; ++e) {
+      pair_start[e] = cnt;
+      for (int c = 0; c < 8; ++c) cnt += child_uses(c, e) ? 1 : 0;
+    }
+    pair_start[27] = cnt;   // 64
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::);
+  const unsigned tmem = tmem_ptr_s;
+  unsigned phase = 0;
+
+  const long long my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const long long n_items = my_tiles * 27;
+  float x[2 * Q][8];
+  int idx = -1, idx_next = -1;
+  const int row_off = (tid >> 3) * 256 + (tid & 7) * 16;
+
+  auto load_idx = [&](long long item) -> int {
+    const long long tile = blockIdx.x + (item / 27) * gridDim.x;
+    const int e = (int)(item % 27);
+    const long long j = tile * T32_M + tid;
+    return j < p.n_rows ? __ldg(p.nbr + (long long)e * p.nbr_stride + j) : -1;
+  };
+  auto load_rows = [&]() {
+    if (idx >= 0) {
+      const float* src = p.in + (long long)idx * p.ld_in;
+#pragma unroll
+      for (int u = 0; u < 2 * Q; ++u) load8<true>(src, 8 * u, p.cin, x[u]);
+    }
+  };
+
+  if (n_items > 0) {
+    idx = load_idx(0);
+    load_rows();
+    if (n_items > 1) idx_next = load_idx(1);
+  }
+  unsigned written = 0;   // (thread 0) children whose accumulator columns hold data of the current tile
+  for (long long it = 0; it < n_items; ++it) {
+    const long long tile = blockIdx.x + (it / 27) * gridDim.x;
+    const int e = (int)(it % 27);
+#pragma unroll
+    for (int u = 0; u < 2 * Q; ++u) {
+      unsigned char* dst = As + (u >> 1) * (3 * T32_ABLK) + (u & 1) * 128 + row_off;
+      if (idx >= 0) split8_store(x[u], dst, T32_ABLK);
+      else zero_store(dst, T32_ABLK);
+    }
+    const int ps = pair_start[e], np = pair_start[e + 1] - ps;
+    {
+      const unsigned char* wsrc = p.wsplit + (size_t)ps * PAIR_BYTES;
+      for (int i = tid; i < np * (PAIR_BYTES / 16); i += 128) cp16(Bs + i * 16, wsrc + i * 16);
+      asm volatile("cp.async.commit_group;\n" ::);
+      asm volatile("cp.async.wait_group 0;\n" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::);
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::);
+      if (e == 0) written = 0;
+      int slot = 0;
+      for (int c = 0; c < 8; ++c) {
+        if (!child_uses(c, e)) continue;
+        const unsigned d = tmem + 16u * c;
+        const unsigned had = (written >> c) & 1u;
+#pragma unroll
+        for (int qc = 0; qc < Q; ++qc)
+          mma_split6(d, d + 128u, smem_u32(As + qc * 3 * T32_ABLK), smem_u32(Bs + slot * PAIR_BYTES + qc * 3 * T32_BBLK),
+                     (qc == 0 && !had) ? 0u : 1u);
+        written |= 1u << c;
+        ++slot;
+      }
+      mma_commit(&mbar);
+    }
+    if (it + 1 < n_items) {
+      idx = idx_next;
+      load_rows();
+      if (it + 2 < n_items) idx_next = load_idx(it + 2);
+    }
+    mbar_wait(&mbar, phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::);
+    if (e == 26) {
+      const long long pj = tile * T32_M + tid;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        unsigned v[16], vc[16];
+        tmem_ld16(tmem + ((unsigned)(warp * 32) << 16) + 16u * c, v);
+        tmem_ld16(tmem + ((unsigned)(warp * 32) << 16) + 128u + 16u * c, vc);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(vc[q]));
+        if (pj < p.n_rows) epilogue_row16(p, v, pj * 8 + c);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+}
+
+bool al(const void* p, uintptr_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
+
+template <int Q, int KG, bool A32>
+int launch_regular(const Tc32Params& p, cudaStream_t st) {
+  constexpr size_t smem = (size_t)KG * Q * 3 * (T32_ABLK + T32_BBLK);
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_kernel<Q, KG, A32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    SGNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tc32_kernel<Q, KG, A32>, 128, smem));
+    ctas_per_sm = occ < 1 ? 1 : (occ > 8 ? 8 : occ);
+  }
+  const long long tiles = (p.n_rows + T32_M - 1) / T32_M;
+  long long grid = (long long)148 * ctas_per_sm;
+  if (grid > tiles) grid = tiles;
+  conv_tc32_kernel<Q, KG, A32><<<(int)grid, 128, smem, st>>>(p, tiles);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+}  // namespace
+
+extern "C" size_t sgnn_conv_tc32_workspace_bytes(int32_t K, int32_t cin, int32_t child_mode) {
+  const int Q = (cin + 15) / 16;
+  return child_mode ? (size_t)64 * 3 * 3 * T32_BBLK : (size_t)K * Q * 3 * T32_BBLK;
+}
+
+extern "C" int sgnn_conv_forward_tc32(const SgnnConvArgs* a, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!a || a->n_out < 0 || a->cin <= 0 || !a->weight) return SGNN_E_INVALID;
+  if (a->dtype != SGNN_F32 || a->cout != 16 || a->cin > 48) return SGNN_E_UNSUPPORTED;
+  if (a->K != 27 && a->K != 8) return SGNN_E_UNSUPPORTED;
+  if (a->child_mode && (a->K != 27 || a->cin != 48 || a->residual || (a->n_out & 7))) return SGNN_E_UNSUPPORTED;
+  if (a->n_out == 0) return SGNN_OK;
+  if (!a->a.out && !a->b.out) return SGNN_E_INVALID;
+  if (!a->in || !a->nbr || !workspace) return SGNN_E_INVALID;
+  if (workspace_bytes < sgnn_conv_tc32_workspace_bytes(a->K, a->cin, a->child_mode)) return SGNN_E_NOMEM;
+  const SgnnEpilogue* eps[2] = {&a->a, &a->b};
+  for (int i = 0; i < 2; ++i) {
+    const SgnnEpilogue& e = *eps[i];
+    if (!e.out) continue;
+    if ((e.scale == nullptr) != (e.shift == nullptr)) return SGNN_E_INVALID;
+    if (!al(e.out, 16) || (e.ld & 3) || (e.scale && (!al(e.scale, 16) || !al(e.shift, 16)))) return SGNN_E_ALIGN;
+  }
+  if (!al(a->in, 16) || (a->ld_in & 3) || a->ld_in < a->cin || !al(workspace, 16)) return SGNN_E_ALIGN;
+  if (a->residual && (!al(a->residual, 16) || (a->ld_res & 3))) return SGNN_E_ALIGN;
+  const bool a32 = al(a->in, 32) && (a->ld_in & 7) == 0;
+  if (a->child_mode && !a32) return SGNN_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Q = (a->cin + 15) / 16;
+  Tc32Params p;
+  p.in = (const float*)a->in; p.ld_in = a->ld_in; p.cin = a->cin;
+  p.nbr = a->nbr; p.nbr_stride = a->nbr_stride; p.K = a->K;
+  p.wsplit = (const unsigned char*)workspace;
+  p.n_rows = a->child_mode ? a->n_out / 8 : a->n_out;
+  p.residual = (const float*)a->residual; p.ld_res = a->ld_res;
+  p.out_a = (float*)a->a.out; p.ld_a = a->a.ld; p.relu_a = a->a.relu; p.scale_a = a->a.scale; p.shift_a = a->a.shift;
+  p.out_b = (float*)a->b.out; p.ld_b = a->b.ld; p.relu_b = a->b.relu; p.scale_b = a->b.scale; p.shift_b = a->b.shift;
+  if (a->child_mode) {
+    tc32_prep_child_kernel<<<96, 512, 0, st>>>((const float*)a->weight, a->cin, (unsigned char*)workspace);
+    SGNN_CHECK_LAUNCH();
+    constexpr size_t smem = (size_t)3 * 3 * T32_ABLK + (size_t)8 * 3 * 3 * T32_BBLK;
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
+      SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_child_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int occ = 0;
+      SGNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tc32_child_kernel, 128, smem));
+      ctas_per_sm = occ < 1 ? 1 : (occ > 2 ? 2 : occ);   // 256 TMEM columns each (main + correction accumulators)
+    }
+    const long long tiles = (p.n_rows + T32_M - 1) / T32_M;
+    long long grid = (long long)148 * ctas_per_sm;
+    if (grid > tiles) grid = tiles;
+    conv_tc32_child_kernel<<<(int)grid, 128, smem, st>>>(p, tiles);
+    SGNN_CHECK_LAUNCH();
+    return SGNN_OK;
+  }
+  {
+    const int total = a->K * Q * 256;
+    tc32_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)a->weight, a->K, a->cin, Q, (unsigned char*)workspace);
+    SGNN_CHECK_LAUNCH();
+  }
+  const bool kg1 = g_sgnn_conv_impl == 21;   // A/B: one filter offset per work item for 16-channel inputs
+  if (Q == 1) {
+    if (kg1) return a32 ? launch_regular<1, 1, true>(p, st) : launch_regular<1, 1, false>(p, st);
+    return a32 ? launch_regular<1, 3, true>(p, st) : launch_regular<1, 3, false>(p, st);
+  }
+  if (Q == 2) return a32 ? launch_regular<2, 1, true>(p, st) : launch_regular<2, 1, false>(p, st);
+  return a32 ? launch_regular<3, 1, true>(p, st) : launch_regular<3, 1, false>(p, st);
+}

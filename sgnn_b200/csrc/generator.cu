@@ -29,12 +29,17 @@ struct Ctx {
   cudaStream_t st;
   void* stream;
   bool profile;
+  bool tc32;
   int n_ev;
 };
 
 // event pool for SGNN_GEN_PROFILE (pairs around every sgnn_conv_forward of the pass)
 static thread_local cudaEvent_t g_ev[512];
 static thread_local int g_ev_made = 0;
+// shapes + durations of the convolutions of the last profiled pass (sgnn_generator_profile_entry)
+struct ConvRec { int64_t n_out; int cin, cout, K, child, tc; float ms; };
+static thread_local ConvRec g_rec[256];
+static thread_local int g_nrec = 0;
 
 struct Epi {
   float* out; int ld; const float* scale; const float* shift; int relu;
@@ -168,14 +173,25 @@ static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr,
   x.child_mode = child; x.weight = w; x.cin = cin; x.cout = cout; x.n_out = n_out; x.residual = res; x.ld_res = ld_res;
   x.a.out = a.out; x.a.ld = a.ld; x.a.relu = a.relu; x.a.scale = a.scale; x.a.shift = a.shift;
   x.b.out = b.out; x.b.ld = b.ld; x.b.relu = b.relu; x.b.scale = b.scale; x.b.shift = b.shift;
-  const bool prof = c.profile && c.n_ev + 2 <= 512;
+  const bool prof = c.profile && c.n_ev + 2 <= 512;   // 256 records
   if (prof) {
     while (g_ev_made < c.n_ev + 2) SGNN_CUDA(cudaEventCreate(&g_ev[g_ev_made++]));
     SGNN_CUDA(cudaEventRecord(g_ev[c.n_ev], c.st));
   }
-  const int rc = sgnn_conv_forward(&x, c.stream);
+  int rc = SGNN_E_UNSUPPORTED;
+  bool used_tc = false;
+  if (c.tc32 && cout == 16 && cin >= 12 && cin <= 48 && (!child || cin == 48)) {
+    const size_t wb = sgnn_conv_tc32_workspace_bytes(K, cin, child);
+    void* ws = c.ar.get(wb);
+    if (!ws) return SGNN_E_NOMEM;
+    rc = sgnn_conv_forward_tc32(&x, ws, wb, c.stream);
+    used_tc = rc == SGNN_OK;
+  }
+  if (rc == SGNN_E_UNSUPPORTED || rc == SGNN_E_ALIGN) rc = sgnn_conv_forward(&x, c.stream);
   if (prof) {
     SGNN_CUDA(cudaEventRecord(g_ev[c.n_ev + 1], c.st));
+    ConvRec& r = g_rec[c.n_ev / 2];
+    r.n_out = n_out; r.cin = cin; r.cout = cout; r.K = K; r.child = child; r.tc = used_tc ? 1 : 0; r.ms = 0.f;
     c.n_ev += 2;
   }
   return rc;
@@ -252,6 +268,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
   c.ar.base = (char*)arena; c.ar.cap = arena_bytes; c.ar.off = 0; c.ar.high = 0; c.ar.oom = false;
   c.st = (cudaStream_t)stream; c.stream = stream;
   c.profile = (flags & SGNN_GEN_PROFILE) != 0; c.n_ev = 0;
+  c.tc32 = (flags & SGNN_GEN_TC32) != 0;
   int rc = SGNN_OK;
   do {
 #define GEN(call)                 \
@@ -463,7 +480,9 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       float t = 0.f;
       SGNN_CUDA(cudaEventElapsedTime(&t, g_ev[i], g_ev[i + 1]));
       ms += t;
+      g_rec[i / 2].ms = t;
     }
+    g_nrec = c.n_ev / 2;
     out->conv_ms = ms;
     out->n_conv = c.n_ev / 2;
   }
@@ -472,4 +491,13 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
   if (c.ar.oom && rc == SGNN_OK) rc = SGNN_E_NOMEM;
   if (c.ar.oom) rc = SGNN_E_NOMEM;
   return rc;
+}
+
+// i-th convolution of the calling thread's last SGNN_GEN_PROFILE pass: rec = {n_out, cin, cout, K, child_mode, tensor-core}
+extern "C" int sgnn_generator_profile_entry(int32_t i, int64_t* rec6, float* ms) {
+  if (i < 0 || i >= g_nrec || !rec6 || !ms) return SGNN_E_INVALID;
+  const ConvRec& r = g_rec[i];
+  rec6[0] = r.n_out; rec6[1] = r.cin; rec6[2] = r.cout; rec6[3] = r.K; rec6[4] = r.child; rec6[5] = r.tc;
+  *ms = r.ms;
+  return SGNN_OK;
 }

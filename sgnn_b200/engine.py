@@ -148,9 +148,11 @@ def _epilogue(out, scale=None, shift=None, relu=False):
 
 
 def conv(x, nbr, weight, n_out, out_a, child_mode=False, residual=None, scale_a=None, shift_a=None,
-         relu_a=False, out_b=None, scale_b=None, shift_b=None, relu_b=False):
+         relu_a=False, out_b=None, scale_b=None, shift_b=None, relu_b=False, tc32=False):
     """a3/a4/a9: out[j] = sum_k x[nbr[k][j]] @ W[k]  (+residual, affine, relu; two output slots).
-    x / out_* may be column views of wider row-major buffers (stride(1) == 1)."""
+    x / out_* may be column views of wider row-major buffers (stride(1) == 1).
+    tc32=True: the tensor-core path for fp32 features (sgnn_conv_forward_tc32: Cout = 16, Cin <= 48; fp32 accuracy,
+    not the fixed fmaf order); raises for unsupported shapes."""
     _need_cuda(x, nbr, weight, out_a, residual, out_b)
     K, cin, cout = weight.shape
     assert weight.is_contiguous() and weight.dtype in (torch.float32, torch.bfloat16)
@@ -178,7 +180,12 @@ def conv(x, nbr, weight, n_out, out_a, child_mode=False, residual=None, scale_a=
     a.b = _epilogue(out_b, scale_b, shift_b, relu_b)
     ctx = PROFILER.conv(x, nbr, weight, int(n_out), child_mode, residual is not None,
                         out_b is not None) if PROFILER is not None else None
-    check(lib.sgnn_conv_forward(C.byref(a), _stream()), 'sgnn_conv_forward')
+    if tc32:
+        wb = lib.sgnn_conv_tc32_workspace_bytes(K, cin, a.child_mode)
+        ws = _scratch(wb, x.device)
+        check(lib.sgnn_conv_forward_tc32(C.byref(a), C.c_void_p(ws.data_ptr()), wb, _stream()), 'sgnn_conv_forward_tc32')
+    else:
+        check(lib.sgnn_conv_forward(C.byref(a), _stream()), 'sgnn_conv_forward')
     if ctx is not None:
         ctx.done()
     return out_a

@@ -219,6 +219,9 @@ class GenModel(nn.Module):
         self.surfacepred = SurfacePrediction(nf_in, nf, 1, self.refine_sizes[-1])
         self.return_long = True      # LongTensor coordinates at the boundary, like the reference
         self._native = None
+        # 'exact': fixed-order FFMA convolutions (bit-reproducible, == oracle/o3.c);  'tc32': the Cout = 16 convolutions
+        # of the native generator run on the tensor cores (3-way bf16 split, fp32 accuracy, not bit-identical)
+        self.conv_mode = 'exact'
 
     # model.py:357-369.  The sizes are upper bounds of mode-0 InputLayers; the reference doubles
     # refine_max_dim inside the k loop -- mirrored, not "fixed": bounds only grow.
