@@ -44,6 +44,7 @@ def parse():
     ap.add_argument('--conv-impl', type=int, default=0, help='sgnn_debug_set_conv_impl (kernel A/B runs)')
     ap.add_argument('--conv-mode', default='exact', choices=['exact', 'tc32'],
                     help="exact: fixed-order FFMA convolutions; tc32: Cout=16 convolutions on tcgen05 (3-way bf16 split)")
+    ap.add_argument('--tc32-min-rows', type=int, default=-1, help='sgnn_debug_set_tc32_min_rows (A/B runs)')
     return ap.parse_args()
 
 
@@ -207,6 +208,8 @@ def run_b200(args):
         dist.init_process_group('nccl', device_id=dev)
     ones = np.ones(5, dtype=np.float32)
     lib.sgnn_debug_set_conv_impl(args.conv_impl)
+    if args.tc32_min_rows >= 0:
+        lib.sgnn_debug_set_tc32_min_rows(args.tc32_min_rows)
 
     model = sgnn_b200.GenModel(8, 64, 1, 16, 16, 4, True, True, 1, 1)
     if rank == 0:

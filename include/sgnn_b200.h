@@ -313,6 +313,9 @@ int64_t sgnn_launch_count(void);
  * 2 = runtime-shape kernel).  All give bit-identical results. */
 void sgnn_debug_set_conv_impl(int impl);
 
+/* Tuning hook: under SGNN_GEN_TC32 only convolutions with at least n output rows use the tensor-core path (default 60000). */
+void sgnn_debug_set_tc32_min_rows(int64_t n);
+
 /* Measures the sustained 3-register FFMA rate of the device (TFLOP/s): roofline denominator of the fp32 kernels. */
 int sgnn_debug_ffma_peak(int iters, double* tflops, void* stream);
 

@@ -25,7 +25,7 @@ echo "bench exact rc=$?"; cat gpurun_out/bench_exact.json | cut -c1-400
 
 MODE=exact
 KREGEX='regex:conv_ro_kernel|conv_child'
-if [ "$TC_RC" = "0" ]; then
+if [ "$TC_RC" = "0" ] || [ "$FORCE_TC" = "1" ]; then
   MODE=tc32
   KREGEX='regex:conv_tc32'
   stamp bench-tc32

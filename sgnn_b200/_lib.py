@@ -123,6 +123,7 @@ SIGNATURES = {
     'sgnn_concat_skip': (_I, [_G, _P, _I, _I, _P, _L, _P, _I, _I, _P]),
     'sgnn_coords_to_i64': (_I, [_P, _L, _P, _P]),
     'sgnn_debug_set_conv_impl': (None, [_I]),
+    'sgnn_debug_set_tc32_min_rows': (None, [_L]),
     'sgnn_debug_ffma_peak': (_I, [_I, C.POINTER(C.c_double), _P]),
     'sgnn_launch_count': (_L, []),
     'sgnn_version': (_I, []),

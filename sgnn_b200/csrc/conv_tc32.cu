@@ -34,6 +34,8 @@
 #define T32_M 128
 #define T32_ABLK 4096
 #define T32_BBLK 512
+#define T32_COLS 128   // TMEM columns of the regular kernel: 7 main accumulators (16 each) + the correction accumulator
+#define T32_CORR 112u
 
 extern int g_sgnn_conv_impl;
 
@@ -193,13 +195,13 @@ __device__ __forceinline__ void epilogue_row16(const Tc32Params& p, const unsign
 // the epilogue adds the two.  The tensor core rounds each accumulate step on its own (not round-to-nearest-even), so
 // keeping the small terms out of the main accumulator leaves it one rounding per (offset, slice) instead of six.
 __device__ __forceinline__ void mma_split6(unsigned tmem_main, unsigned tmem_corr, unsigned a_base, unsigned b_base,
-                                           unsigned first_acc) {
+                                           unsigned acc_main, unsigned acc_corr) {
   const int pi[5] = {2, 1, 0, 1, 0};
   const int pj[5] = {0, 1, 2, 0, 1};
 #pragma unroll
   for (int t = 0; t < 5; ++t)
-    mma_bf16(tmem_corr, umma_desc(a_base + pi[t] * T32_ABLK), umma_desc(b_base + pj[t] * T32_BBLK), t == 0 ? first_acc : 1u);
-  mma_bf16(tmem_main, umma_desc(a_base), umma_desc(b_base), first_acc);
+    mma_bf16(tmem_corr, umma_desc(a_base + pi[t] * T32_ABLK), umma_desc(b_base + pj[t] * T32_BBLK), t == 0 ? acc_corr : 1u);
+  mma_bf16(tmem_main, umma_desc(a_base), umma_desc(b_base), acc_main);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -277,7 +279,7 @@ conv_tc32_kernel(Tc32Params p, long long n_tiles) {
 
   const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr_s)), "r"(32));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr_s)), "r"(T32_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   if (tid == 0) {
@@ -291,6 +293,7 @@ conv_tc32_kernel(Tc32Params p, long long n_tiles) {
   unsigned phase = 0;
 
   const int ngroups = (p.K + KG - 1) / KG;
+  const int n_main = (p.K + 3) >> 2;   // main accumulators in use (filter offset k accumulates into column 16 (k >> 2))
   const long long my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
   const long long n_items = my_tiles * ngroups;
 
@@ -325,7 +328,13 @@ conv_tc32_kernel(Tc32Params p, long long n_tiles) {
     const long long tile = blockIdx.x + (it / ngroups) * gridDim.x;
     const int g = (int)(it % ngroups);
     const int k0 = g * KG, kg = min(KG, p.K - k0);
-    // ---- stage item `it`: split the prefetched rows into the three planes, copy the prepared filter slices
+    // ---- stage item `it`: copy the prepared filter slices (asynchronously, under the conversion below), split the
+    // prefetched rows into the three planes
+    {
+      const unsigned char* wsrc = p.wsplit + (size_t)k0 * B_OFF;
+      for (int i = tid; i < kg * (B_OFF / 16); i += 128) cp16(Bs + i * 16, wsrc + i * 16);
+      asm volatile("cp.async.commit_group;\n" ::);
+    }
 #pragma unroll
     for (int kk = 0; kk < KG; ++kk)
       if (kk < kg) {
@@ -336,21 +345,19 @@ conv_tc32_kernel(Tc32Params p, long long n_tiles) {
           else zero_store(dst, T32_ABLK);
         }
       }
-    {
-      const unsigned char* wsrc = p.wsplit + (size_t)k0 * B_OFF;
-      for (int i = tid; i < kg * (B_OFF / 16); i += 128) cp16(Bs + i * 16, wsrc + i * 16);
-      asm volatile("cp.async.commit_group;\n" ::);
-      asm volatile("cp.async.wait_group 0;\n" ::);
-    }
+    asm volatile("cp.async.wait_group 0;\n" ::);
     asm volatile("fence.proxy.async.shared::cta;" ::);   // generic-proxy writes -> visible to the tensor-core proxy
     __syncthreads();                                      // item staged; previous epilogue's TMEM loads retired
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::);
-      for (int kk = 0; kk < kg; ++kk)
+      for (int kk = 0; kk < kg; ++kk) {
+        const int k = k0 + kk;
 #pragma unroll
         for (int qc = 0; qc < Q; ++qc)
-          mma_split6(tmem, tmem + 16u, smem_u32(As + kk * A_OFF + qc * 3 * T32_ABLK),
-                     smem_u32(Bs + kk * B_OFF + qc * 3 * T32_BBLK), (k0 + kk == 0 && qc == 0) ? 0u : 1u);
+          mma_split6(tmem + 16u * (unsigned)(k >> 2), tmem + T32_CORR, smem_u32(As + kk * A_OFF + qc * 3 * T32_ABLK),
+                     smem_u32(Bs + kk * B_OFF + qc * 3 * T32_BBLK), ((k & 3) == 0 && qc == 0) ? 0u : 1u,
+                     (k == 0 && qc == 0) ? 0u : 1u);
+      }
       mma_commit(&mbar);
     }
     // ---- prefetch the rows of item it+1 (and the indices of it+2) while the tensor core works
@@ -364,11 +371,15 @@ conv_tc32_kernel(Tc32Params p, long long n_tiles) {
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::);
     if (g == ngroups - 1) {
+      // sum of the partial accumulators in fp32 round-to-nearest (unbiased), corrections first
       unsigned v[16], vc[16];
-      tmem_ld16(tmem + ((unsigned)(warp * 32) << 16), v);
-      tmem_ld16(tmem + ((unsigned)(warp * 32) << 16) + 16u, vc);
+      const unsigned lane_base = tmem + ((unsigned)(warp * 32) << 16);
+      tmem_ld16(lane_base + T32_CORR, v);
+      for (int a = n_main - 1; a >= 0; --a) {
+        tmem_ld16(lane_base + 16u * (unsigned)a, vc);
 #pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(vc[c]));
+        for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(vc[c]));
+      }
       const long long j = tile * T32_M + tid;
       if (j < p.n_rows) epilogue_row16(p, v, j);
       asm volatile("tcgen05.fence::before_thread_sync;" ::);
@@ -376,7 +387,7 @@ conv_tc32_kernel(Tc32Params p, long long n_tiles) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::);
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(T32_COLS));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -443,19 +454,19 @@ conv_tc32_child_kernel(Tc32Params p, long long n_tiles) {
   for (long long it = 0; it < n_items; ++it) {
     const long long tile = blockIdx.x + (it / 27) * gridDim.x;
     const int e = (int)(it % 27);
+    const int ps = pair_start[e], np = pair_start[e + 1] - ps;
+    {   // pre-summed filters of the children that read parent offset e: asynchronous, lands under the conversion below
+      const unsigned char* wsrc = p.wsplit + (size_t)ps * PAIR_BYTES;
+      for (int i = tid; i < np * (PAIR_BYTES / 16); i += 128) cp16(Bs + i * 16, wsrc + i * 16);
+      asm volatile("cp.async.commit_group;\n" ::);
+    }
 #pragma unroll
     for (int u = 0; u < 2 * Q; ++u) {
       unsigned char* dst = As + (u >> 1) * (3 * T32_ABLK) + (u & 1) * 128 + row_off;
       if (idx >= 0) split8_store(x[u], dst, T32_ABLK);
       else zero_store(dst, T32_ABLK);
     }
-    const int ps = pair_start[e], np = pair_start[e + 1] - ps;
-    {
-      const unsigned char* wsrc = p.wsplit + (size_t)ps * PAIR_BYTES;
-      for (int i = tid; i < np * (PAIR_BYTES / 16); i += 128) cp16(Bs + i * 16, wsrc + i * 16);
-      asm volatile("cp.async.commit_group;\n" ::);
-      asm volatile("cp.async.wait_group 0;\n" ::);
-    }
+    asm volatile("cp.async.wait_group 0;\n" ::);
     asm volatile("fence.proxy.async.shared::cta;" ::);
     __syncthreads();
     if (tid == 0) {
@@ -469,7 +480,7 @@ conv_tc32_child_kernel(Tc32Params p, long long n_tiles) {
 #pragma unroll
         for (int qc = 0; qc < Q; ++qc)
           mma_split6(d, d + 128u, smem_u32(As + qc * 3 * T32_ABLK), smem_u32(Bs + slot * PAIR_BYTES + qc * 3 * T32_BBLK),
-                     (qc == 0 && !had) ? 0u : 1u);
+                     (qc == 0 && !had) ? 0u : 1u, (qc == 0 && !had) ? 0u : 1u);
         written |= 1u << c;
         ++slot;
       }
@@ -504,15 +515,29 @@ conv_tc32_child_kernel(Tc32Params p, long long n_tiles) {
 
 bool al(const void* p, uintptr_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
 
+// CTAs of 128 threads one SM holds: shared memory (227 KB usable, 1 KB reserved per CTA), registers (64 K, allocated
+// per warp in units of 8 per thread) and TMEM columns.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor answered 1 for
+// these kernels -- it assumes the default shared-memory carve-out -- which left three quarters of each SM idle.)
+int resident_ctas(const void* fn, size_t dyn_smem, int tmem_limit) {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) { g_sgnn_last_cuda_error = (int)cudaGetLastError(); return -1; }
+  const int by_smem = (int)((227 * 1024) / (dyn_smem + fa.sharedSizeBytes + 1024));
+  const int regs = (fa.numRegs + 7) & ~7;
+  const int by_regs = 65536 / (regs * 128);
+  int n = by_smem < by_regs ? by_smem : by_regs;
+  if (n > tmem_limit) n = tmem_limit;
+  return n < 1 ? 1 : n;
+}
+
 template <int Q, int KG, bool A32>
 int launch_regular(const Tc32Params& p, cudaStream_t st) {
   constexpr size_t smem = (size_t)KG * Q * 3 * (T32_ABLK + T32_BBLK);
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
     SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_kernel<Q, KG, A32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    SGNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tc32_kernel<Q, KG, A32>, 128, smem));
-    ctas_per_sm = occ < 1 ? 1 : (occ > 8 ? 8 : occ);
+    SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_kernel<Q, KG, A32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    ctas_per_sm = resident_ctas((const void*)conv_tc32_kernel<Q, KG, A32>, smem, 512 / T32_COLS);
+    if (ctas_per_sm < 0) return SGNN_E_CUDA;
   }
   const long long tiles = (p.n_rows + T32_M - 1) / T32_M;
   long long grid = (long long)148 * ctas_per_sm;
@@ -566,9 +591,9 @@ extern "C" int sgnn_conv_forward_tc32(const SgnnConvArgs* a, void* workspace, si
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) {
       SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_child_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int occ = 0;
-      SGNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tc32_child_kernel, 128, smem));
-      ctas_per_sm = occ < 1 ? 1 : (occ > 2 ? 2 : occ);   // 256 TMEM columns each (main + correction accumulators)
+      SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_child_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      ctas_per_sm = resident_ctas((const void*)conv_tc32_child_kernel, smem, 2);   // 256 TMEM columns each
+      if (ctas_per_sm < 0) return SGNN_E_CUDA;
     }
     const long long tiles = (p.n_rows + T32_M - 1) / T32_M;
     long long grid = (long long)148 * ctas_per_sm;

@@ -8,6 +8,11 @@
 #include <string.h>
 #include "common.cuh"
 
+// SGNN_GEN_TC32: convolutions with fewer output rows stay on the FFMA kernels (a launch that cannot fill the chip with
+// 128-row tiles is latency bound either way, and the FFMA kernel's per-tile latency is shorter)
+long long g_sgnn_tc32_min_rows = 60000;
+extern "C" void sgnn_debug_set_tc32_min_rows(int64_t n) { g_sgnn_tc32_min_rows = n; }
+
 namespace {
 
 struct Arena {
@@ -180,7 +185,7 @@ static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr,
   }
   int rc = SGNN_E_UNSUPPORTED;
   bool used_tc = false;
-  if (c.tc32 && cout == 16 && cin >= 12 && cin <= 48 && (!child || cin == 48)) {
+  if (c.tc32 && cout == 16 && cin >= 12 && cin <= 48 && (!child || cin == 48) && n_out >= g_sgnn_tc32_min_rows) {
     const size_t wb = sgnn_conv_tc32_workspace_bytes(K, cin, child);
     void* ws = c.ar.get(wb);
     if (!ws) return SGNN_E_NOMEM;

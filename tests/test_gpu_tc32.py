@@ -156,6 +156,8 @@ def _model(dims, seed, mode):
     m = sgnn_b200.GenModel(8, list(dims), 1, 16, 16, 4, True, True, 1, 1)
     fill_parameters(m, seed)
     m.conv_mode = mode
+    from sgnn_b200._lib import lib
+    lib.sgnn_debug_set_tc32_min_rows(0 if mode == 'tc32' else 60000)   # tests: every eligible layer on the tensor cores
     return m.cuda().eval()
 
 
