@@ -1,0 +1,20 @@
+#!/bin/bash
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+export PYTHONUNBUFFERED=1
+t0=$(date +%s)
+stamp() { echo "[$(( $(date +%s) - t0 ))s] $*"; }
+stamp pytest-tc32
+timeout 500 python -m pytest tests/test_gpu_tc32.py -q -x > gpurun_out/pytest_tc32.log 2>&1
+RC=$?
+echo "pytest tc32 rc=$RC"; tail -n 12 gpurun_out/pytest_tc32.log | cut -c1-300
+if [ "$RC" = "0" ]; then
+for IMPL in 0 23; do
+  stamp bench-tc32-impl-$IMPL
+  timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --conv-mode tc32 --conv-impl $IMPL --tc32-min-rows 0 --ledger gpurun_out/ledger_tc32_impl$IMPL.json \
+    > gpurun_out/bench_tc32_impl$IMPL.json 2> gpurun_out/bench_tc32_impl$IMPL.err
+  echo "rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/bench_tc32_impl$IMPL.json')); print('ms/step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], 'conv share', d['roofline']['share_of_step'])"
+done
+fi
+stamp done

@@ -391,6 +391,171 @@ conv_tc32_kernel(Tc32Params p, long long n_tiles) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Warp-specialised version of the regular kernel.  Warps 0-3 (thread t = output row t of the tile) are PRODUCERS:
+// they gather + split the neighbour rows of work item i into stage i % 2 of a two-stage shared-memory ring and
+// arrive on full[stage]; warp 4 is the MMA ISSUER: it waits for full[stage], issues the item's tcgen05.mma's and
+// commits them to empty[stage] (the stage may be refilled when the tensor core has read it) and, after the last item
+// of a tile, to acc_full[buf].  The accumulators are double buffered in TMEM (2 x 128 columns), so the producers run
+// the epilogue of tile t (wait acc_full, tcgen05.ld, sum of the partial accumulators, stores, arrive acc_empty) one
+// item into tile t+1 while the tensor core already works on t+1.  Nobody waits for the tensor core in the steady
+// state: conversion, MMA issue and epilogue overlap inside one CTA.
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+
+template <int Q, int KG, bool A32>
+__global__ void __launch_bounds__(160)
+conv_tc32_ws_kernel(Tc32Params p, long long n_tiles) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  constexpr int A_OFF = Q * 3 * T32_ABLK;
+  constexpr int B_OFF = Q * 3 * T32_BBLK;
+  constexpr int STAGE = KG * (A_OFF + B_OFF);   // [A: KG x Q x 3 x 4096 | B: KG x Q x 3 x 512]
+  __shared__ __align__(8) unsigned long long full[2], empty[2], acc_full[2], acc_empty[2];
+  __shared__ unsigned tmem_ptr_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr_s)), "r"(2 * T32_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 128);
+      mbar_init(&empty[i], 1);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::);
+  const unsigned tmem = tmem_ptr_s;
+
+  const int ngroups = (p.K + KG - 1) / KG;
+  const int n_main = (p.K + 3) >> 2;
+  const long long my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const long long n_items = my_tiles * ngroups;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers + epilogue
+    float x[KG][2 * Q][8];
+    int idx[KG], idx_next[KG];
+    const int row_off = (tid >> 3) * 256 + (tid & 7) * 16;
+    auto load_idx = [&](long long item, int (&dst)[KG]) {
+      const long long tile = blockIdx.x + (item / ngroups) * gridDim.x;
+      const int k0 = (int)(item % ngroups) * KG;
+      const long long j = tile * T32_M + tid;
+#pragma unroll
+      for (int kk = 0; kk < KG; ++kk)
+        dst[kk] = (k0 + kk < p.K && j < p.n_rows) ? __ldg(p.nbr + (long long)(k0 + kk) * p.nbr_stride + j) : -1;
+    };
+    auto load_rows = [&]() {
+#pragma unroll
+      for (int kk = 0; kk < KG; ++kk)
+        if (idx[kk] >= 0) {
+          const float* src = p.in + (long long)idx[kk] * p.ld_in;
+#pragma unroll
+          for (int u = 0; u < 2 * Q; ++u) load8<A32>(src, 8 * u, p.cin, x[kk][u]);
+        }
+    };
+    auto epilogue = [&](long long tl) {   // tl: index of the tile in this CTA's sequence
+      const int ab = (int)(tl & 1);
+      mbar_wait(&acc_full[ab], (unsigned)((tl >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::);
+      unsigned v[16], vc[16];
+      const unsigned lane_base = tmem + (unsigned)(ab * T32_COLS) + ((unsigned)(warp * 32) << 16);
+      tmem_ld16(lane_base + T32_CORR, v);
+      for (int a = n_main - 1; a >= 0; --a) {
+        tmem_ld16(lane_base + 16u * (unsigned)a, vc);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(vc[c]));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::);
+      mbar_arrive(&acc_empty[ab]);        // the accumulator buffer may be overwritten by tile tl + 2
+      const long long j = (blockIdx.x + tl * gridDim.x) * T32_M + tid;
+      if (j < p.n_rows) epilogue_row16(p, v, j);
+    };
+
+    if (n_items > 0) {
+      load_idx(0, idx);
+      load_rows();
+      if (n_items > 1) load_idx(1, idx_next);
+    }
+    for (long long it = 0; it < n_items; ++it) {
+      const long long tl = it / ngroups;
+      const int g = (int)(it % ngroups);
+      const int k0 = g * KG, kg = min(KG, p.K - k0);
+      const int s = (int)(it & 1);
+      const long long u = it >> 1;
+      if (u > 0) mbar_wait(&empty[s], (unsigned)((u - 1) & 1));   // the MMAs that read this stage last have completed
+      unsigned char* As = sm + s * STAGE;
+      unsigned char* Bs = As + KG * A_OFF;
+      {
+        const unsigned char* wsrc = p.wsplit + (size_t)k0 * B_OFF;
+        for (int i = tid; i < kg * (B_OFF / 16); i += 128) cp16(Bs + i * 16, wsrc + i * 16);
+        asm volatile("cp.async.commit_group;\n" ::);
+      }
+#pragma unroll
+      for (int kk = 0; kk < KG; ++kk)
+        if (kk < kg) {
+#pragma unroll
+          for (int uu = 0; uu < 2 * Q; ++uu) {
+            unsigned char* dst = As + kk * A_OFF + (uu >> 1) * (3 * T32_ABLK) + (uu & 1) * 128 + row_off;
+            if (idx[kk] >= 0) split8_store(x[kk][uu], dst, T32_ABLK);
+            else zero_store(dst, T32_ABLK);
+          }
+        }
+      asm volatile("cp.async.wait_group 0;\n" ::);
+      asm volatile("fence.proxy.async.shared::cta;" ::);
+      mbar_arrive(&full[s]);
+      if (it + 1 < n_items) {
+#pragma unroll
+        for (int kk = 0; kk < KG; ++kk) idx[kk] = idx_next[kk];
+        load_rows();
+        if (it + 2 < n_items) load_idx(it + 2, idx_next);
+      }
+      if (g == 0 && tl > 0) epilogue(tl - 1);   // previous tile, one item late: its MMAs are done or nearly so
+    }
+    if (my_tiles > 0) epilogue(my_tiles - 1);
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (warp 4)
+    for (long long it = 0; it < n_items; ++it) {
+      const long long tl = it / ngroups;
+      const int g = (int)(it % ngroups);
+      const int k0 = g * KG, kg = min(KG, p.K - k0);
+      const int s = (int)(it & 1);
+      const int ab = (int)(tl & 1);
+      mbar_wait(&full[s], (unsigned)((it >> 1) & 1));
+      if (g == 0 && tl >= 2) mbar_wait(&acc_empty[ab], (unsigned)(((tl >> 1) - 1) & 1));   // epilogue of tile tl-2 drained
+      asm volatile("tcgen05.fence::after_thread_sync;" ::);
+      if (lane == 0) {
+        const unsigned char* As = sm + s * STAGE;
+        const unsigned char* Bs = As + KG * A_OFF;
+        const unsigned acc = tmem + (unsigned)(ab * T32_COLS);
+        for (int kk = 0; kk < kg; ++kk) {
+          const int k = k0 + kk;
+#pragma unroll
+          for (int qc = 0; qc < Q; ++qc)
+            mma_split6(acc + 16u * (unsigned)(k >> 2), acc + T32_CORR, smem_u32(As + kk * A_OFF + qc * 3 * T32_ABLK),
+                       smem_u32(Bs + kk * B_OFF + qc * 3 * T32_BBLK), ((k & 3) == 0 && qc == 0) ? 0u : 1u,
+                       (k == 0 && qc == 0) ? 0u : 1u);
+        }
+        mma_commit(&empty[s]);
+        if (g == ngroups - 1) mma_commit(&acc_full[ab]);
+      }
+      __syncwarp();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * T32_COLS));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // child mode: Cin = 48 (Q = 3), Cout = 16; p.n_rows = parent rows, output row 8 p + c
 __global__ void __launch_bounds__(128)
 conv_tc32_child_kernel(Tc32Params p, long long n_tiles) {
@@ -515,15 +680,15 @@ conv_tc32_child_kernel(Tc32Params p, long long n_tiles) {
 
 bool al(const void* p, uintptr_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
 
-// CTAs of 128 threads one SM holds: shared memory (227 KB usable, 1 KB reserved per CTA), registers (64 K, allocated
+// CTAs one SM holds: shared memory (227 KB usable, 1 KB reserved per CTA), registers (64 K, allocated
 // per warp in units of 8 per thread) and TMEM columns.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor answered 1 for
 // these kernels -- it assumes the default shared-memory carve-out -- which left three quarters of each SM idle.)
-int resident_ctas(const void* fn, size_t dyn_smem, int tmem_limit) {
+int resident_ctas(const void* fn, size_t dyn_smem, int tmem_limit, int threads = 128) {
   cudaFuncAttributes fa;
   if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) { g_sgnn_last_cuda_error = (int)cudaGetLastError(); return -1; }
   const int by_smem = (int)((227 * 1024) / (dyn_smem + fa.sharedSizeBytes + 1024));
   const int regs = (fa.numRegs + 7) & ~7;
-  const int by_regs = 65536 / (regs * 128);
+  const int by_regs = 65536 / (regs * threads);
   int n = by_smem < by_regs ? by_smem : by_regs;
   if (n > tmem_limit) n = tmem_limit;
   return n < 1 ? 1 : n;
@@ -543,6 +708,24 @@ int launch_regular(const Tc32Params& p, cudaStream_t st) {
   long long grid = (long long)148 * ctas_per_sm;
   if (grid > tiles) grid = tiles;
   conv_tc32_kernel<Q, KG, A32><<<(int)grid, 128, smem, st>>>(p, tiles);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+template <int Q, int KG, bool A32>
+int launch_ws(const Tc32Params& p, cudaStream_t st) {
+  constexpr size_t smem = (size_t)2 * KG * Q * 3 * (T32_ABLK + T32_BBLK);
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_ws_kernel<Q, KG, A32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_ws_kernel<Q, KG, A32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    ctas_per_sm = resident_ctas((const void*)conv_tc32_ws_kernel<Q, KG, A32>, smem, 512 / (2 * T32_COLS), 160);
+    if (ctas_per_sm < 0) return SGNN_E_CUDA;
+  }
+  const long long tiles = (p.n_rows + T32_M - 1) / T32_M;
+  long long grid = (long long)148 * ctas_per_sm;
+  if (grid > tiles) grid = tiles;
+  conv_tc32_ws_kernel<Q, KG, A32><<<(int)grid, 160, smem, st>>>(p, tiles);
   SGNN_CHECK_LAUNCH();
   return SGNN_OK;
 }
@@ -606,6 +789,11 @@ extern "C" int sgnn_conv_forward_tc32(const SgnnConvArgs* a, void* workspace, si
     const int total = a->K * Q * 256;
     tc32_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)a->weight, a->K, a->cin, Q, (unsigned char*)workspace);
     SGNN_CHECK_LAUNCH();
+  }
+  if (g_sgnn_conv_impl == 23) {              // A/B: warp-specialised kernel (producers / MMA issuer, double-buffered TMEM)
+    if (Q == 1) return a32 ? launch_ws<1, 3, true>(p, st) : launch_ws<1, 3, false>(p, st);
+    if (Q == 2) return a32 ? launch_ws<2, 1, true>(p, st) : launch_ws<2, 1, false>(p, st);
+    return a32 ? launch_ws<3, 1, true>(p, st) : launch_ws<3, 1, false>(p, st);
   }
   const bool kg1 = g_sgnn_conv_impl == 21;   // A/B: one filter offset per work item for 16-channel inputs
   if (Q == 1) {

@@ -22,6 +22,16 @@ def _E():
     return E
 
 
+@pytest.fixture(autouse=True, params=[0, 23], ids=['single-role', 'warp-specialised'])
+def tc_impl(request):
+    """Both generations of the regular tensor-core kernel: 0 = every warp gathers, thread 0 issues the MMAs;
+    23 = producer warps + MMA-issuer warp with a two-stage ring and double-buffered TMEM accumulators."""
+    from sgnn_b200._lib import lib
+    lib.sgnn_debug_set_conv_impl(request.param)
+    yield request.param
+    lib.sgnn_debug_set_conv_impl(0)
+
+
 def _bound(x, nbr, w, n_out, child_mode=False):
     """sum over the rules of |x| @ |w|: the magnitude the rounding errors scale with."""
     return o3.conv(x.abs(), nbr, w.abs(), n_out, child_mode=child_mode)
