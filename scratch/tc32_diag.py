@@ -45,6 +45,8 @@ def run(x, nbr, w, n_out, **kw):
 
 
 def main():
+    from sgnn_b200._lib import lib
+    lib.sgnn_debug_set_conv_impl(int(os.environ.get('SGNN_DIAG_IMPL', '0')))
     rng = np.random.default_rng(0)
     for n in (128, 100, 300):
         x = torch.from_numpy(rng.standard_normal((n, 16)).astype(np.float32))

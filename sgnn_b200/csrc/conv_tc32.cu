@@ -556,6 +556,204 @@ conv_tc32_ws_kernel(Tc32Params p, long long n_tiles) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// v3: the A operand goes through TENSOR MEMORY instead of shared memory (tcgen05.mma with A in TMEM, "TS" form).
+// ncu on v2 (profiles/r01_tc32_*): the L1/shared data pipe was the limiter at 79 % -- 578 wavefronts per work item for
+// the st.shared of the split planes (64 B per wavefront) plus 669 for the row gathers, and the tensor core re-read the
+// same bytes from shared memory.  Here thread t (= output row t = TMEM lane t) writes its row's split planes with
+// tcgen05.st.32x32b.x8 (16 bf16 = 8 packed 32-bit columns per plane and 16-channel slice): no shared-memory stores,
+// no generic->async proxy fence, no bank conflicts, 256 B/clk TMEM write port.  The whole prepared filter bank is
+// resident in shared memory (loaded once per persistent CTA).  Roles as in the warp-specialised kernel: warps 0-3
+// produce (rows of item i+1 are in flight while item i is converted: two register sets) and run the epilogue one item
+// into the next tile, warp 4 issues the MMAs; TMEM columns: [0,128) accumulators (7 main + correction),
+// [128,256) two A stages of 64 columns.
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const unsigned (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+__device__ __forceinline__ void mma_bf16_ts(unsigned tmem_d, unsigned tmem_a, unsigned long long db, unsigned acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(T32_IDESC), "r"(acc));
+}
+
+// 16 channels (two 8-channel units) of one row -> the three planes, 8 packed columns each
+__device__ __forceinline__ void split16_tmem(const float (&x0)[8], const float (&x1)[8], unsigned taddr) {
+  unsigned h[8], m[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    split2(x0[2 * i], x0[2 * i + 1], h[i], m[i], l[i]);
+    split2(x1[2 * i], x1[2 * i + 1], h[4 + i], m[4 + i], l[4 + i]);
+  }
+  tmem_st8(taddr, h);
+  tmem_st8(taddr + 8u, m);
+  tmem_st8(taddr + 16u, l);
+}
+
+#define T32_ASTAGE_COLS 64u
+
+template <int Q, int KG, bool A32>
+__global__ void __launch_bounds__(160)
+conv_tc32_tm_kernel(Tc32Params p, long long n_tiles) {
+  static_assert(KG * Q * 24 <= 64, "A stage must fit its 64 TMEM columns");
+  extern __shared__ __align__(1024) unsigned char sm[];   // prepared filter bank [K][Q][3][512 B]
+  constexpr int B_OFF = Q * 3 * T32_BBLK;
+  __shared__ __align__(8) unsigned long long full[2], empty[2], acc_full, acc_empty;
+  __shared__ unsigned tmem_ptr_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr_s)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 128);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&acc_full, 1);
+    mbar_init(&acc_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::);
+  }
+  // filter bank: plain 16-byte copies (already in the canonical layout), once per CTA
+  for (int i = tid; i < p.K * (B_OFF / 16); i += 160) cp16(sm + i * 16, p.wsplit + (size_t)i * 16);
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  asm volatile("fence.proxy.async.shared::cta;" ::);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::);
+  const unsigned tmem = tmem_ptr_s;
+
+  const int ngroups = (p.K + KG - 1) / KG;
+  const int n_main = (p.K + 3) >> 2;
+  const long long my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const long long n_items = my_tiles * ngroups;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers + epilogue
+    float x0[KG][2 * Q][8], x1[KG][2 * Q][8];
+    int idxn[KG];                                   // neighbour rows of the NEXT item to load
+    const unsigned lane_base = tmem + ((unsigned)(warp * 32) << 16);
+    auto load_idx = [&](long long item) {
+      const long long tile = blockIdx.x + (item / ngroups) * gridDim.x;
+      const int k0 = (int)(item % ngroups) * KG;
+      const long long j = tile * T32_M + tid;
+#pragma unroll
+      for (int kk = 0; kk < KG; ++kk)
+        idxn[kk] = (k0 + kk < p.K && j < p.n_rows) ? __ldg(p.nbr + (long long)(k0 + kk) * p.nbr_stride + j) : -1;
+    };
+    auto load_rows = [&](float (&x)[KG][2 * Q][8]) {   // rows idxn[] -> x (zeros for absent neighbours)
+#pragma unroll
+      for (int kk = 0; kk < KG; ++kk) {
+        if (idxn[kk] >= 0) {
+          const float* src = p.in + (long long)idxn[kk] * p.ld_in;
+#pragma unroll
+          for (int u = 0; u < 2 * Q; ++u) load8<A32>(src, 8 * u, p.cin, x[kk][u]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 2 * Q; ++u)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[kk][u][e] = 0.f;
+        }
+      }
+    };
+    auto epilogue = [&](long long tl) {
+      mbar_wait(&acc_full, (unsigned)(tl & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::);
+      unsigned v[16], vc[16];
+      tmem_ld16(lane_base + T32_CORR, v);
+      for (int a = n_main - 1; a >= 0; --a) {
+        tmem_ld16(lane_base + 16u * (unsigned)a, vc);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(vc[c]));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::);
+      mbar_arrive(&acc_empty);
+      const long long j = (blockIdx.x + tl * gridDim.x) * T32_M + tid;
+      if (j < p.n_rows) epilogue_row16(p, v, j);
+    };
+    // one pipeline step: rows of item it+1 -> xn (in flight), item `it` (held in xc) -> TMEM stage it % 2
+    auto step = [&](long long it, float (&xc)[KG][2 * Q][8], float (&xn)[KG][2 * Q][8]) {
+      const long long tl = it / ngroups;
+      const int g = (int)(it % ngroups);
+      const int kg = min(KG, p.K - g * KG);
+      const int s = (int)(it & 1);
+      const long long u = it >> 1;
+      if (it + 1 < n_items) {
+        load_rows(xn);
+        if (it + 2 < n_items) load_idx(it + 2);
+      }
+      if (u > 0) mbar_wait(&empty[s], (unsigned)((u - 1) & 1));   // the MMAs that read this A stage have completed
+      asm volatile("tcgen05.fence::after_thread_sync;" ::);
+      const unsigned a_stage = lane_base + 128u + (unsigned)s * T32_ASTAGE_COLS;
+#pragma unroll
+      for (int kk = 0; kk < KG; ++kk)
+        if (kk < kg) {
+#pragma unroll
+          for (int qc = 0; qc < Q; ++qc)
+            split16_tmem(xc[kk][2 * qc], xc[kk][2 * qc + 1], a_stage + (unsigned)((kk * Q + qc) * 24));
+        }
+      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::);
+      mbar_arrive(&full[s]);
+      if (g == 0 && tl > 0) epilogue(tl - 1);
+    };
+
+    if (n_items > 0) {
+      load_idx(0);
+      load_rows(x0);
+      if (n_items > 1) load_idx(1);
+    }
+    for (long long it = 0; it < n_items; it += 2) {
+      step(it, x0, x1);
+      if (it + 1 < n_items) step(it + 1, x1, x0);
+    }
+    if (my_tiles > 0) epilogue(my_tiles - 1);
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (warp 4)
+    for (long long it = 0; it < n_items; ++it) {
+      const long long tl = it / ngroups;
+      const int g = (int)(it % ngroups);
+      const int k0 = g * KG, kg = min(KG, p.K - k0);
+      const int s = (int)(it & 1);
+      mbar_wait(&full[s], (unsigned)((it >> 1) & 1));
+      if (g == 0 && tl >= 1) mbar_wait(&acc_empty, (unsigned)((tl - 1) & 1));   // epilogue of the previous tile drained
+      asm volatile("tcgen05.fence::after_thread_sync;" ::);
+      if (lane == 0) {
+        const unsigned a_stage = tmem + 128u + (unsigned)s * T32_ASTAGE_COLS;
+        for (int kk = 0; kk < kg; ++kk) {
+          const int k = k0 + kk;
+#pragma unroll
+          for (int qc = 0; qc < Q; ++qc) {
+            const unsigned a = a_stage + (unsigned)((kk * Q + qc) * 24);          // planes at +0, +8, +16 columns
+            const unsigned b = smem_u32(sm + (size_t)(k * Q + qc) * 3 * T32_BBLK); // planes at +0, +512, +1024 bytes
+            const unsigned first_corr = (k == 0 && qc == 0) ? 0u : 1u;
+            const unsigned first_main = ((k & 3) == 0 && qc == 0) ? 0u : 1u;
+            mma_bf16_ts(tmem + T32_CORR, a + 16u, umma_desc(b), first_corr);                    // x2 w0
+            mma_bf16_ts(tmem + T32_CORR, a + 8u, umma_desc(b + T32_BBLK), 1u);                  // x1 w1
+            mma_bf16_ts(tmem + T32_CORR, a, umma_desc(b + 2 * T32_BBLK), 1u);                   // x0 w2
+            mma_bf16_ts(tmem + T32_CORR, a + 8u, umma_desc(b), 1u);                             // x1 w0
+            mma_bf16_ts(tmem + T32_CORR, a, umma_desc(b + T32_BBLK), 1u);                       // x0 w1
+            mma_bf16_ts(tmem + 16u * (unsigned)(k >> 2), a, umma_desc(b), first_main);          // x0 w0
+          }
+        }
+        mma_commit(&empty[s]);
+        if (g == ngroups - 1) mma_commit(&acc_full);
+      }
+      __syncwarp();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // child mode: Cin = 48 (Q = 3), Cout = 16; p.n_rows = parent rows, output row 8 p + c
 __global__ void __launch_bounds__(128)
 conv_tc32_child_kernel(Tc32Params p, long long n_tiles) {
@@ -730,6 +928,24 @@ int launch_ws(const Tc32Params& p, cudaStream_t st) {
   return SGNN_OK;
 }
 
+template <int Q, int KG, bool A32>
+int launch_tm(const Tc32Params& p, cudaStream_t st) {
+  const size_t smem = (size_t)p.K * Q * 3 * T32_BBLK;
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_tm_kernel<Q, KG, A32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 27 * Q * 3 * T32_BBLK));
+    SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_tm_kernel<Q, KG, A32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    ctas_per_sm = resident_ctas((const void*)conv_tc32_tm_kernel<Q, KG, A32>, (size_t)27 * Q * 3 * T32_BBLK, 2, 160);
+    if (ctas_per_sm < 0) return SGNN_E_CUDA;
+  }
+  const long long tiles = (p.n_rows + T32_M - 1) / T32_M;
+  long long grid = (long long)148 * ctas_per_sm;
+  if (grid > tiles) grid = tiles;
+  conv_tc32_tm_kernel<Q, KG, A32><<<(int)grid, 160, smem, st>>>(p, tiles);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
 }  // namespace
 
 extern "C" size_t sgnn_conv_tc32_workspace_bytes(int32_t K, int32_t cin, int32_t child_mode) {
@@ -789,6 +1005,10 @@ extern "C" int sgnn_conv_forward_tc32(const SgnnConvArgs* a, void* workspace, si
     const int total = a->K * Q * 256;
     tc32_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)a->weight, a->K, a->cin, Q, (unsigned char*)workspace);
     SGNN_CHECK_LAUNCH();
+  }
+  if (g_sgnn_conv_impl == 24 && Q <= 2) {    // A/B: A operand through tensor memory (v3)
+    if (Q == 1) return a32 ? launch_tm<1, 2, true>(p, st) : launch_tm<1, 2, false>(p, st);
+    return a32 ? launch_tm<2, 1, true>(p, st) : launch_tm<2, 1, false>(p, st);
   }
   if (g_sgnn_conv_impl == 23) {              // A/B: warp-specialised kernel (producers / MMA issuer, double-buffered TMEM)
     if (Q == 1) return a32 ? launch_ws<1, 3, true>(p, st) : launch_ws<1, 3, false>(p, st);

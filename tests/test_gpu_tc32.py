@@ -22,10 +22,11 @@ def _E():
     return E
 
 
-@pytest.fixture(autouse=True, params=[0, 23], ids=['single-role', 'warp-specialised'])
+@pytest.fixture(autouse=True, params=[0, 23, 24], ids=['single-role', 'warp-specialised', 'tmem-operand'])
 def tc_impl(request):
-    """Both generations of the regular tensor-core kernel: 0 = every warp gathers, thread 0 issues the MMAs;
-    23 = producer warps + MMA-issuer warp with a two-stage ring and double-buffered TMEM accumulators."""
+    """Every generation of the regular tensor-core kernel: 0 = every warp gathers, thread 0 issues the MMAs;
+    23 = producer warps + MMA-issuer warp with a two-stage shared-memory ring and double-buffered TMEM accumulators;
+    24 = as 23 but the A operand is written to tensor memory (tcgen05.st) and the MMAs read it from there."""
     from sgnn_b200._lib import lib
     lib.sgnn_debug_set_conv_impl(request.param)
     yield request.param
