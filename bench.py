@@ -42,7 +42,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ledger', default='', help='write the per-layer ledger JSON here')
     ap.add_argument('--conv-impl', type=int, default=0, help='sgnn_debug_set_conv_impl (kernel A/B runs)')
-    ap.add_argument('--conv-mode', default='exact', choices=['exact', 'tc32'],
+    ap.add_argument('--conv-mode', default='tc32', choices=['exact', 'tc32'],
                     help="exact: fixed-order FFMA convolutions; tc32: Cout=16 convolutions on tcgen05 (3-way bf16 split)")
     ap.add_argument('--tc32-min-rows', type=int, default=-1, help='sgnn_debug_set_tc32_min_rows (A/B runs)')
     return ap.parse_args()

@@ -219,9 +219,11 @@ class GenModel(nn.Module):
         self.surfacepred = SurfacePrediction(nf_in, nf, 1, self.refine_sizes[-1])
         self.return_long = True      # LongTensor coordinates at the boundary, like the reference
         self._native = None
-        # 'exact': fixed-order FFMA convolutions (bit-reproducible, == oracle/o3.c);  'tc32': the Cout = 16 convolutions
-        # of the native generator run on the tensor cores (3-way bf16 split, fp32 accuracy, not bit-identical)
-        self.conv_mode = 'exact'
+        # 'tc32' (default): the wide (Cout = 16) convolutions of the native generator with >= 60000 output rows run on
+        # the tensor cores (tcgen05, exact 3-way bf16 split of fp32 features and filters: fp32 accuracy, but not the
+        # fmaf order of the FFMA kernels);  'exact': every convolution on the fixed-order FFMA kernels -- bit-reproducible,
+        # == oracle/o3.c, and bit-identical to forward_fused / forward_modules.
+        self.conv_mode = 'tc32'
 
     # model.py:357-369.  The sizes are upper bounds of mode-0 InputLayers; the reference doubles
     # refine_max_dim inside the k loop -- mirrored, not "fixed": bounds only grow.
