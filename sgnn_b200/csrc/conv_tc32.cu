@@ -876,6 +876,180 @@ conv_tc32_child_kernel(Tc32Params p, long long n_tiles) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-specialised child-mode kernel.  ncu on the single-role version above: 2 CTAs x 4 warps per SM (TMEM: 256
+// accumulator columns per CTA), issue slots 18 % busy, long-scoreboard stalls dominant -- every item serialises row
+// latency, conversion, barrier, MMA issue (43 MMAs on average, by one thread) and the commit round trip.  Here warps
+// 0-3 only produce: the rows of item i+1 are in flight (second register set) while item i is split into stage i % 2
+// of a two-stage ring, and warp 4 issues the MMAs and commits them to the stage's `empty` barrier.  A work item is a
+// ROUND = (parent offset e, <= 4 children): the centre offset, read by all 8 children, takes two rounds, so a stage's
+// filter slot holds 4 pairs (18 KB) and two stages fit twice per SM.
+__device__ __forceinline__ void child_round(int r, int& e, int& half) {
+  e = r <= 13 ? r : r - 1;
+  half = r == 14 ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(160)
+conv_tc32_child_ws_kernel(Tc32Params p, long long n_tiles) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  constexpr int Q = 3;
+  constexpr int A_BYTES = Q * 3 * T32_ABLK;     // 36864
+  constexpr int PAIR_BYTES = Q * 3 * T32_BBLK;  // 4608
+  constexpr int STAGE = A_BYTES + 4 * PAIR_BYTES;
+  constexpr int ROUNDS = 28;
+  __shared__ __align__(8) unsigned long long full[2], empty[2], acc_full, acc_empty;
+  __shared__ unsigned tmem_ptr_s;
+  __shared__ int pair_start[28];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr_s)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 128);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&acc_full, 1);
+    mbar_init(&acc_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::);
+    int cnt = 0;
+    for (int e = 0; e < 27; ++e) {
+      pair_start[e] = cnt;
+      for (int c = 0; c < 8; ++c) cnt += child_uses(c, e) ? 1 : 0;
+    }
+    pair_start[27] = cnt;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::);
+  const unsigned tmem = tmem_ptr_s;
+
+  const long long my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const long long n_items = my_tiles * ROUNDS;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers + epilogue
+    float x0[2 * Q][8], x1[2 * Q][8];
+    int idxn = -1;                                   // neighbour row of the NEXT item to load
+    const int row_off = (tid >> 3) * 256 + (tid & 7) * 16;
+    const unsigned lane_base = tmem + ((unsigned)(warp * 32) << 16);
+    auto load_idx = [&](long long item) {
+      int e, half;
+      child_round((int)(item % ROUNDS), e, half);
+      const long long j = (blockIdx.x + (item / ROUNDS) * gridDim.x) * T32_M + tid;
+      idxn = j < p.n_rows ? __ldg(p.nbr + (long long)e * p.nbr_stride + j) : -1;
+    };
+    auto load_rows = [&](float (&x)[2 * Q][8]) {
+      if (idxn >= 0) {
+        const float* src = p.in + (long long)idxn * p.ld_in;
+#pragma unroll
+        for (int u = 0; u < 2 * Q; ++u) load8<true>(src, 8 * u, p.cin, x[u]);
+      } else {
+#pragma unroll
+        for (int u = 0; u < 2 * Q; ++u)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) x[u][q] = 0.f;
+      }
+    };
+    auto epilogue = [&](long long tl) {
+      mbar_wait(&acc_full, (unsigned)(tl & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::);
+      const long long pj = (blockIdx.x + tl * gridDim.x) * T32_M + tid;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        unsigned v[16], vc[16];
+        tmem_ld16(lane_base + 16u * c, v);
+        tmem_ld16(lane_base + 128u + 16u * c, vc);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(vc[q]));
+        if (pj < p.n_rows) epilogue_row16(p, v, pj * 8 + c);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::);
+      mbar_arrive(&acc_empty);
+    };
+    auto step = [&](long long it, float (&xc)[2 * Q][8], float (&xn)[2 * Q][8]) {
+      const long long tl = it / ROUNDS;
+      const int r = (int)(it % ROUNDS);
+      int e, half;
+      child_round(r, e, half);
+      const int s = (int)(it & 1);
+      const long long u = it >> 1;
+      if (it + 1 < n_items) {
+        load_rows(xn);
+        if (it + 2 < n_items) load_idx(it + 2);
+      }
+      if (u > 0) mbar_wait(&empty[s], (unsigned)((u - 1) & 1));
+      unsigned char* As = sm + s * STAGE;
+      unsigned char* Bs = As + A_BYTES;
+      const int ps = pair_start[e] + 4 * half;
+      const int np = min(4, pair_start[e + 1] - ps);
+      {
+        const unsigned char* wsrc = p.wsplit + (size_t)ps * PAIR_BYTES;
+        for (int i = tid; i < np * (PAIR_BYTES / 16); i += 128) cp16(Bs + i * 16, wsrc + i * 16);
+        asm volatile("cp.async.commit_group;\n" ::);
+      }
+#pragma unroll
+      for (int uu = 0; uu < 2 * Q; ++uu)
+        split8_store(xc[uu], As + (uu >> 1) * (3 * T32_ABLK) + (uu & 1) * 128 + row_off, T32_ABLK);
+      asm volatile("cp.async.wait_group 0;\n" ::);
+      asm volatile("fence.proxy.async.shared::cta;" ::);
+      mbar_arrive(&full[s]);
+      if (r == 0 && tl > 0) epilogue(tl - 1);
+    };
+
+    if (n_items > 0) {
+      load_idx(0);
+      load_rows(x0);
+      if (n_items > 1) load_idx(1);
+    }
+    for (long long it = 0; it < n_items; it += 2) {
+      step(it, x0, x1);
+      if (it + 1 < n_items) step(it + 1, x1, x0);
+    }
+    if (my_tiles > 0) epilogue(my_tiles - 1);
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (warp 4)
+    unsigned written = 0;
+    for (long long it = 0; it < n_items; ++it) {
+      const long long tl = it / ROUNDS;
+      const int r = (int)(it % ROUNDS);
+      int e, half;
+      child_round(r, e, half);
+      const int s = (int)(it & 1);
+      mbar_wait(&full[s], (unsigned)((it >> 1) & 1));
+      if (r == 0 && tl >= 1) mbar_wait(&acc_empty, (unsigned)((tl - 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::);
+      if (r == 0) written = 0;
+      if (lane == 0) {
+        const unsigned char* As = sm + s * STAGE;
+        const unsigned char* Bs = As + A_BYTES;
+        int seen = 0, slot = 0;
+        for (int c = 0; c < 8; ++c) {
+          if (!child_uses(c, e)) continue;
+          if (seen++ < 4 * half) continue;      // second round of the centre offset: children 4..7
+          if (slot == 4) break;
+          const unsigned d = tmem + 16u * c;
+          const unsigned had = (written >> c) & 1u;
+#pragma unroll
+          for (int qc = 0; qc < Q; ++qc)
+            mma_split6(d, d + 128u, smem_u32(As + qc * 3 * T32_ABLK), smem_u32(Bs + slot * PAIR_BYTES + qc * 3 * T32_BBLK),
+                       (qc == 0 && !had) ? 0u : 1u, (qc == 0 && !had) ? 0u : 1u);
+          written |= 1u << c;
+          ++slot;
+        }
+        mma_commit(&empty[s]);
+        if (r == ROUNDS - 1) mma_commit(&acc_full);
+      }
+      written = __shfl_sync(0xffffffffu, written, 0);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+}
+
 bool al(const void* p, uintptr_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
 
 // CTAs one SM holds: shared memory (227 KB usable, 1 KB reserved per CTA), registers (64 K, allocated
@@ -986,6 +1160,22 @@ extern "C" int sgnn_conv_forward_tc32(const SgnnConvArgs* a, void* workspace, si
   if (a->child_mode) {
     tc32_prep_child_kernel<<<96, 512, 0, st>>>((const float*)a->weight, a->cin, (unsigned char*)workspace);
     SGNN_CHECK_LAUNCH();
+    if (g_sgnn_conv_impl != 25) {   // default: warp-specialised kernel; 25 = single-role kernel (A/B)
+      constexpr size_t smem_ws = (size_t)2 * (3 * 3 * T32_ABLK + 4 * 3 * 3 * T32_BBLK);
+      static int ctas_ws = 0;
+      if (!ctas_ws) {
+        SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_child_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+        SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_child_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        ctas_ws = resident_ctas((const void*)conv_tc32_child_ws_kernel, smem_ws, 2, 160);
+        if (ctas_ws < 0) return SGNN_E_CUDA;
+      }
+      const long long tiles = (p.n_rows + T32_M - 1) / T32_M;
+      long long grid = (long long)148 * ctas_ws;
+      if (grid > tiles) grid = tiles;
+      conv_tc32_child_ws_kernel<<<(int)grid, 160, smem_ws, st>>>(p, tiles);
+      SGNN_CHECK_LAUNCH();
+      return SGNN_OK;
+    }
     constexpr size_t smem = (size_t)3 * 3 * T32_ABLK + (size_t)8 * 3 * 3 * T32_BBLK;
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) {
