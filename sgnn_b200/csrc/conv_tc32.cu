@@ -73,6 +73,21 @@ __device__ __forceinline__ void mma_bf16(unsigned tmem_d, unsigned long long da,
       "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(T32_IDESC), "r"(acc));
 }
 
+// One lane of a CONVERGED warp.  Issuing tcgen05.mma under `if (lane == 0)` makes ptxas wrap every UTCHMMA in an
+// ELECT / BRA.U.ANY serialisation loop (12 instructions + a branch per MMA); under elect.sync it emits straight-line
+// uniform-datapath code.
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mma_commit(unsigned long long* mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
 }
@@ -348,17 +363,20 @@ conv_tc32_kernel(Tc32Params p, long long n_tiles) {
     asm volatile("cp.async.wait_group 0;\n" ::);
     asm volatile("fence.proxy.async.shared::cta;" ::);   // generic-proxy writes -> visible to the tensor-core proxy
     __syncthreads();                                      // item staged; previous epilogue's TMEM loads retired
-    if (tid == 0) {
+    if (warp == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::);
-      for (int kk = 0; kk < kg; ++kk) {
-        const int k = k0 + kk;
+      if (elect_one()) {
+        for (int kk = 0; kk < kg; ++kk) {
+          const int k = k0 + kk;
 #pragma unroll
-        for (int qc = 0; qc < Q; ++qc)
-          mma_split6(tmem + 16u * (unsigned)(k >> 2), tmem + T32_CORR, smem_u32(As + kk * A_OFF + qc * 3 * T32_ABLK),
-                     smem_u32(Bs + kk * B_OFF + qc * 3 * T32_BBLK), ((k & 3) == 0 && qc == 0) ? 0u : 1u,
-                     (k == 0 && qc == 0) ? 0u : 1u);
+          for (int qc = 0; qc < Q; ++qc)
+            mma_split6(tmem + 16u * (unsigned)(k >> 2), tmem + T32_CORR, smem_u32(As + kk * A_OFF + qc * 3 * T32_ABLK),
+                       smem_u32(Bs + kk * B_OFF + qc * 3 * T32_BBLK), ((k & 3) == 0 && qc == 0) ? 0u : 1u,
+                       (k == 0 && qc == 0) ? 0u : 1u);
+        }
+        mma_commit(&mbar);
       }
-      mma_commit(&mbar);
+      __syncwarp();
     }
     // ---- prefetch the rows of item it+1 (and the indices of it+2) while the tensor core works
     if (it + 1 < n_items) {
@@ -416,7 +434,7 @@ conv_tc32_ws_kernel(Tc32Params p, long long n_tiles) {
   __shared__ __align__(8) unsigned long long full[2], empty[2], acc_full[2], acc_empty[2];
   __shared__ unsigned tmem_ptr_s;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr_s)), "r"(2 * T32_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -532,7 +550,7 @@ conv_tc32_ws_kernel(Tc32Params p, long long n_tiles) {
       mbar_wait(&full[s], (unsigned)((it >> 1) & 1));
       if (g == 0 && tl >= 2) mbar_wait(&acc_empty[ab], (unsigned)(((tl >> 1) - 1) & 1));   // epilogue of tile tl-2 drained
       asm volatile("tcgen05.fence::after_thread_sync;" ::);
-      if (lane == 0) {
+      if (elect_one()) {
         const unsigned char* As = sm + s * STAGE;
         const unsigned char* Bs = As + KG * A_OFF;
         const unsigned acc = tmem + (unsigned)(ab * T32_COLS);
@@ -605,7 +623,7 @@ conv_tc32_tm_kernel(Tc32Params p, long long n_tiles) {
   __shared__ __align__(8) unsigned long long full[2], empty[2], acc_full, acc_empty;
   __shared__ unsigned tmem_ptr_s;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr_s)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -724,7 +742,7 @@ conv_tc32_tm_kernel(Tc32Params p, long long n_tiles) {
       mbar_wait(&full[s], (unsigned)((it >> 1) & 1));
       if (g == 0 && tl >= 1) mbar_wait(&acc_empty, (unsigned)((tl - 1) & 1));   // epilogue of the previous tile drained
       asm volatile("tcgen05.fence::after_thread_sync;" ::);
-      if (lane == 0) {
+      if (elect_one()) {
         const unsigned a_stage = tmem + 128u + (unsigned)s * T32_ASTAGE_COLS;
         for (int kk = 0; kk < kg; ++kk) {
           const int k = k0 + kk;
@@ -813,7 +831,7 @@ conv_tc32_child_kernel(Tc32Params p, long long n_tiles) {
     load_rows();
     if (n_items > 1) idx_next = load_idx(1);
   }
-  unsigned written = 0;   // (thread 0) children whose accumulator columns hold data of the current tile
+  unsigned written = 0;   // (warp 0) children whose accumulator columns hold data of the current tile
   for (long long it = 0; it < n_items; ++it) {
     const long long tile = blockIdx.x + (it / 27) * gridDim.x;
     const int e = (int)(it % 27);
@@ -832,7 +850,7 @@ conv_tc32_child_kernel(Tc32Params p, long long n_tiles) {
     asm volatile("cp.async.wait_group 0;\n" ::);
     asm volatile("fence.proxy.async.shared::cta;" ::);
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {   // all lanes track `written`; one elected lane issues
       asm volatile("tcgen05.fence::after_thread_sync;" ::);
       if (e == 0) written = 0;
       int slot = 0;
@@ -840,14 +858,17 @@ conv_tc32_child_kernel(Tc32Params p, long long n_tiles) {
         if (!child_uses(c, e)) continue;
         const unsigned d = tmem + 16u * c;
         const unsigned had = (written >> c) & 1u;
+        if (elect_one()) {
 #pragma unroll
-        for (int qc = 0; qc < Q; ++qc)
-          mma_split6(d, d + 128u, smem_u32(As + qc * 3 * T32_ABLK), smem_u32(Bs + slot * PAIR_BYTES + qc * 3 * T32_BBLK),
-                     (qc == 0 && !had) ? 0u : 1u, (qc == 0 && !had) ? 0u : 1u);
+          for (int qc = 0; qc < Q; ++qc)
+            mma_split6(d, d + 128u, smem_u32(As + qc * 3 * T32_ABLK), smem_u32(Bs + slot * PAIR_BYTES + qc * 3 * T32_BBLK),
+                       (qc == 0 && !had) ? 0u : 1u, (qc == 0 && !had) ? 0u : 1u);
+        }
         written |= 1u << c;
         ++slot;
       }
-      mma_commit(&mbar);
+      if (elect_one()) mma_commit(&mbar);
+      __syncwarp();
     }
     if (it + 1 < n_items) {
       idx = idx_next;
@@ -901,7 +922,7 @@ conv_tc32_child_ws_kernel(Tc32Params p, long long n_tiles) {
   __shared__ unsigned tmem_ptr_s;
   __shared__ int pair_start[28];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr_s)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -1022,7 +1043,7 @@ conv_tc32_child_ws_kernel(Tc32Params p, long long n_tiles) {
       if (r == 0 && tl >= 1) mbar_wait(&acc_empty, (unsigned)((tl - 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::);
       if (r == 0) written = 0;
-      if (lane == 0) {
+      {   // every lane walks the child list (uniform); one elected lane issues
         const unsigned char* As = sm + s * STAGE;
         const unsigned char* Bs = As + A_BYTES;
         int seen = 0, slot = 0;
@@ -1032,17 +1053,21 @@ conv_tc32_child_ws_kernel(Tc32Params p, long long n_tiles) {
           if (slot == 4) break;
           const unsigned d = tmem + 16u * c;
           const unsigned had = (written >> c) & 1u;
+          if (elect_one()) {
 #pragma unroll
-          for (int qc = 0; qc < Q; ++qc)
-            mma_split6(d, d + 128u, smem_u32(As + qc * 3 * T32_ABLK), smem_u32(Bs + slot * PAIR_BYTES + qc * 3 * T32_BBLK),
-                       (qc == 0 && !had) ? 0u : 1u, (qc == 0 && !had) ? 0u : 1u);
+            for (int qc = 0; qc < Q; ++qc)
+              mma_split6(d, d + 128u, smem_u32(As + qc * 3 * T32_ABLK), smem_u32(Bs + slot * PAIR_BYTES + qc * 3 * T32_BBLK),
+                         (qc == 0 && !had) ? 0u : 1u, (qc == 0 && !had) ? 0u : 1u);
+          }
           written |= 1u << c;
           ++slot;
         }
-        mma_commit(&empty[s]);
-        if (r == ROUNDS - 1) mma_commit(&acc_full);
+        if (elect_one()) {
+          mma_commit(&empty[s]);
+          if (r == ROUNDS - 1) mma_commit(&acc_full);
+        }
+        __syncwarp();
       }
-      written = __shfl_sync(0xffffffffu, written, 0);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::);
