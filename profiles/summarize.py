@@ -2,6 +2,8 @@
 """Summarise ncu artefacts brought back in gpurun_out/ into small text files under profiles/.
   python profiles/summarize.py rep <file.ncu-rep> <out.txt>       key metrics per captured kernel
   python profiles/summarize.py launches <launches.csv> <out.txt> [forwards-per-run kernel-name count]
+  python profiles/summarize.py dram <metrics.csv> <out.json>      DRAM bytes + duration per captured launch (bench.py's
+                                                                  roofline.traffic reads profiles/conv_dram_traffic.json)
 """
 import collections
 import csv
@@ -71,8 +73,30 @@ def launches(path, out, per=None):
         f.write('%-72s %9s %14.1f\n' % ('TOTAL', '', tot / 1e3 / nf))
 
 
+def dram(path, out):
+    import json
+    lines = [l for l in open(path) if not l.startswith('==')]
+    by = collections.OrderedDict()
+    for r in csv.DictReader(lines):
+        d = by.setdefault(r['ID'], {'kernel': re.sub(r'\(.*', '', r['Kernel Name'])})
+        scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-3, 'us': 1, 'ms': 1e3}.get(r['Metric Unit'], 1)
+        d[r['Metric Name']] = float(r['Metric Value'].replace(',', '')) * scale
+    launches_ = [{'kernel': d['kernel'], 'dram_read_bytes': d.get('dram__bytes_read.sum', 0.0),
+                  'dram_write_bytes': d.get('dram__bytes_write.sum', 0.0), 'us': d.get('gpu__time_duration.sum', 0.0)}
+                 for d in by.values()]
+    tot = sum(l['dram_read_bytes'] + l['dram_write_bytes'] for l in launches_)
+    with open(out, 'w') as f:
+        json.dump({'source': 'ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control '
+                             'none over the %d convolution launches of one generator pass (cold cache: ncu flushes L2 '
+                             'before every launch)' % len(launches_),
+                   'n_launches': len(launches_), 'dram_bytes_total': tot,
+                   'dram_bytes_per_launch': tot / max(len(launches_), 1), 'launches': launches_}, f, indent=1)
+
+
 if __name__ == '__main__':
     if sys.argv[1] == 'rep':
         rep(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == 'dram':
+        dram(sys.argv[2], sys.argv[3])
     else:
         launches(sys.argv[2], sys.argv[3], sys.argv[4:6] if len(sys.argv) > 5 else None)

@@ -1235,6 +1235,9 @@ extern "C" int sgnn_conv_forward_tc32(const SgnnConvArgs* a, void* workspace, si
     if (kg1) return a32 ? launch_regular<1, 1, true>(p, st) : launch_regular<1, 1, false>(p, st);
     return a32 ? launch_regular<1, 3, true>(p, st) : launch_regular<1, 3, false>(p, st);
   }
-  if (Q == 2) return a32 ? launch_regular<2, 1, true>(p, st) : launch_regular<2, 1, false>(p, st);
+  if (Q == 2) {
+    if (g_sgnn_conv_impl == 26) return a32 ? launch_regular<2, 1, true>(p, st) : launch_regular<2, 1, false>(p, st);   // A/B
+    return a32 ? launch_regular<2, 2, true>(p, st) : launch_regular<2, 2, false>(p, st);
+  }
   return a32 ? launch_regular<3, 1, true>(p, st) : launch_regular<3, 1, false>(p, st);
 }

@@ -258,7 +258,8 @@ static int fcn(Ctx& c, const Level& lv0, const SgnnFcnW& f, const float* x_raw, 
   return sgnn_unpool(J1, 2 * ch, par01, 2 * ch, lv0.n, &e0, c.stream);
 }
 
-static int pad4(int v) { return (v + 3) / 4 * 4; }
+// leading dimension of the joined feature rows: a multiple of 8 floats keeps every row 32-byte aligned (256-bit gathers)
+static int pad8(int v) { return (v + 7) / 8 * 8; }
 
 struct Skip { SgnnGrid g; const float* f; int c; int64_t n; };
 
@@ -396,7 +397,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       GEN(read_i32(c, offs + ncell, &cnt));
       m = cnt;
       live_c = w->nf_coarse + 2;
-      ld_f = pad4(live_c + skips[3].c);
+      ld_f = pad8(live_c + skips[3].c);
       GALLOC(l0, int32_t, m * 4);
       GALLOC(f0, float, m * ld_f);
       locs = l0; fts = f0;
@@ -446,7 +447,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
         out->cand_locs[h + 1] = cl;
       }
       const int next_skip = h < 2 ? skips[2 - h].c : skips[0].c;
-      const int ld_n = pad4(ch + 2 + next_skip);
+      const int ld_n = pad8(ch + 2 + next_skip);
       GALLOC(nl, int32_t, (int64_t)cnt * 4);
       GALLOC(nf, float, (int64_t)cnt * ld_n);
       GEN(sgnn_heads_write(xc, ch, ch, cand, locs, ncand, flg, offs, nl, nf, ld_n, stream));
