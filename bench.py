@@ -205,6 +205,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: ONE JSON line
         dist.init_process_group('nccl', device_id=dev)
     ones = np.ones(5, dtype=np.float32)
     lib.sgnn_debug_set_conv_impl(args.conv_impl)
@@ -365,6 +367,16 @@ def run_b200(args):
         per_set_flops += rec['flops']
     n_conv = max(n_conv, 1)
     convs_per_step = n_conv / max(args.steps, 1)
+    # DRAM bytes per launch of the same kernels from the committed ncu pass (profiles/conv_dram_traffic.json, made by
+    # profiles/summarize.py dram from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`): bench.py cannot run
+    # under ncu itself.  Cold cache (ncu flushes L2 per launch), conv_mode tc32.
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'conv_dram_traffic.json')))
+        if args.conv_mode == 'tc32' and args.blocks == 32:
+            traffic, traffic_src = tj['dram_bytes_per_launch'], 'profiles/conv_dram_traffic.json: ' + tj['source']
+    except Exception:
+        pass
     # ledger is of set 0; all sets are statistically alike (same generator) -> scale by launches
     alg_bytes_total = per_set_bytes * args.steps
     achieved = alg_bytes_total / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0
@@ -374,7 +386,7 @@ def run_b200(args):
                    'sgnn_conv_forward = conv_ro_kernel<COUT,CIN,..> + conv_child_f32_kernel (all %d launches per step)')
                   % round(convs_per_step),
         'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
-        'traffic': None, 'peak_source': peak_src,
+        'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
         'algorithmic_bytes_per_launch': per_set_bytes / max(convs_per_step, 1),
         'avg_launch_us': 1e3 * conv_ms / n_conv,
         'share_of_step': conv_ms / prof_ms if prof_ms > 0 else None,
@@ -383,8 +395,10 @@ def run_b200(args):
         'achieved_tflops_fp32': per_set_flops * args.steps / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0,
         'fp32_ffma_peak_tflops': 148 * 128 * 2 * 1.965e9 / 1e12,
         'fp32_ffma_peak_tflops_measured': ffma_meas,
-        'note': ('tc32: fp32 features on tcgen05 via an exact 3-way bf16 split; activations are L2 resident, the kernel is '
-                 'L2-gather / shared-memory-store bound' if args.conv_mode == 'tc32' else
+        'note': ('tc32: fp32 features on tcgen05 via an exact 3-way bf16 split for the wide layers with >= 60000 rows (child-mode '
+                 'upsampling + FCN/head convolutions), FFMA kernels for the rest; activations are L2 resident, the tensor-core '
+                 'kernels are bound by the L1/shared data pipe (row gathers + st.shared of the split planes, ncu: 79 %) and by '
+                 'latency at 8-16 warps per SM, not by HBM or the tensor pipe (8-14 % busy)' if args.conv_mode == 'tc32' else
                  'fp32 FFMA path: activations are L2 resident and the kernel is FFMA / L2-gather bound, so the HBM '
                  'fraction (SURVEY 8(d) definition) is small by construction; achieved_tflops_fp32 vs the FFMA peak '
                  'is the meaningful ceiling for this dtype'),
