@@ -902,7 +902,11 @@ __global__ void conv_gather_f32_generic_kernel(ConvParams p) {
 // (declared near the top of the file) 0 (default): v4 row-owner kernel, whole-row stages for wide inputs, parent-staged kernel for child mode;
 // 1: v2 tile kernels; 2: v1 runtime-shape kernel; 3: v4 only (whole-row stages for wide inputs); 4: v4 with
 // 16-channel sub-stages + child kernel; 5: v4 with 16-channel sub-stages only.  Tuning hook, all bit-identical.
-extern "C" void sgnn_debug_set_conv_impl(int v) { g_sgnn_conv_impl = v; }
+extern int g_sgnn_dense_impl;   // dense.cu
+extern "C" void sgnn_debug_set_conv_impl(int v) {
+  g_sgnn_dense_impl = v == 30 ? 1 : 0;
+  g_sgnn_conv_impl = v == 30 ? 0 : v;
+}
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 

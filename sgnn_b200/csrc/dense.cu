@@ -9,6 +9,8 @@
 // and relu.  The input may be the channel concatenation of two tensors (torch.cat of model.py:156,160).
 #include "common.cuh"
 
+int g_sgnn_dense_impl = 0;   // A/B hook (sgnn_debug_set_conv_impl 30): 1 = one-thread-per-output transposed convolution
+
 struct DenseArgs {
   const float* in0; int c0;
   const float* in1; int c1;
@@ -196,6 +198,75 @@ dense_convT3d_k4s2p1_kernel(DenseArgs a) {
   }
 }
 
+// Register-tiled version of the k4 s2 p1 transposed convolution (the two decoder layers are 60 % of the dense
+// U-Net's time: the kernel above issues 16 loads per 8 fmaf).  An output cell with parities (z&1, y&1, x&1) reads
+// the same 8 filter taps as every other cell of that parity class, and the cells of a class map 1:1 to input cells
+// q: (z,y,x) = 2q + parity.  A CTA owns one (parity class, tile of 4 output channels): its cin x 8 taps x 4 filter
+// values sit in shared memory ([ci][tap][4], read back as one warp-uniform LDS.128 per tap); a thread owns one
+// (batch, q) and 4 accumulators -- 8 input loads + 8 LDS.128 per 32 fmaf.  Per output element the order is unchanged:
+// ci ascending, then the in-range taps in kz,ky,kx order, one fmaf chain from +0.
+#define DCT_CO 4
+__global__ void __launch_bounds__(128)
+dense_convT3d_k4s2p1_tile_kernel(DenseArgs a) {
+  extern __shared__ __align__(16) float dct_w[];   // [cin][8][DCT_CO]
+  const int cin = a.c0 + a.c1;
+  const int cls = blockIdx.y & 7, co0 = (blockIdx.y >> 3) * DCT_CO;
+  const int pz = (cls >> 2) & 1, py = (cls >> 1) & 1, px = cls & 1;          // output parities of this class
+  const int kz0 = (pz + 1) & 1, ky0 = (py + 1) & 1, kx0 = (px + 1) & 1;
+  for (int i = threadIdx.x; i < cin * 8 * DCT_CO; i += blockDim.x) {
+    const int j = i % DCT_CO, t = (i / DCT_CO) & 7, ci = i / (8 * DCT_CO);
+    const int kz = kz0 + 2 * (t >> 2), ky = ky0 + 2 * ((t >> 1) & 1), kx = kx0 + 2 * (t & 1);
+    dct_w[i] = __ldg(a.w + ((long long)ci * a.cout + co0 + j) * 64 + (kz * 4 + ky) * 4 + kx);
+  }
+  __syncthreads();
+  const long long ivol = (long long)a.d0 * a.d1 * a.d2, ovol = (long long)a.o0 * a.o1 * a.o2;
+  const long long total = (long long)a.nb * ivol;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int qx = (int)(idx % a.d2), qy = (int)((idx / a.d2) % a.d1), qz = (int)((idx / ((long long)a.d1 * a.d2)) % a.d0);
+    const int b = (int)(idx / ivol);
+    const int z = 2 * qz + pz, y = 2 * qy + py, x = 2 * qx + px;
+    int off[8];
+    bool ok[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int kz = kz0 + 2 * (t >> 2), ky = ky0 + 2 * ((t >> 1) & 1), kx = kx0 + 2 * (t & 1);
+      const int tz = z + 1 - kz, ty = y + 1 - ky, tx = x + 1 - kx;
+      const int iz = tz >> 1, iy = ty >> 1, ix = tx >> 1;
+      ok[t] = tz >= 0 && ty >= 0 && tx >= 0 && iz < a.d0 && iy < a.d1 && ix < a.d2;
+      off[t] = (iz * a.d1 + iy) * a.d2 + ix;
+    }
+    float acc[DCT_CO];
+#pragma unroll
+    for (int j = 0; j < DCT_CO; ++j) acc[j] = 0.f;
+#pragma unroll 2
+    for (int ci = 0; ci < cin; ++ci) {
+      const float* src = dense_chan(a, b, ci, ivol);
+      float xv[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) xv[t] = ok[t] ? __ldg(src + off[t]) : 0.f;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float4 wv = *reinterpret_cast<const float4*>(dct_w + (ci * 8 + t) * DCT_CO);
+        if (ok[t]) {
+          acc[0] = fmaf(xv[t], wv.x, acc[0]);
+          acc[1] = fmaf(xv[t], wv.y, acc[1]);
+          acc[2] = fmaf(xv[t], wv.z, acc[2]);
+          acc[3] = fmaf(xv[t], wv.w, acc[3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < DCT_CO; ++j) {
+      const int co = co0 + j;
+      float v = acc[j];
+      if (a.scale) v = fmaf(v, __ldg(a.scale + co), __ldg(a.shift + co));
+      if (a.relu) v = fmaxf(v, 0.f);
+      a.out[((long long)b * a.cout + co) * ovol + ((long long)z * a.o1 + y) * a.o2 + x] = v;
+    }
+  }
+}
+
 static int dense_launch(bool transposed, const float* in0, int c0, const float* in1, int c1, int nb, int d0, int d1,
                         int d2, const float* w, int cout, int ks, int stride, int pad, const float* scale,
                         const float* shift, int relu, float* out, void* stream) {
@@ -220,6 +291,12 @@ static int dense_launch(bool transposed, const float* in0, int c0, const float* 
     const int fb = sgnn_blocks(total, 64, (int64_t)148 * 64);
     if (ks == 4) dense_conv3d_fast_kernel<4><<<fb, 64, 0, (cudaStream_t)stream>>>(a);
     else dense_conv3d_fast_kernel<1><<<fb, 64, 0, (cudaStream_t)stream>>>(a);
+  } else if (transposed && ks == 4 && stride == 2 && pad == 1 && cout % DCT_CO == 0 && (c0 + c1) * 8 * DCT_CO * 4 <= 48 * 1024 &&
+             g_sgnn_dense_impl == 0) {
+    // outputs = 8 parity classes x (nb x input cells): the extents are exactly twice the input's
+    const long long cells = (long long)nb * d0 * d1 * d2;
+    dim3 grid((unsigned)sgnn_blocks(cells, 128, 4096), (unsigned)(8 * (cout / DCT_CO)));
+    dense_convT3d_k4s2p1_tile_kernel<<<grid, 128, (size_t)(c0 + c1) * 8 * DCT_CO * 4, (cudaStream_t)stream>>>(a);
   } else if (transposed && ks == 4 && stride == 2 && pad == 1) dense_convT3d_k4s2p1_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a);
   else if (transposed) dense_convT3d_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a);
   else dense_conv3d_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a);

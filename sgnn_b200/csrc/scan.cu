@@ -59,57 +59,52 @@ scan_block_kernel(const void* __restrict__ in, int mode, int* __restrict__ out, 
   }
 }
 
-// Small inputs (the per-level grids and candidate lists of a 32-block batch): ONE CTA walks the tiles carrying the
-// running prefix, instead of the 3-launch hierarchy -- these scans sit on the critical path between two host reads.
-#define SCAN_SINGLE_MAX (SCAN_TILE * 16)
-__global__ void __launch_bounds__(SCAN_THREADS)
+// Small inputs (the per-level grids and candidate lists of a 32-block batch): ONE CTA instead of the 3-launch
+// hierarchy -- these scans sit on the critical path between two host reads.  1024 threads, IT contiguous items per
+// thread, one sweep: thread sums -> warp scans -> scan of the 32 warp totals -> write (2 barriers; the earlier
+// 256-thread version walked up to 16 tiles serially with 4 barriers each, 11 us per call, 20 calls per pass).
+#define SCAN_SINGLE_THREADS 1024
+#define SCAN_SINGLE_MAX (SCAN_SINGLE_THREADS * 32)
+template <int IT>
+__global__ void __launch_bounds__(SCAN_SINGLE_THREADS)
 scan_single_kernel(const void* __restrict__ in, int mode, int* __restrict__ out, long long n) {
-  __shared__ int warp_tot[SCAN_THREADS / 32];
-  __shared__ int carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
+  __shared__ int warp_tot[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (long long tile0 = 0; tile0 < n; tile0 += SCAN_TILE) {
-    const long long base = tile0 + (long long)threadIdx.x * SCAN_ITEMS;
-    int v[SCAN_ITEMS];
-    int tsum = 0;
+  const long long base = (long long)threadIdx.x * IT;
+  int v[IT];
+  int tsum = 0;
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-      const long long idx = base + i;
-      v[i] = idx < n ? scan_load(in, mode, idx) : 0;
-      tsum += v[i];
-    }
-    int inc = tsum;
+  for (int i = 0; i < IT; ++i) {
+    const long long idx = base + i;
+    v[i] = idx < n ? scan_load(in, mode, idx) : 0;
+    tsum += v[i];
+  }
+  int inc = tsum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = warp_tot[lane];
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += t;
+      int t = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += t;
     }
-    if (lane == 31) warp_tot[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-      int w = lane < SCAN_THREADS / 32 ? warp_tot[lane] : 0;
-#pragma unroll
-      for (int d = 1; d < SCAN_THREADS / 32; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, w, d);
-        if (lane >= d) w += t;
-      }
-      if (lane < SCAN_THREADS / 32) warp_tot[lane] = w;
-    }
-    __syncthreads();
-    const int carry = carry_s;
-    int excl = carry + inc - tsum + (wid ? warp_tot[wid - 1] : 0);
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-      const long long idx = base + i;
-      if (idx < n) out[idx] = excl;
-      excl += v[i];
-    }
-    __syncthreads();
-    if (threadIdx.x == SCAN_THREADS - 1) carry_s = excl;
-    __syncthreads();
+    warp_tot[lane] = w;  // inclusive
   }
-  if (threadIdx.x == 0) out[n] = carry_s;
+  __syncthreads();
+  int excl = inc - tsum + (wid ? warp_tot[wid - 1] : 0);
+#pragma unroll
+  for (int i = 0; i < IT; ++i) {
+    const long long idx = base + i;
+    if (idx < n) out[idx] = excl;
+    excl += v[i];
+  }
+  if (threadIdx.x == SCAN_SINGLE_THREADS - 1) out[n] = excl;   // items past n are zeros: the last thread holds the total
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
@@ -142,7 +137,11 @@ int sgnn_scan_exclusive(const void* in, int mode, int* out, int64_t n, void* scr
   if (n < 0 || !out || (!in && n > 0) || !scratch) return SGNN_E_INVALID;
   if (scratch_bytes < sgnn_scan_scratch_bytes(n)) return SGNN_E_INVALID;
   if (n <= SCAN_SINGLE_MAX) {
-    scan_single_kernel<<<1, SCAN_THREADS, 0, st>>>(in, mode, out, (long long)n);
+    const int per = (int)((n + SCAN_SINGLE_THREADS - 1) / SCAN_SINGLE_THREADS);
+    if (per <= 4) scan_single_kernel<4><<<1, SCAN_SINGLE_THREADS, 0, st>>>(in, mode, out, (long long)n);
+    else if (per <= 8) scan_single_kernel<8><<<1, SCAN_SINGLE_THREADS, 0, st>>>(in, mode, out, (long long)n);
+    else if (per <= 16) scan_single_kernel<16><<<1, SCAN_SINGLE_THREADS, 0, st>>>(in, mode, out, (long long)n);
+    else scan_single_kernel<32><<<1, SCAN_SINGLE_THREADS, 0, st>>>(in, mode, out, (long long)n);
     SGNN_CHECK_LAUNCH();
     return SGNN_OK;
   }
