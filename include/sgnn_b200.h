@@ -139,7 +139,7 @@ typedef struct SgnnConvArgs {
   int64_t n_out;          /* output rows (8 * parent rows in child mode) */
   const void* residual;   /* dev [n_out, ld_res] or NULL */
   int32_t ld_res;
-  int32_t reserved;
+  int32_t n_in;           /* rows of `in`, or 0 if not stated (only the pre-split tensor-core kernel needs it) */
   SgnnEpilogue a, b;
 } SgnnConvArgs;
 int sgnn_conv_forward(const SgnnConvArgs* args, void* stream);
@@ -153,6 +153,9 @@ int sgnn_conv_forward(const SgnnConvArgs* args, void* stream);
  * offset).  `workspace`: dev scratch of sgnn_conv_tc32_workspace_bytes(K, cin, child_mode) bytes for the prepared
  * filter bank (written by the call, on `stream`).  SGNN_E_UNSUPPORTED for shapes outside the above. */
 size_t sgnn_conv_tc32_workspace_bytes(int32_t K, int32_t cin, int32_t child_mode);
+/* Same plus room for the input rows pre-split into bf16 planes (96 B per row and 16-channel slice): with a workspace
+ * of this size and args->n_in set, the call may split the rows once per layer instead of once per (row, filter offset). */
+size_t sgnn_conv_tc32_workspace_bytes_rows(int32_t K, int32_t cin, int32_t child_mode, int64_t n_in);
 int sgnn_conv_forward_tc32(const SgnnConvArgs* args, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- scn.Deconvolution(3,Cin,Cout,2,2) (north_star operator surface; upstream Deconvolution_updateOutput)

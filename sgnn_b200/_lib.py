@@ -31,7 +31,7 @@ class SgnnConvArgs(C.Structure):
                 ('nbr', C.c_void_p), ('nbr_stride', C.c_int64), ('K', C.c_int32),
                 ('child_mode', C.c_int32), ('weight', C.c_void_p), ('cin', C.c_int32),
                 ('cout', C.c_int32), ('n_out', C.c_int64), ('residual', C.c_void_p),
-                ('ld_res', C.c_int32), ('reserved', C.c_int32),
+                ('ld_res', C.c_int32), ('n_in', C.c_int32),
                 ('a', SgnnEpilogue), ('b', SgnnEpilogue)]
 
 
@@ -100,6 +100,7 @@ SIGNATURES = {
     'sgnn_rulebook_strided': (_I, [_G, _P, _L, _P, _P, _L, _P]),
     'sgnn_conv_forward': (_I, [C.POINTER(SgnnConvArgs), _P]),
     'sgnn_conv_tc32_workspace_bytes': (_Z, [_I, _I, _I]),
+    'sgnn_conv_tc32_workspace_bytes_rows': (_Z, [_I, _I, _I, _L]),
     'sgnn_conv_forward_tc32': (_I, [C.POINTER(SgnnConvArgs), _P, _Z, _P]),
     'sgnn_deconv_forward': (_I, [_P, _I, _I, _P, _P, _I, _I, _L, _E, _P]),
     'sgnn_unpool': (_I, [_P, _I, _P, _I, _L, _E, _P]),

@@ -43,6 +43,8 @@ struct Tc32Params {
   const float* in; int ld_in; int cin;
   const int* nbr; long long nbr_stride; int K;
   const unsigned char* wsplit;
+  const unsigned char* planes;   // pre-split input rows [3][Q][n_in][16] bf16 (conv_tc32_pm_kernel), else NULL
+  long long n_in;
   long long n_rows;     // output rows (regular) / parent rows (child mode)
   const float* residual; int ld_res;
   float* out_a; int ld_a; int relu_a; const float* scale_a; const float* shift_a;
@@ -772,6 +774,204 @@ conv_tc32_tm_kernel(Tc32Params p, long long n_tiles) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// v4: as v3, but the input rows are split ONCE per layer instead of once per (row, tap): tc32_split_rows_kernel writes
+// the three bf16 planes of the layer's input as separate [n_in][16] arrays (plane-major, so the 32-byte rows of
+// raster-adjacent sites are contiguous), and the producers move 3 x 32 bytes per (row, tap, 16-channel slice) from
+// global memory to tensor memory (ld.global.v8 -> tcgen05.st.x8): ~20 instructions where v2/v3 spend ~300 on the
+// conversion, no shared-memory traffic at all for the A operand.
+__global__ void tc32_split_rows_kernel(const float* __restrict__ in, int ld_in, int cin, long long n_in, int Q,
+                                       unsigned char* __restrict__ planes) {
+  const long long total = n_in * Q;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx % n_in;
+    const int qc = (int)(idx / n_in);
+    float x0[8], x1[8];
+    load8<false>(in + row * ld_in, 16 * qc, cin, x0);
+    load8<false>(in + row * ld_in, 16 * qc + 8, cin, x1);
+    uint4 h[2], m[2], l[2];
+    split2(x0[0], x0[1], h[0].x, m[0].x, l[0].x); split2(x0[2], x0[3], h[0].y, m[0].y, l[0].y);
+    split2(x0[4], x0[5], h[0].z, m[0].z, l[0].z); split2(x0[6], x0[7], h[0].w, m[0].w, l[0].w);
+    split2(x1[0], x1[1], h[1].x, m[1].x, l[1].x); split2(x1[2], x1[3], h[1].y, m[1].y, l[1].y);
+    split2(x1[4], x1[5], h[1].z, m[1].z, l[1].z); split2(x1[6], x1[7], h[1].w, m[1].w, l[1].w);
+    uint4* d0 = reinterpret_cast<uint4*>(planes + ((size_t)(0 * Q + qc) * (size_t)n_in + (size_t)row) * 32);
+    uint4* d1 = reinterpret_cast<uint4*>(planes + ((size_t)(1 * Q + qc) * (size_t)n_in + (size_t)row) * 32);
+    uint4* d2 = reinterpret_cast<uint4*>(planes + ((size_t)(2 * Q + qc) * (size_t)n_in + (size_t)row) * 32);
+    d0[0] = h[0]; d0[1] = h[1];
+    d1[0] = m[0]; d1[1] = m[1];
+    d2[0] = l[0]; d2[1] = l[1];
+  }
+}
+
+
+template <int Q, int KG>
+__global__ void __launch_bounds__(160)
+conv_tc32_pm_kernel(Tc32Params p, long long n_tiles) {
+  static_assert(KG * Q * 24 <= 64, "A stage must fit its 64 TMEM columns");
+  extern __shared__ __align__(1024) unsigned char sm[];   // prepared filter bank [K][Q][3][512 B]
+  constexpr int B_OFF = Q * 3 * T32_BBLK;
+  __shared__ __align__(8) unsigned long long full[2], empty[2], acc_full, acc_empty;
+  __shared__ unsigned tmem_ptr_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr_s)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 128);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&acc_full, 1);
+    mbar_init(&acc_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::);
+  }
+  // filter bank: plain 16-byte copies (already in the canonical layout), once per CTA
+  for (int i = tid; i < p.K * (B_OFF / 16); i += 160) cp16(sm + i * 16, p.wsplit + (size_t)i * 16);
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  asm volatile("fence.proxy.async.shared::cta;" ::);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::);
+  const unsigned tmem = tmem_ptr_s;
+
+  const int ngroups = (p.K + KG - 1) / KG;
+  const int n_main = (p.K + 3) >> 2;
+  const long long my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const long long n_items = my_tiles * ngroups;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers + epilogue
+    unsigned x0[KG][Q][3][8], x1[KG][Q][3][8];   // packed bf16 pairs, straight from the pre-split planes
+    int idxn[KG];                                   // neighbour rows of the NEXT item to load
+    const unsigned lane_base = tmem + ((unsigned)(warp * 32) << 16);
+    auto load_idx = [&](long long item) {
+      const long long tile = blockIdx.x + (item / ngroups) * gridDim.x;
+      const int k0 = (int)(item % ngroups) * KG;
+      const long long j = tile * T32_M + tid;
+#pragma unroll
+      for (int kk = 0; kk < KG; ++kk)
+        idxn[kk] = (k0 + kk < p.K && j < p.n_rows) ? __ldg(p.nbr + (long long)(k0 + kk) * p.nbr_stride + j) : -1;
+    };
+    auto load_rows = [&](unsigned (&x)[KG][Q][3][8]) {   // rows idxn[] of every plane -> x (zeros for absent neighbours)
+#pragma unroll
+      for (int kk = 0; kk < KG; ++kk) {
+        if (idxn[kk] >= 0) {
+#pragma unroll
+          for (int qc = 0; qc < Q; ++qc)
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) {
+              const unsigned char* src = p.planes + ((size_t)(pl * Q + qc) * (size_t)p.n_in + (size_t)idxn[kk]) * 32;
+              asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                           : "=r"(x[kk][qc][pl][0]), "=r"(x[kk][qc][pl][1]), "=r"(x[kk][qc][pl][2]), "=r"(x[kk][qc][pl][3]),
+                             "=r"(x[kk][qc][pl][4]), "=r"(x[kk][qc][pl][5]), "=r"(x[kk][qc][pl][6]), "=r"(x[kk][qc][pl][7])
+                           : "l"(src));
+            }
+        } else {
+#pragma unroll
+          for (int qc = 0; qc < Q; ++qc)
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[kk][qc][pl][e] = 0u;
+        }
+      }
+    };
+    auto epilogue = [&](long long tl) {
+      mbar_wait(&acc_full, (unsigned)(tl & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::);
+      unsigned v[16], vc[16];
+      tmem_ld16(lane_base + T32_CORR, v);
+      for (int a = n_main - 1; a >= 0; --a) {
+        tmem_ld16(lane_base + 16u * (unsigned)a, vc);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(vc[c]));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::);
+      mbar_arrive(&acc_empty);
+      const long long j = (blockIdx.x + tl * gridDim.x) * T32_M + tid;
+      if (j < p.n_rows) epilogue_row16(p, v, j);
+    };
+    // one pipeline step: rows of item it+1 -> xn (in flight), item `it` (held in xc) -> TMEM stage it % 2
+    auto step = [&](long long it, unsigned (&xc)[KG][Q][3][8], unsigned (&xn)[KG][Q][3][8]) {
+      const long long tl = it / ngroups;
+      const int g = (int)(it % ngroups);
+      const int kg = min(KG, p.K - g * KG);
+      const int s = (int)(it & 1);
+      const long long u = it >> 1;
+      if (it + 1 < n_items) {
+        load_rows(xn);
+        if (it + 2 < n_items) load_idx(it + 2);
+      }
+      if (u > 0) mbar_wait(&empty[s], (unsigned)((u - 1) & 1));   // the MMAs that read this A stage have completed
+      asm volatile("tcgen05.fence::after_thread_sync;" ::);
+      const unsigned a_stage = lane_base + 128u + (unsigned)s * T32_ASTAGE_COLS;
+#pragma unroll
+      for (int kk = 0; kk < KG; ++kk)
+        if (kk < kg) {
+#pragma unroll
+          for (int qc = 0; qc < Q; ++qc)
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) tmem_st8(a_stage + (unsigned)((kk * Q + qc) * 24 + pl * 8), xc[kk][qc][pl]);
+        }
+      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::);
+      mbar_arrive(&full[s]);
+      if (g == 0 && tl > 0) epilogue(tl - 1);
+    };
+
+    if (n_items > 0) {
+      load_idx(0);
+      load_rows(x0);
+      if (n_items > 1) load_idx(1);
+    }
+    for (long long it = 0; it < n_items; it += 2) {
+      step(it, x0, x1);
+      if (it + 1 < n_items) step(it + 1, x1, x0);
+    }
+    if (my_tiles > 0) epilogue(my_tiles - 1);
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (warp 4)
+    for (long long it = 0; it < n_items; ++it) {
+      const long long tl = it / ngroups;
+      const int g = (int)(it % ngroups);
+      const int k0 = g * KG, kg = min(KG, p.K - k0);
+      const int s = (int)(it & 1);
+      mbar_wait(&full[s], (unsigned)((it >> 1) & 1));
+      if (g == 0 && tl >= 1) mbar_wait(&acc_empty, (unsigned)((tl - 1) & 1));   // epilogue of the previous tile drained
+      asm volatile("tcgen05.fence::after_thread_sync;" ::);
+      if (elect_one()) {
+        const unsigned a_stage = tmem + 128u + (unsigned)s * T32_ASTAGE_COLS;
+        for (int kk = 0; kk < kg; ++kk) {
+          const int k = k0 + kk;
+#pragma unroll
+          for (int qc = 0; qc < Q; ++qc) {
+            const unsigned a = a_stage + (unsigned)((kk * Q + qc) * 24);          // planes at +0, +8, +16 columns
+            const unsigned b = smem_u32(sm + (size_t)(k * Q + qc) * 3 * T32_BBLK); // planes at +0, +512, +1024 bytes
+            const unsigned first_corr = (k == 0 && qc == 0) ? 0u : 1u;
+            const unsigned first_main = ((k & 3) == 0 && qc == 0) ? 0u : 1u;
+            mma_bf16_ts(tmem + T32_CORR, a + 16u, umma_desc(b), first_corr);                    // x2 w0
+            mma_bf16_ts(tmem + T32_CORR, a + 8u, umma_desc(b + T32_BBLK), 1u);                  // x1 w1
+            mma_bf16_ts(tmem + T32_CORR, a, umma_desc(b + 2 * T32_BBLK), 1u);                   // x0 w2
+            mma_bf16_ts(tmem + T32_CORR, a + 8u, umma_desc(b), 1u);                             // x1 w0
+            mma_bf16_ts(tmem + T32_CORR, a, umma_desc(b + T32_BBLK), 1u);                       // x0 w1
+            mma_bf16_ts(tmem + 16u * (unsigned)(k >> 2), a, umma_desc(b), first_main);          // x0 w0
+          }
+        }
+        mma_commit(&empty[s]);
+        if (g == ngroups - 1) mma_commit(&acc_full);
+      }
+      __syncwarp();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // child mode: Cin = 48 (Q = 3), Cout = 16; p.n_rows = parent rows, output row 8 p + c
 __global__ void __launch_bounds__(128)
 conv_tc32_child_kernel(Tc32Params p, long long n_tiles) {
@@ -1145,7 +1345,40 @@ int launch_tm(const Tc32Params& p, cudaStream_t st) {
   return SGNN_OK;
 }
 
+template <int Q, int KG>
+int launch_pm(const Tc32Params& p, const float* in, int ld_in, cudaStream_t st) {
+  const size_t smem = (size_t)p.K * Q * 3 * T32_BBLK;
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_pm_kernel<Q, KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 27 * Q * 3 * T32_BBLK));
+    SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_pm_kernel<Q, KG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    ctas_per_sm = resident_ctas((const void*)conv_tc32_pm_kernel<Q, KG>, (size_t)27 * Q * 3 * T32_BBLK, 2, 160);
+    if (ctas_per_sm < 0) return SGNN_E_CUDA;
+  }
+  tc32_split_rows_kernel<<<sgnn_blocks(p.n_in * Q, 256), 256, 0, st>>>(in, ld_in, p.cin, p.n_in, Q, (unsigned char*)p.planes);
+  SGNN_CHECK_LAUNCH();
+  const long long tiles = (p.n_rows + T32_M - 1) / T32_M;
+  long long grid = (long long)148 * ctas_per_sm;
+  if (grid > tiles) grid = tiles;
+  conv_tc32_pm_kernel<Q, KG><<<(int)grid, 160, smem, st>>>(p, tiles);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+size_t tc32_weight_bytes(int K, int cin, int child_mode) {
+  const int Q = (cin + 15) / 16;
+  const size_t b = child_mode ? (size_t)64 * 3 * 3 * T32_BBLK : (size_t)K * Q * 3 * T32_BBLK;
+  return (b + 255) & ~(size_t)255;
+}
+
 }  // namespace
+
+extern "C" size_t sgnn_conv_tc32_workspace_bytes_rows(int32_t K, int32_t cin, int32_t child_mode, int64_t n_in) {
+  const int Q = (cin + 15) / 16;
+  size_t b = tc32_weight_bytes(K, cin, child_mode);
+  if (!child_mode && Q <= 2 && n_in > 0) b += (size_t)3 * Q * (size_t)n_in * 32;
+  return b;
+}
 
 extern "C" size_t sgnn_conv_tc32_workspace_bytes(int32_t K, int32_t cin, int32_t child_mode) {
   const int Q = (cin + 15) / 16;
@@ -1178,6 +1411,7 @@ extern "C" int sgnn_conv_forward_tc32(const SgnnConvArgs* a, void* workspace, si
   p.in = (const float*)a->in; p.ld_in = a->ld_in; p.cin = a->cin;
   p.nbr = a->nbr; p.nbr_stride = a->nbr_stride; p.K = a->K;
   p.wsplit = (const unsigned char*)workspace;
+  p.planes = nullptr; p.n_in = a->n_in;
   p.n_rows = a->child_mode ? a->n_out / 8 : a->n_out;
   p.residual = (const float*)a->residual; p.ld_res = a->ld_res;
   p.out_a = (float*)a->a.out; p.ld_a = a->a.ld; p.relu_a = a->a.relu; p.scale_a = a->a.scale; p.shift_a = a->a.shift;
@@ -1220,6 +1454,12 @@ extern "C" int sgnn_conv_forward_tc32(const SgnnConvArgs* a, void* workspace, si
     const int total = a->K * Q * 256;
     tc32_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)a->weight, a->K, a->cin, Q, (unsigned char*)workspace);
     SGNN_CHECK_LAUNCH();
+  }
+  if (g_sgnn_conv_impl == 27 && Q <= 2 && a->n_in > 0 &&
+      workspace_bytes >= sgnn_conv_tc32_workspace_bytes_rows(a->K, a->cin, 0, a->n_in)) {   // A/B: pre-split planes -> TMEM (v4)
+    p.planes = (const unsigned char*)workspace + tc32_weight_bytes(a->K, a->cin, 0);
+    if (Q == 1) return launch_pm<1, 2>(p, (const float*)a->in, a->ld_in, st);
+    return launch_pm<2, 1>(p, (const float*)a->in, a->ld_in, st);
   }
   if (g_sgnn_conv_impl == 24 && Q <= 2) {    // A/B: A operand through tensor memory (v3)
     if (Q == 1) return a32 ? launch_tm<1, 2, true>(p, st) : launch_tm<1, 2, false>(p, st);

@@ -10,6 +10,7 @@
 
 // SGNN_GEN_TC32: convolutions with fewer output rows stay on the FFMA kernels (a launch that cannot fill the chip with
 // 128-row tiles is latency bound either way, and the FFMA kernel's per-tile latency is shorter)
+extern int g_sgnn_conv_impl;   // conv.cu
 long long g_sgnn_tc32_min_rows = 60000;
 extern "C" void sgnn_debug_set_tc32_min_rows(int64_t n) { g_sgnn_tc32_min_rows = n; }
 
@@ -171,11 +172,13 @@ static int coarsen_finish(Ctx& c, const Level& f, Level* L, int32_t** parent, in
 
 static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr, int64_t nbr_stride, int K,
                 int child, const float* w, int cout, int64_t n_out, const float* res, int ld_res, const Epi& a,
-                const Epi& b) {
+                const Epi& b, int64_t n_in = 0) {
   SgnnConvArgs x;
   memset(&x, 0, sizeof(x));
   x.in = in; x.ld_in = ld_in; x.dtype = SGNN_F32; x.nbr = nbr; x.nbr_stride = nbr_stride; x.K = K;
   x.child_mode = child; x.weight = w; x.cin = cin; x.cout = cout; x.n_out = n_out; x.residual = res; x.ld_res = ld_res;
+  if (n_in == 0 && K == 27 && !child) n_in = n_out;   // submanifold: input rows == output rows
+  x.n_in = n_in > 0 && n_in <= 0x7fffffff ? (int32_t)n_in : 0;
   x.a.out = a.out; x.a.ld = a.ld; x.a.relu = a.relu; x.a.scale = a.scale; x.a.shift = a.shift;
   x.b.out = b.out; x.b.ld = b.ld; x.b.relu = b.relu; x.b.scale = b.scale; x.b.shift = b.shift;
   const bool prof = c.profile && c.n_ev + 2 <= 512;   // 256 records
@@ -186,7 +189,9 @@ static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr,
   int rc = SGNN_E_UNSUPPORTED;
   bool used_tc = false;
   if (c.tc32 && cout == 16 && cin >= 12 && cin <= 48 && (!child || cin == 48) && n_out >= g_sgnn_tc32_min_rows) {
-    const size_t wb = sgnn_conv_tc32_workspace_bytes(K, cin, child);
+    // room for the pre-split input planes only when that kernel generation is selected (hook 27)
+    const size_t wb = g_sgnn_conv_impl == 27 ? sgnn_conv_tc32_workspace_bytes_rows(K, cin, child, x.n_in)
+                                             : sgnn_conv_tc32_workspace_bytes(K, cin, child);
     void* ws = c.ar.get(wb);
     if (!ws) return SGNN_E_NOMEM;
     rc = sgnn_conv_forward_tc32(&x, ws, wb, c.stream);
@@ -238,7 +243,7 @@ static int fcn(Ctx& c, const Level& lv0, const SgnnFcnW& f, const float* x_raw, 
     ALLOC(z1_raw, float, lv1.n * ch);
     ALLOC(z1_bn, float, lv1.n * ch);
     RC(conv(c, y0_bn, ch, ch, chi01, lv1.n, 8, 0, f.w_down[0], ch, lv1.n, nullptr, 0, epi(z1_raw, ch),
-            epi_bn(z1_bn, ch, f.blk[1].bn0)));
+            epi_bn(z1_bn, ch, f.blk[1].bn0), lv0.n));
     ALLOC(y1_bn, float, lv1.n * ch);
     RC(res_block(c, lv1, f.blk[1], ch, z1_raw, z1_bn, epi(J1, 2 * ch), epi_bn(y1_bn, ch, f.bn_down[1])));
     ALLOC(y2, float, lv2.n * ch);
@@ -246,7 +251,7 @@ static int fcn(Ctx& c, const Level& lv0, const SgnnFcnW& f, const float* x_raw, 
       ALLOC(z2_raw, float, lv2.n * ch);
       ALLOC(z2_bn, float, lv2.n * ch);
       RC(conv(c, y1_bn, ch, ch, chi12, lv2.n, 8, 0, f.w_down[1], ch, lv2.n, nullptr, 0, epi(z2_raw, ch),
-              epi_bn(z2_bn, ch, f.blk[2].bn0)));
+              epi_bn(z2_bn, ch, f.blk[2].bn0), lv1.n));
       RC(res_block(c, lv2, f.blk[2], ch, z2_raw, z2_bn, epi(y2, ch), kNoEpi));
     }
     SgnnEpilogue e1;
@@ -329,7 +334,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       out->rows[l + 1] = cl.n;
       GALLOC(h, float, cl.n * ch);
       if (cl.n) {
-        GEN(conv(c, skip, ch, ch, chi, cl.n, 8, 0, e.w_down, ch, cl.n, nullptr, 0, epi_bn(h, ch, e.bn_down), kNoEpi));
+        GEN(conv(c, skip, ch, ch, chi, cl.n, 8, 0, e.w_down, ch, cl.n, nullptr, 0, epi_bn(h, ch, e.bn_down), kNoEpi, lv.n));
       }
       lv = cl;
       x = h;

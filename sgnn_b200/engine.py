@@ -169,6 +169,7 @@ def conv(x, nbr, weight, n_out, out_a, child_mode=False, residual=None, scale_a=
     a.weight = weight.data_ptr()
     a.cin, a.cout = cin, cout
     a.n_out = int(n_out)
+    a.n_in = int(x.shape[0])
     if residual is not None:
         assert residual.stride(1) == 1
         a.residual = residual.data_ptr()
@@ -181,7 +182,7 @@ def conv(x, nbr, weight, n_out, out_a, child_mode=False, residual=None, scale_a=
     ctx = PROFILER.conv(x, nbr, weight, int(n_out), child_mode, residual is not None,
                         out_b is not None) if PROFILER is not None else None
     if tc32:
-        wb = lib.sgnn_conv_tc32_workspace_bytes(K, cin, a.child_mode)
+        wb = lib.sgnn_conv_tc32_workspace_bytes_rows(K, cin, a.child_mode, a.n_in)
         ws = _scratch(wb, x.device)
         check(lib.sgnn_conv_forward_tc32(C.byref(a), C.c_void_p(ws.data_ptr()), wb, _stream()), 'sgnn_conv_forward_tc32')
     else:

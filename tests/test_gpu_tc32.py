@@ -22,12 +22,14 @@ def _E():
     return E
 
 
-@pytest.fixture(autouse=True, params=[0, 23, 24, 25], ids=['default', 'warp-specialised', 'tmem-operand', 'child-single-role'])
+@pytest.fixture(autouse=True, params=[0, 23, 24, 25, 27],
+                ids=['default', 'warp-specialised', 'tmem-operand', 'child-single-role', 'presplit-planes'])
 def tc_impl(request):
     """Every generation of the regular tensor-core kernel: 0 = every warp gathers, thread 0 issues the MMAs;
     23 = producer warps + MMA-issuer warp with a two-stage shared-memory ring and double-buffered TMEM accumulators;
     24 = as 23 but the A operand is written to tensor memory (tcgen05.st) and the MMAs read it from there;
-    25 = regular kernel as 0, child-mode convolution on the single-role kernel instead of the warp-specialised one."""
+    25 = regular kernel as 0, child-mode convolution on the single-role kernel instead of the warp-specialised one;
+    27 = as 24 but the input rows are split into bf16 planes once per layer (pre-pass) and gathered straight into TMEM."""
     from sgnn_b200._lib import lib
     lib.sgnn_debug_set_conv_impl(request.param)
     yield request.param
