@@ -312,8 +312,13 @@ int sgnn_coords_to_i64(const int32_t* in, int64_t n, int64_t* out, void* stream)
 /* Number of CUDA kernels this library has launched in the calling process (monotonic). */
 int64_t sgnn_launch_count(void);
 
-/* Test hook: choose the convolution implementation (0 = default constant-weight kernel, 1 = tile kernels,
- * 2 = runtime-shape kernel).  All give bit-identical results. */
+/* Test / A-B hook: choose among kernel generations that compute the same thing.
+ *   FFMA convolution (all bit-identical): 0 default row-owner kernel, 1 tile kernels, 2 runtime-shape kernel, 3-7, 10, 11
+ *   variants of the row-owner policy.
+ *   Tensor-core fp32 convolution (sgnn_conv_forward_tc32; all within the same tolerance): 0 default (single-role regular
+ *   kernel + warp-specialised child kernel), 21 one filter offset per work item, 23 warp-specialised regular kernel,
+ *   24 A operand through tensor memory, 27 input rows pre-split into bf16 planes once per layer, 25 single-role child
+ *   kernel, 26 one offset per item for 32-channel inputs.   30: one-thread-per-output transposed dense convolution. */
 void sgnn_debug_set_conv_impl(int impl);
 
 /* Tuning hook: under SGNN_GEN_TC32 only convolutions with at least n output rows use the tensor-core path (default 60000). */

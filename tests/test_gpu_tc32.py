@@ -34,6 +34,7 @@ def tc_impl(request):
     lib.sgnn_debug_set_conv_impl(request.param)
     yield request.param
     lib.sgnn_debug_set_conv_impl(0)
+    lib.sgnn_debug_set_tc32_min_rows(60000)     # _model() lowers it to 0 so that every eligible layer is covered
 
 
 def _bound(x, nbr, w, n_out, child_mode=False):
