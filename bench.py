@@ -439,10 +439,17 @@ def run_b200(args):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 from C (NCCL's version banner under
+    # torchrun, for one) are sent to stderr; the line itself goes to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, 'w', buffering=1)
     if args.impl == 'reference':
         run_reference(args)
     else:
         run_b200(args)
+    sys.stdout.flush()
 
 
 if __name__ == '__main__':
