@@ -29,6 +29,7 @@
 // a 2x2x2 stencil per child over PARENT rows -- 64 (e,c) pairs instead of 216 (d,c) pairs.  A tile is 128 parents
 // (M = 128), the accumulators 2 x [128 x (8 children x 16)] fp32 = 256 TMEM columns; per parent offset e the 128 neighbour
 // rows (48 channels) are gathered ONCE and multiplied with the pre-summed filter of every child that uses e.
+#include <stdlib.h>
 #include "common.cuh"
 
 #define T32_M 128
@@ -1327,13 +1328,26 @@ int launch_ws(const Tc32Params& p, cudaStream_t st) {
   return SGNN_OK;
 }
 
+// Shared-memory carve-out of the TMEM-operand kernels (percent of the 228 KB).  They need only the filter bank in shared
+// memory (2 CTAs x 42 KB), so a smaller carve-out leaves the L1 data cache room for the distinct rows of a tile, which the
+// 27 filter offsets re-read ~9 times (scratch/reuse_model.py).  A/B knob: SGNN_TC32_TM_CARVEOUT (default 100).
+int tm_carveout() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SGNN_TC32_TM_CARVEOUT");
+    v = e ? atoi(e) : 100;
+    if (v < 40 || v > 100) v = 100;
+  }
+  return v;
+}
+
 template <int Q, int KG, bool A32>
 int launch_tm(const Tc32Params& p, cudaStream_t st) {
   const size_t smem = (size_t)p.K * Q * 3 * T32_BBLK;
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
     SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_tm_kernel<Q, KG, A32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 27 * Q * 3 * T32_BBLK));
-    SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_tm_kernel<Q, KG, A32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_tm_kernel<Q, KG, A32>, cudaFuncAttributePreferredSharedMemoryCarveout, tm_carveout()));
     ctas_per_sm = resident_ctas((const void*)conv_tc32_tm_kernel<Q, KG, A32>, (size_t)27 * Q * 3 * T32_BBLK, 2, 160);
     if (ctas_per_sm < 0) return SGNN_E_CUDA;
   }
@@ -1351,7 +1365,7 @@ int launch_pm(const Tc32Params& p, const float* in, int ld_in, cudaStream_t st) 
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
     SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_pm_kernel<Q, KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 27 * Q * 3 * T32_BBLK));
-    SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_pm_kernel<Q, KG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_pm_kernel<Q, KG>, cudaFuncAttributePreferredSharedMemoryCarveout, tm_carveout()));
     ctas_per_sm = resident_ctas((const void*)conv_tc32_pm_kernel<Q, KG>, (size_t)27 * Q * 3 * T32_BBLK, 2, 160);
     if (ctas_per_sm < 0) return SGNN_E_CUDA;
   }
