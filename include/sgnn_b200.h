@@ -318,7 +318,8 @@ int64_t sgnn_launch_count(void);
  *   Tensor-core fp32 convolution (sgnn_conv_forward_tc32; all within the same tolerance): 0 default (single-role regular
  *   kernel + warp-specialised child kernel), 21 one filter offset per work item, 23 warp-specialised regular kernel,
  *   24 A operand through tensor memory, 27 input rows pre-split into bf16 planes once per layer, 25 single-role child
- *   kernel, 26 one offset per item for 32-channel inputs.   30: one-thread-per-output transposed dense convolution. */
+ *   kernel, 26 one offset per item for 32-channel inputs, 28 EXPERIMENTAL (never run on a GPU yet): distinct rows of a
+ *   tile staged once in shared memory.   30: one-thread-per-output transposed dense convolution. */
 void sgnn_debug_set_conv_impl(int impl);
 
 /* Tuning hook: under SGNN_GEN_TC32 only convolutions with at least n output rows use the tensor-core path (default 60000). */

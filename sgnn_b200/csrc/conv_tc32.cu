@@ -973,6 +973,226 @@ conv_tc32_pm_kernel(Tc32Params p, long long n_tiles) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// v5 (EXPERIMENTAL, hook 28, not yet run on a GPU): stage every DISTINCT input row of a tile once.
+// scratch/reuse_model.py: with the generator's row order a 128-row tile of the fine levels issues 14 present taps per
+// output row but touches only 1.6 distinct input rows per output row -- the kernels above read (and convert) every row
+// ~9 times, and the L2->SM gather is their common wall.  Per tile this kernel
+//   1. loads the 27 x 128 neighbour indices and de-duplicates them in a shared-memory hash table (atomicCAS on the row
+//      id; a second pass numbers the occupied slots = local ids, one list entry per distinct row);
+//   2. gathers each distinct row ONCE (64 B), splits it into the three bf16 planes and parks the 96 bytes in shared
+//      memory (U_CAP = 512 rows; rows past the cap -- not seen on the fine levels -- take a slow per-tap global path);
+//   3. for every tap moves the 128 rows' planes shared memory -> tensor memory (6 LDS.128 + 3 tcgen05.st per row) for
+//      the MMA warp, exactly as the pre-split kernel does from global memory.
+// 16-channel inputs only (Q = 1), 3^3 submanifold convolutions (the strided rulebook has no reuse).
+#define UR_CAP 512
+#define UR_HASH 1024
+__device__ __forceinline__ void bar_producers() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int KG>
+__global__ void __launch_bounds__(160)
+conv_tc32_ur_kernel(Tc32Params p, long long n_tiles) {
+  static_assert(KG * 24 <= 64, "A stage must fit its 64 TMEM columns");
+  extern __shared__ __align__(1024) unsigned char sm[];
+  constexpr int B_OFF = 3 * T32_BBLK;
+  unsigned char* bank = sm;                                               // [K][3][512]
+  unsigned char* rows = sm + 27 * B_OFF;                                  // [UR_CAP][3][32 B]
+  int* hkey = reinterpret_cast<int*>(rows + UR_CAP * 96);                 // [UR_HASH] row id or -1
+  int* hval = hkey + UR_HASH;                                             // [UR_HASH] local id
+  int* list = hval + UR_HASH;                                             // [UR_CAP] row id of local id
+  __shared__ __align__(8) unsigned long long full[2], empty[2], acc_full, acc_empty;
+  __shared__ unsigned tmem_ptr_s;
+  __shared__ int n_unique;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr_s)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 128);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&acc_full, 1);
+    mbar_init(&acc_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::);
+  }
+  for (int i = tid; i < 27 * (B_OFF / 16); i += 160) cp16(bank + i * 16, p.wsplit + (size_t)i * 16);
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  asm volatile("fence.proxy.async.shared::cta;" ::);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::);
+  const unsigned tmem = tmem_ptr_s;
+
+  constexpr int K = 27;                       // 3^3 submanifold only: lets the tap loop unroll, indices stay in registers
+  constexpr int ngroups = (K + KG - 1) / KG;
+  constexpr int n_main = (K + 3) >> 2;
+  const long long my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers + epilogue
+    const unsigned lane_base = tmem + ((unsigned)(warp * 32) << 16);
+    auto epilogue = [&](long long tl) {
+      mbar_wait(&acc_full, (unsigned)(tl & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::);
+      unsigned v[16], vc[16];
+      tmem_ld16(lane_base + T32_CORR, v);
+      for (int a = n_main - 1; a >= 0; --a) {
+        tmem_ld16(lane_base + 16u * (unsigned)a, vc);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(vc[c]));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::);
+      mbar_arrive(&acc_empty);
+      const long long j = (blockIdx.x + tl * gridDim.x) * T32_M + tid;
+      if (j < p.n_rows) epilogue_row16(p, v, j);
+    };
+
+    long long it = 0;                                   // running work-item counter (stage / parity bookkeeping)
+    for (long long tl = 0; tl < my_tiles; ++tl) {
+      const long long j = (blockIdx.x + tl * gridDim.x) * T32_M + tid;
+      // ---- 1. neighbour indices of this thread's row, hash slots of the present ones
+      int idx[27];
+#pragma unroll
+      for (int k = 0; k < 27; ++k)
+        idx[k] = j < p.n_rows ? __ldg(p.nbr + (long long)k * p.nbr_stride + j) : -1;
+      for (int i = tid; i < UR_HASH; i += 128) hkey[i] = -1;
+      if (tid == 0) n_unique = 0;
+      bar_producers();
+      unsigned short slot[27];
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        slot[k] = 0xffff;
+        if (idx[k] >= 0) {
+          unsigned h = ((unsigned)idx[k] * 2654435761u) >> 22;          // 10 bits
+          slot[k] = 0xfffe;                                             // "not in the table": fetched per tap from global
+          for (int tries = 0; tries < 32; ++tries) {                    // bounded: a tile may have > UR_HASH distinct rows
+            const int old = atomicCAS(&hkey[h], -1, idx[k]);
+            if (old == -1 || old == idx[k]) { slot[k] = (unsigned short)h; break; }
+            h = (h + 1) & (UR_HASH - 1);
+          }
+        }
+      }
+      bar_producers();
+      // ---- number the occupied slots (local ids) and list the distinct rows
+      for (int i = tid; i < UR_HASH; i += 128) {
+        const int key = hkey[i];
+        if (key >= 0) {
+          const int lid = atomicAdd(&n_unique, 1);
+          hval[i] = lid;
+          if (lid < UR_CAP) list[lid] = key;
+        }
+      }
+      bar_producers();
+      const int nu = min(n_unique, UR_CAP);
+      // ---- 2. every distinct row once: gather, split, park the three planes
+      for (int q = tid; q < nu; q += 128) {
+        const float* src = p.in + (long long)list[q] * p.ld_in;
+        float a0[8], a1[8];
+        load8<false>(src, 0, p.cin, a0);
+        load8<false>(src, 8, p.cin, a1);
+        uint4 h0, h1, m0, m1, l0, l1;
+        split2(a0[0], a0[1], h0.x, m0.x, l0.x); split2(a0[2], a0[3], h0.y, m0.y, l0.y);
+        split2(a0[4], a0[5], h0.z, m0.z, l0.z); split2(a0[6], a0[7], h0.w, m0.w, l0.w);
+        split2(a1[0], a1[1], h1.x, m1.x, l1.x); split2(a1[2], a1[3], h1.y, m1.y, l1.y);
+        split2(a1[4], a1[5], h1.z, m1.z, l1.z); split2(a1[6], a1[7], h1.w, m1.w, l1.w);
+        uint4* dst = reinterpret_cast<uint4*>(rows + q * 96);
+        dst[0] = h0; dst[1] = h1; dst[2] = m0; dst[3] = m1; dst[4] = l0; dst[5] = l1;
+      }
+      bar_producers();
+      // ---- 3. tap by tap: shared memory -> tensor memory
+#pragma unroll
+      for (int g = 0; g < ngroups; ++g, ++it) {
+        const int s = (int)(it & 1);
+        const long long u = it >> 1;
+        if (u > 0) mbar_wait(&empty[s], (unsigned)((u - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::);
+        const unsigned a_stage = lane_base + 128u + (unsigned)s * T32_ASTAGE_COLS;
+#pragma unroll
+        for (int kk = 0; kk < KG; ++kk) {
+          if (g * KG + kk < K) {
+            const int my_idx = idx[g * KG + kk];
+            const unsigned my_slot = slot[g * KG + kk];
+            unsigned r[3][8];
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) r[pl][e] = 0u;
+            if (my_idx >= 0) {
+              const int lid = my_slot < UR_HASH ? hval[my_slot] : UR_CAP;
+              if (lid < UR_CAP) {
+                const uint4* src = reinterpret_cast<const uint4*>(rows + lid * 96);
+#pragma unroll
+                for (int pl = 0; pl < 3; ++pl) {
+                  const uint4 lo = src[2 * pl], hi = src[2 * pl + 1];
+                  r[pl][0] = lo.x; r[pl][1] = lo.y; r[pl][2] = lo.z; r[pl][3] = lo.w;
+                  r[pl][4] = hi.x; r[pl][5] = hi.y; r[pl][6] = hi.z; r[pl][7] = hi.w;
+                }
+              } else {                                   // past the cap: this row was not staged, split it here
+                const float* src = p.in + (long long)my_idx * p.ld_in;
+                float a0[8], a1[8];
+                load8<false>(src, 0, p.cin, a0);
+                load8<false>(src, 8, p.cin, a1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  split2(a0[2 * i], a0[2 * i + 1], r[0][i], r[1][i], r[2][i]);
+                  split2(a1[2 * i], a1[2 * i + 1], r[0][4 + i], r[1][4 + i], r[2][4 + i]);
+                }
+              }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) tmem_st8(a_stage + (unsigned)(kk * 24 + pl * 8), r[pl]);
+          }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::);
+        mbar_arrive(&full[s]);
+        if (g == 0 && tl > 0) epilogue(tl - 1);
+      }
+      bar_producers();    // every producer is done reading `rows` / the hash before the next tile rebuilds them
+    }
+    if (my_tiles > 0) epilogue(my_tiles - 1);
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (warp 4)
+    const long long n_items = my_tiles * ngroups;
+    for (long long it = 0; it < n_items; ++it) {
+      const long long tl = it / ngroups;
+      const int g = (int)(it % ngroups);
+      const int k0 = g * KG, kg = min(KG, K - k0);
+      const int s = (int)(it & 1);
+      mbar_wait(&full[s], (unsigned)((it >> 1) & 1));
+      if (g == 0 && tl >= 1) mbar_wait(&acc_empty, (unsigned)((tl - 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::);
+      if (elect_one()) {
+        const unsigned a_stage = tmem + 128u + (unsigned)s * T32_ASTAGE_COLS;
+        for (int kk = 0; kk < kg; ++kk) {
+          const int k = k0 + kk;
+          const unsigned a = a_stage + (unsigned)(kk * 24);
+          const unsigned b = smem_u32(bank + (size_t)k * 3 * T32_BBLK);
+          const unsigned first_corr = k == 0 ? 0u : 1u;
+          const unsigned first_main = (k & 3) == 0 ? 0u : 1u;
+          mma_bf16_ts(tmem + T32_CORR, a + 16u, umma_desc(b), first_corr);
+          mma_bf16_ts(tmem + T32_CORR, a + 8u, umma_desc(b + T32_BBLK), 1u);
+          mma_bf16_ts(tmem + T32_CORR, a, umma_desc(b + 2 * T32_BBLK), 1u);
+          mma_bf16_ts(tmem + T32_CORR, a + 8u, umma_desc(b), 1u);
+          mma_bf16_ts(tmem + T32_CORR, a, umma_desc(b + T32_BBLK), 1u);
+          mma_bf16_ts(tmem + 16u * (unsigned)(k >> 2), a, umma_desc(b), first_main);
+        }
+        mma_commit(&empty[s]);
+        if (g == ngroups - 1) mma_commit(&acc_full);
+      }
+      __syncwarp();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // child mode: Cin = 48 (Q = 3), Cout = 16; p.n_rows = parent rows, output row 8 p + c
 __global__ void __launch_bounds__(128)
 conv_tc32_child_kernel(Tc32Params p, long long n_tiles) {
@@ -1379,6 +1599,23 @@ int launch_pm(const Tc32Params& p, const float* in, int ld_in, cudaStream_t st) 
   return SGNN_OK;
 }
 
+int launch_ur(const Tc32Params& p, cudaStream_t st) {
+  constexpr size_t smem = (size_t)27 * 3 * T32_BBLK + (size_t)UR_CAP * 96 + (size_t)(2 * UR_HASH + UR_CAP) * 4;
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_ur_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGNN_CUDA(cudaFuncSetAttribute(conv_tc32_ur_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    ctas_per_sm = resident_ctas((const void*)conv_tc32_ur_kernel<2>, smem, 2, 160);
+    if (ctas_per_sm < 0) return SGNN_E_CUDA;
+  }
+  const long long tiles = (p.n_rows + T32_M - 1) / T32_M;
+  long long grid = (long long)148 * ctas_per_sm;
+  if (grid > tiles) grid = tiles;
+  conv_tc32_ur_kernel<2><<<(int)grid, 160, smem, st>>>(p, tiles);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
 size_t tc32_weight_bytes(int K, int cin, int child_mode) {
   const int Q = (cin + 15) / 16;
   const size_t b = child_mode ? (size_t)64 * 3 * 3 * T32_BBLK : (size_t)K * Q * 3 * T32_BBLK;
@@ -1469,6 +1706,7 @@ extern "C" int sgnn_conv_forward_tc32(const SgnnConvArgs* a, void* workspace, si
     tc32_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)a->weight, a->K, a->cin, Q, (unsigned char*)workspace);
     SGNN_CHECK_LAUNCH();
   }
+  if (g_sgnn_conv_impl == 28 && Q == 1 && a->K == 27) return launch_ur(p, st);   // EXPERIMENTAL: distinct rows staged once per tile
   if (g_sgnn_conv_impl == 27 && Q <= 2 && a->n_in > 0 &&
       workspace_bytes >= sgnn_conv_tc32_workspace_bytes_rows(a->K, a->cin, 0, a->n_in)) {   // A/B: pre-split planes -> TMEM (v4)
     p.planes = (const unsigned char*)workspace + tc32_weight_bytes(a->K, a->cin, 0);
