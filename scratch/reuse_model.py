@@ -46,7 +46,7 @@ def main():
         c = l[0].numpy()
         kept = (torch.sigmoid(l[1][:, 0]) > 0.5).numpy()
         analyse('level %d candidates' % i, c)
-        analyse('level %d kept (next level rows)' % i, c[kept])
+        analyse('level %d kept (next rows; child-conv parents)' % i, c[kept])
     analyse('surface level rows', out_locs.numpy())
     # the same surface rows in raster order, for comparison
     o = out_locs.numpy()
@@ -56,3 +56,4 @@ def main():
 
 if __name__ == '__main__':
     main()
+
