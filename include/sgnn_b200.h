@@ -298,6 +298,27 @@ int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coords, int coor
  * rec6 = {n_out, cin, cout, K, child_mode, ran on tensor cores}, *ms = CUDA-event duration.  SGNN_E_INVALID past the end. */
 int sgnn_generator_profile_entry(int32_t i, int64_t* rec6, float* ms);
 
+/* ---- marching cubes on the predicted dense TSDF, the step after the forward pass
+ * (reference torch/marching_cubes/marching_cubes.cpp:459-517 run_marching_cubes, called from data_util.py:270-284).
+ * tsdf dev [n0,n1,n2] fp32 (z,y,x), -inf = unobserved.  Three calls:
+ *   sgnn_mc_count   per cell the number of triangles the reference emits for it (8 trilinear corner samples, cube index,
+ *                   the reference's threshold tests and table), exclusive-scanned: offs dev [n0*n1*n2 + 1]; offs[last]
+ *                   = number of triangles.  scratch >= sgnn_mc_scratch_bytes(n0, n1, n2).
+ *   sgnn_mc_emit    the triangle soup, tris dev [n_tri, 3, 3] (x,y,z per vertex), in the reference's order (cells z,y,x
+ *                   raster, table order) and with its bits (every float operation rounds once, in its operand order).
+ *   sgnn_mc_merge_host  HOST function on host arrays: merge_close_vertices(1e-5, approx) in first-come order, then
+ *                   remove_degenerate_faces / remove_duplicate_faces (:266-455).  verts [3*n_tri,3] and faces [n_tri,3]
+ *                   are caller-allocated upper bounds; the used counts are returned. */
+size_t sgnn_mc_scratch_bytes(int32_t n0, int32_t n1, int32_t n2);
+int sgnn_mc_count(const float* tsdf, int32_t n0, int32_t n1, int32_t n2, float isovalue, float truncation, float thresh,
+                  int32_t* offs, void* scratch, size_t scratch_bytes, void* stream);
+int sgnn_mc_emit(const float* tsdf, int32_t n0, int32_t n1, int32_t n2, float isovalue, float truncation, float thresh,
+                 const int32_t* offs, float* tris, void* stream);
+int sgnn_mc_merge_host(const float* tris, int64_t n_tri, float* verts, int32_t* faces, int64_t* n_verts,
+                       int64_t* n_faces);
+/* The packed triangulation table the kernels use: 256 words, 4 bits per triangle-vertex edge id, 0xF terminates. */
+int sgnn_mc_table(uint64_t* out256);
+
 /* Candidate coordinates of model.py:192-207: out dev [8*n_parent,4]. */
 int sgnn_children_coords(const int32_t* parent_coords, int64_t n_parent, int32_t* out, void* stream);
 

@@ -120,6 +120,11 @@ SIGNATURES = {
     'sgnn_generator_forward': (_I, [C.POINTER(SgnnGeneratorW), _P, _I, _P, _L, _I, C.POINTER(C.c_int32), _P, _Z, _I,
                                     C.POINTER(SgnnGeneratorOut), _P]),
     'sgnn_generator_profile_entry': (_I, [_I, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
+    'sgnn_mc_scratch_bytes': (_Z, [_I, _I, _I]),
+    'sgnn_mc_count': (_I, [_P, _I, _I, _I, C.c_float, C.c_float, C.c_float, _P, _P, _Z, _P]),
+    'sgnn_mc_emit': (_I, [_P, _I, _I, _I, C.c_float, C.c_float, C.c_float, _P, _P, _P]),
+    'sgnn_mc_merge_host': (_I, [_P, _L, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    'sgnn_mc_table': (_I, [_P]),
     'sgnn_children_coords': (_I, [_P, _L, _P, _P]),
     'sgnn_concat_skip': (_I, [_G, _P, _I, _I, _P, _L, _P, _I, _I, _P]),
     'sgnn_coords_to_i64': (_I, [_P, _L, _P, _P]),

@@ -1,0 +1,91 @@
+"""the product's marching cubes (csrc/mcubes.cu, sgnn_b200/mesh.py).
+CPU part (no GPU): the packed triangulation table equals the one recovered from the reference, and the host half
+(sgnn_mc_merge_host: first-come vertex merge, degenerate / duplicate faces) reproduces the REAL reference's vertices and
+faces from the reference-order triangle soup (the soup comes from the oracle here; on a GPU it comes from the kernels).
+GPU part: the kernels' triangle soup equals the oracle's bit for bit, and the whole call equals the reference fixtures."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import mcubes
+from conftest import GOLDEN
+
+CASES = ['sphere', 'blobs', 'noise', 'plane']
+
+
+def test_packed_table_matches_the_recovered_table():
+    from sgnn_b200._lib import lib
+    words = (C.c_uint64 * 256)()
+    assert lib.sgnn_mc_table(words) == 0
+    t = mcubes.tri_table()
+    for c in range(256):
+        w = int(words[c])
+        got = []
+        for i in range(16):
+            nib = (w >> (4 * i)) & 0xF
+            if nib == 0xF:
+                break
+            got.append(nib)
+        assert got == [int(v) for v in t[c][t[c] >= 0]], c
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_host_merge_reproduces_reference_mesh(name):
+    from sgnn_b200 import mesh
+    g = np.load(os.path.join(GOLDEN, 'mc_ref.npz'))
+    soup = mcubes.triangle_soup(g['case_%s_tsdf' % name])
+    v, f = mesh.merge_triangles(soup)
+    V, F = g['case_%s_verts' % name], g['case_%s_faces' % name]
+    assert v.shape == V.shape and np.array_equal(v.view(np.uint32), V.view(np.uint32))
+    assert f.shape == F.shape and np.array_equal(f, F)
+
+
+def test_host_merge_empty_and_degenerate():
+    from sgnn_b200 import mesh
+    v, f = mesh.merge_triangles(np.zeros((0, 3, 3), dtype=np.float32))
+    assert v.shape == (0, 3) and f.shape == (0, 3)
+    tri = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]],          # kept
+                    [[0, 0, 0], [0, 0, 0], [1, 0, 0]],          # degenerate after the merge
+                    [[0, 1, 0], [0, 0, 0], [1, 0, 0]]],         # same vertex set as the first: duplicate
+                   dtype=np.float32)
+    v, f = mesh.merge_triangles(tri)
+    assert v.shape == (3, 3) and f.tolist() == [[0, 1, 2]]
+
+
+_EXPERIMENTAL = pytest.mark.skipif(not os.environ.get('SGNN_EXPERIMENTAL'),
+                                   reason='kernels written without GPU access; set SGNN_EXPERIMENTAL=1 to run them')
+
+
+@pytest.mark.gpu
+@_EXPERIMENTAL
+@pytest.mark.parametrize('name', CASES)
+def test_gpu_triangle_soup_and_mesh_equal_reference(name):
+    from sgnn_b200 import mesh
+    g = np.load(os.path.join(GOLDEN, 'mc_ref.npz'))
+    tsdf = torch.from_numpy(g['case_%s_tsdf' % name]).cuda()
+    soup = mesh.triangle_soup(tsdf).cpu().numpy()
+    want = mcubes.triangle_soup(g['case_%s_tsdf' % name])
+    assert soup.shape == want.shape and np.array_equal(soup.view(np.uint32), want.view(np.uint32))
+    v, c, f = mesh.run_marching_cubes(tsdf)
+    V, F = g['case_%s_verts' % name], g['case_%s_faces' % name]
+    assert np.array_equal(v.numpy().view(np.uint32), V.view(np.uint32)) and np.array_equal(f.numpy(), F)
+    assert c.shape == (V.shape[0], 3) and int(c.min()) == 220
+
+
+@pytest.mark.gpu
+@_EXPERIMENTAL
+def test_gpu_marching_cubes_scene_sized_volume_vs_oracle():
+    from sgnn_b200 import mesh
+    rng = np.random.default_rng(5)
+    n = rng.standard_normal((64, 96, 80))
+    for ax in range(3):
+        for _ in range(3):
+            n = (np.roll(n, 1, ax) + n + np.roll(n, -1, ax)) / 3
+    d = (3.4 * n / np.abs(n).max()).astype(np.float32)
+    d[rng.random(d.shape) < 0.01] = -np.inf
+    v, c, f = mesh.run_marching_cubes(torch.from_numpy(d).cuda())
+    V, F = mcubes.marching_cubes(d)
+    assert np.array_equal(v.numpy().view(np.uint32), V.view(np.uint32)) and np.array_equal(f.numpy(), F)
