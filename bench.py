@@ -387,6 +387,9 @@ def run_b200(args):
                   % round(convs_per_step),
         'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
         'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
+        # the per-layer ledger the totals come from: [op, n_in, n_out, cin, cout, K, R, bytes, flops] per launch
+        'ledger_set0': [[r['op'], r['n_in'], r['n_out'], r['cin'], r['cout'], r['K'], r['R'], r['bytes'], r['flops']]
+                        for r in ledger],
         'algorithmic_bytes_per_launch': per_set_bytes / max(convs_per_step, 1),
         'avg_launch_us': 1e3 * conv_ms / n_conv,
         'share_of_step': conv_ms / prof_ms if prof_ms > 0 else None,
