@@ -6,6 +6,9 @@
   configs[2]  one 128^3 block @3 % (and a 32-block batch for stable timing), bf16 features, C=16
               Convolution(k2,s2) + Deconvolution(k2,s2) on the tcgen05 path
   ffma        sustained 3-register FFMA rate (roofline denominator of the fp32 convolution)
+  tc32        one 16->16 3^3 submanifold convolution and one child-mode 48->16 convolution on a surface-like site set
+              (32 blocks of 64^3, a 3-voxel shell, rows in Morton order like the generator's hierarchical order), every
+              kernel generation: the A/B tool behind DESIGN.md section 5 (hooks 0/23/24/27, 28 with SGNN_EXPERIMENTAL=1)
 
 The headline metric lives in bench.py; this file feeds DESIGN.md §5 and the ncu captures under profiles/.
 """
@@ -90,6 +93,9 @@ def main():
                           'hbm_peak_GBps': hbm}))
         del state, coords
 
+    if args.which in ('all', 'tc32'):
+        bench_tc32(args, E, lib, dev, flush, hbm)
+
     if args.which in ('all', 'config2'):
         for nblk in (1, 32):
             g = torch.Generator(device=dev).manual_seed(1234)
@@ -119,6 +125,62 @@ def main():
                               'deconv_frac_of_hbm': b_dec / (t_dec * 1e-3) / 1e9 / hbm,
                               'conv_tflops': 2.0 * n * 256 / (t_conv * 1e-3) / 1e12,
                               'ms_conv_fp32_ffma_same_geometry': t_f32, 'hbm_peak_GBps': hbm}))
+
+
+def morton_order(c):
+    """Permutation that sorts int32 coords [n,4] (z,y,x,b) by (b, Morton(z,y,x)) -- the generator emits rows parent by parent,
+    8 z-major children each, recursively from the coarse grid, i.e. in this order."""
+    key = c[:, 3].long() << 18
+    for bit in range(6):
+        for ax, sh in ((0, 2), (1, 1), (2, 0)):
+            key |= ((c[:, ax].long() >> bit) & 1) << (3 * bit + sh)
+    return torch.argsort(key)
+
+
+def bench_tc32(args, E, lib, dev, flush, hbm):
+    nb = 32
+    zz, yy, xx = torch.meshgrid(torch.arange(64, device=dev), torch.arange(64, device=dev), torch.arange(64, device=dev),
+                                indexing='ij')
+    cs = []
+    g = torch.Generator(device=dev).manual_seed(7)
+    for b in range(nb):
+        ctr = 20 + 24 * torch.rand(3, device=dev, generator=g)
+        rad = 14 + 8 * torch.rand(1, device=dev, generator=g)
+        d = torch.sqrt((zz - ctr[0]) ** 2 + (yy - ctr[1]) ** 2 + (xx - ctr[2]) ** 2) - rad
+        m = d.abs() < 1.5
+        c = torch.nonzero(m)
+        cs.append(torch.cat([c, torch.full((c.shape[0], 1), b, device=dev)], 1))
+    coords = torch.cat(cs).int().contiguous()
+    coords = coords[morton_order(coords)].contiguous()
+    n = coords.shape[0]
+    grid = E.build_grid(coords, nb, (64, 64, 64))
+    nbr = E.rulebook_submanifold(grid)
+    rules = int((nbr >= 0).sum().item())
+    x = torch.randn((n, 16), device=dev)
+    w = torch.randn((27, 16, 16), device=dev) * 0.1
+    out = torch.empty((n, 16), device=dev)
+    res = {'bench': 'tc32 kernel generations', 'rows': n, 'rules_per_row': rules / n}
+    alg = (2 * n * 16) * 4 + 8 * rules + 27 * 256 * 4
+    res['ms_regular_ffma_exact'] = timed(lambda: E.conv(x, nbr, w, n, out), args.reps, flush)
+    hooks = [(0, 'v2_single_role'), (23, 'warp_specialised'), (24, 'tmem_operand'), (27, 'presplit_planes')]
+    if os.environ.get('SGNN_EXPERIMENTAL'):
+        hooks.append((28, 'unique_rows_experimental'))
+    for impl, name in hooks:
+        lib.sgnn_debug_set_conv_impl(impl)
+        res['ms_regular_' + name] = timed(lambda: E.conv(x, nbr, w, n, out, tc32=True), args.reps, flush)
+    lib.sgnn_debug_set_conv_impl(0)
+    res['regular_best_GBps_algorithmic'] = alg / (min(v for k, v in res.items() if k.startswith('ms_regular')) * 1e-3) / 1e9
+    # child mode: the same sites as parents, 48 -> 16 on their 8 children
+    x48 = torch.randn((n, 48), device=dev)
+    w48 = torch.randn((27, 48, 16), device=dev) * 0.05
+    outc = torch.empty((8 * n, 16), device=dev)
+    res['ms_child_ffma_exact'] = timed(lambda: E.conv(x48, nbr, w48, 8 * n, outc, child_mode=True), args.reps, flush)
+    for impl, name in ((0, 'warp_specialised'), (25, 'single_role')):
+        lib.sgnn_debug_set_conv_impl(impl)
+        res['ms_child_' + name] = timed(lambda: E.conv(x48, nbr, w48, 8 * n, outc, child_mode=True, tc32=True), args.reps, flush)
+    lib.sgnn_debug_set_conv_impl(0)
+    res['hbm_peak_GBps'] = hbm
+    print(json.dumps(res))
 
 
 if __name__ == '__main__':
