@@ -12,102 +12,25 @@
 // FMAs.  The first-come vertex merge is inherently sequential and order defining; it stays on the host
 // (sgnn_mc_merge_host, O(vertices), an open-addressing hash grid).
 //
+// The per-cell arithmetic lives in mc_core.h (shared with the CPU test harness).
 // Conventions (restated from the reference): corner pXYZ = cell + (+-0.5 x, +-0.5 y, +-0.5 z); cube-index bit order
 // p010 p110 p100 p000 p011 p111 p101 p001; edge e joins corners kEdge[e][0] -> kEdge[e][1] (interpolation order).
 #include <math.h>
 #include <string.h>
 #include <vector>
 #include "common.cuh"
-#include "mc_table.h"
+#include "mc_core.h"
 
 namespace {
 
-__constant__ unsigned long long c_mc_tri[256] = {SGNN_MC_TABLE};
 const unsigned long long h_mc_tri[256] = {SGNN_MC_TABLE};
-
-__constant__ int c_corner[8][3] = {{0, 1, 0}, {1, 1, 0}, {1, 0, 0}, {0, 0, 0}, {0, 1, 1}, {1, 1, 1}, {1, 0, 1}, {0, 0, 1}};
-__constant__ int c_edge[12][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}, {4, 5}, {5, 6}, {6, 7}, {7, 4}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
-
-struct McArgs {
-  const float* tsdf; int n0, n1, n2;
-  float iso, trunc, thresh;
-};
-
-// get_voxel (:72-105): value, and whether it is observed and inside the truncation band
-__device__ __forceinline__ bool mc_voxel(const McArgs& a, int x, int y, int z, float* v) {
-  if (z < 0 || z >= a.n0 || y < 0 || y >= a.n1 || x < 0 || x >= a.n2) return false;
-  const float d = __ldg(a.tsdf + ((size_t)z * a.n1 + y) * a.n2 + x);
-  *v = d;
-  return d != -INFINITY && fabsf(d) < a.trunc;
-}
-
-// trilerp (:107-131) at the corner (sx,sy,sz) of cell (x,y,z): the 2x2x2 voxels starting at (x-1+sx, ...), weights
-// 0.5*0.5*0.5 each, accumulated in the reference's order 000,100,010,001,110,011,101,111 (x,y,z offsets)
-__device__ __forceinline__ bool mc_corner(const McArgs& a, int x, int y, int z, int sx, int sy, int sz, float* out) {
-  const int bx = x - 1 + sx, by = y - 1 + sy, bz = z - 1 + sz;
-  const int off[8][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {0, 1, 1}, {1, 0, 1}, {1, 1, 1}};
-  float dist = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float v;
-    if (!mc_voxel(a, bx + off[i][0], by + off[i][1], bz + off[i][2], &v)) return false;
-    dist = __fadd_rn(dist, __fmul_rn(0.125f, v));
-  }
-  *out = dist;
-  return true;
-}
-
-// corner values + cube index of a cell; false = the reference emits nothing for it
-__device__ __forceinline__ bool mc_cell(const McArgs& a, int x, int y, int z, float (&dc)[8], unsigned* cube) {
-#pragma unroll
-  for (int c = 0; c < 8; ++c)
-    if (!mc_corner(a, x, y, z, c_corner[c][0], c_corner[c][1], c_corner[c][2], &dc[c])) return false;
-  unsigned idx = 0;
-#pragma unroll
-  for (int c = 0; c < 8; ++c)
-    if (dc[c] < a.iso) idx |= 1u << c;
-  for (int k = 0; k < 8; ++k)
-    for (int l = 0; l < 8; ++l) {
-      if (__fmul_rn(dc[k], dc[l]) < 0.0f) {
-        if (__fadd_rn(fabsf(dc[k]), fabsf(dc[l])) > a.thresh) return false;
-      } else {
-        if (fabsf(__fsub_rn(dc[k], dc[l])) > a.thresh) return false;
-      }
-    }
-#pragma unroll
-  for (int c = 0; c < 8; ++c)
-    if (fabsf(dc[c]) > a.thresh) return false;
-  *cube = idx;
-  return true;
-}
-
-__device__ __forceinline__ int mc_tri_vertices(unsigned long long w) {   // nibbles before the 0xF terminator
-  int n = 0;
-  while (n < 16 && ((w >> (4 * n)) & 0xF) != 0xF) ++n;
-  return n;
-}
 
 __global__ void mc_count_kernel(McArgs a, int* __restrict__ counts) {
   const long long total = (long long)a.n0 * a.n1 * a.n2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % a.n2), y = (int)((i / a.n2) % a.n1), z = (int)(i / ((long long)a.n1 * a.n2));
-    float dc[8];
-    unsigned cube;
-    int n = 0;
-    if (mc_cell(a, x, y, z, dc, &cube)) n = mc_tri_vertices(c_mc_tri[cube]) / 3;
-    counts[i] = n;
+    counts[i] = mc_cell_count(a, x, y, z);
   }
-}
-
-// vertexInterp (:133-154), operand order kept, no contraction
-__device__ __forceinline__ void mc_interp(float iso, const float (&p1)[3], const float (&p2)[3], float d1, float d2,
-                                          float* out) {
-  if (fabsf(__fsub_rn(iso, d1)) < 0.00001f) { out[0] = p1[0]; out[1] = p1[1]; out[2] = p1[2]; return; }
-  if (fabsf(__fsub_rn(iso, d2)) < 0.00001f) { out[0] = p2[0]; out[1] = p2[1]; out[2] = p2[2]; return; }
-  if (fabsf(__fsub_rn(d1, d2)) < 0.00001f) { out[0] = p1[0]; out[1] = p1[1]; out[2] = p1[2]; return; }
-  const float mu = __fdiv_rn(__fsub_rn(iso, d1), __fsub_rn(d2, d1));
-#pragma unroll
-  for (int i = 0; i < 3; ++i) out[i] = __fadd_rn(p1[i], __fmul_rn(mu, __fsub_rn(p2[i], p1[i])));
 }
 
 __global__ void mc_emit_kernel(McArgs a, const int* __restrict__ offs, float* __restrict__ tris) {
@@ -116,21 +39,7 @@ __global__ void mc_emit_kernel(McArgs a, const int* __restrict__ offs, float* __
     const int first = offs[i], n_tri = offs[i + 1] - first;
     if (n_tri == 0) continue;
     const int x = (int)(i % a.n2), y = (int)((i / a.n2) % a.n1), z = (int)(i / ((long long)a.n1 * a.n2));
-    float dc[8];
-    unsigned cube;
-    if (!mc_cell(a, x, y, z, dc, &cube)) continue;   // cannot happen: the count kernel saw the same cell
-    const unsigned long long w = c_mc_tri[cube];
-    float* dst = tris + (size_t)first * 9;
-    for (int v = 0; v < 3 * n_tri; ++v) {
-      const int e = (int)((w >> (4 * v)) & 0xF);
-      const int ca = c_edge[e][0], cb = c_edge[e][1];
-      float p1[3], p2[3];
-      p1[0] = (float)x + (c_corner[ca][0] ? 0.5f : -0.5f); p1[1] = (float)y + (c_corner[ca][1] ? 0.5f : -0.5f);
-      p1[2] = (float)z + (c_corner[ca][2] ? 0.5f : -0.5f);
-      p2[0] = (float)x + (c_corner[cb][0] ? 0.5f : -0.5f); p2[1] = (float)y + (c_corner[cb][1] ? 0.5f : -0.5f);
-      p2[2] = (float)z + (c_corner[cb][2] ? 0.5f : -0.5f);
-      mc_interp(a.iso, p1, p2, dc[ca], dc[cb], dst + 3 * v);
-    }
+    mc_cell_emit(a, x, y, z, n_tri, tris + (size_t)first * 9);
   }
 }
 
