@@ -6,6 +6,8 @@
   configs[2]  one 128^3 block @3 % (and a 32-block batch for stable timing), bf16 features, C=16
               Convolution(k2,s2) + Deconvolution(k2,s2) on the tcgen05 path
   ffma        sustained 3-register FFMA rate (roofline denominator of the fp32 convolution)
+  mesh        SURVEY 8(f4): marching cubes on a scene-sized dense TSDF (96 x 320 x 256): triangle-soup kernels + host merge,
+              next to the REAL reference's run_marching_cubes (oracle/_ref, compiled from its own source) on the host cores
   tc32        one 16->16 3^3 submanifold convolution and one child-mode 48->16 convolution on a surface-like site set
               (32 blocks of 64^3, a 3-voxel shell, rows in Morton order like the generator's hierarchical order), every
               kernel generation: the A/B tool behind DESIGN.md section 5 (hooks 0/23/24/27, 28 with SGNN_EXPERIMENTAL=1)
@@ -93,6 +95,9 @@ def main():
                           'hbm_peak_GBps': hbm}))
         del state, coords
 
+    if args.which in ('all', 'mesh'):
+        bench_mesh(args, dev, flush)
+
     if args.which in ('all', 'tc32'):
         bench_tc32(args, E, lib, dev, flush, hbm)
 
@@ -125,6 +130,47 @@ def main():
                               'deconv_frac_of_hbm': b_dec / (t_dec * 1e-3) / 1e9 / hbm,
                               'conv_tflops': 2.0 * n * 256 / (t_conv * 1e-3) / 1e12,
                               'ms_conv_fp32_ffma_same_geometry': t_f32, 'hbm_peak_GBps': hbm}))
+
+
+def bench_mesh(args, dev, flush):
+    import time
+    import numpy as np
+    from sgnn_b200 import mesh
+    rng = np.random.default_rng(3)
+    n = rng.standard_normal((96, 320, 256)).astype(np.float32)
+    for ax in range(3):
+        for _ in range(4):
+            n = (np.roll(n, 1, ax) + n + np.roll(n, -1, ax)) / 3
+    d = (3.4 * n / np.abs(n).max()).astype(np.float32)
+    d[rng.random(d.shape) < 0.01] = -np.inf
+    t = torch.from_numpy(d).to(dev)
+    state = {}
+
+    def soup():
+        state['tris'] = mesh.triangle_soup(t)
+    ms_soup = timed(soup, args.reps, flush)
+    host = state['tris'].cpu()
+    t0 = time.perf_counter()
+    v, f = mesh.merge_triangles(host)
+    ms_merge = 1e3 * (time.perf_counter() - t0)
+    res = {'bench': 'mesh (marching cubes) 96x320x256', 'cells': int(d.size), 'triangles': int(host.shape[0]),
+           'vertices': int(v.shape[0]), 'faces': int(f.shape[0]), 'ms_triangle_soup_gpu': ms_soup,
+           'ms_vertex_merge_host': ms_merge, 'cells_per_s_gpu_soup': d.size / (ms_soup * 1e-3)}
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    try:
+        import build_ref
+        mc = build_ref.load_marching_cubes()
+    except Exception:
+        mc = None
+    if mc is not None:                                          # the reference itself, one host core, same volume
+        col = torch.ones(d.shape + (3,), dtype=torch.uint8) * 220
+        t0 = time.perf_counter()
+        rv, _, rf = mc.run_marching_cubes(torch.from_numpy(d), col, 0.0, 3.0, 10.0)
+        res['ms_reference_cpu_total'] = 1e3 * (time.perf_counter() - t0)
+        res['equal_to_reference'] = bool(rv.shape[0] == v.shape[0] and rf.shape[0] == f.shape[0] and
+                                         np.array_equal(rv.numpy().view(np.uint32), v.view(np.uint32)) and
+                                         np.array_equal(rf.numpy(), f))
+    print(json.dumps(res))
 
 
 def morton_order(c):
