@@ -63,6 +63,22 @@ def run_marching_cubes(tsdf, colors=None, isovalue=0.0, truncation=3.0, thresh=1
     return v, torch.full((v.shape[0], 3), 220, dtype=torch.uint8), torch.from_numpy(faces)
 
 
+def sparse_sdf_to_mesh(locs, sdf, dims_zyx, truncation=3.0, thresh=10.0, output_filename=None):
+    """The mesh of a sparse TSDF prediction, as data_util.save_predictions does it (data_util.py:278-281): scatter the
+    values into a dense grid filled with -inf (sparse_to_dense_np, :43-54), marching cubes at isovalue 0 with
+    truncation - 0.1.  locs [N,>=3] (z,y,x[,b]) and sdf [N] / [N,1] are the generator's outputs (CUDA tensors)."""
+    if not sdf.is_cuda:
+        raise RuntimeError('sgnn_b200.mesh: the prediction must be CUDA tensors (no CPU fallback)')
+    d0, d1, d2 = (int(v) for v in dims_zyx)
+    dense = torch.full((d0, d1, d2), float('-inf'), dtype=torch.float32, device=sdf.device)
+    li = locs.to(sdf.device).long()
+    dense[li[:, 0], li[:, 1], li[:, 2]] = sdf.reshape(-1).float()
+    v, c, f = run_marching_cubes(dense, None, 0.0, truncation - 0.1, thresh)
+    if output_filename is not None:
+        save_mesh(v.numpy(), c.numpy(), f.numpy(), output_filename)
+    return v, c, f
+
+
 def save_mesh(verts, colors, faces, output_file):
     """ASCII .ply / .obj writer (marching_cubes.py:9-26 writes .obj with vertex colours, .ply via plyfile)."""
     verts, colors, faces = np.asarray(verts), np.asarray(colors), np.asarray(faces)

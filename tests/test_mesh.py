@@ -135,3 +135,27 @@ def test_gpu_marching_cubes_scene_sized_volume_vs_oracle():
     v, c, f = mesh.run_marching_cubes(torch.from_numpy(d).cuda())
     V, F = mcubes.marching_cubes(d)
     assert np.array_equal(v.numpy().view(np.uint32), V.view(np.uint32)) and np.array_equal(f.numpy(), F)
+
+
+@pytest.mark.gpu
+def test_gpu_sparse_prediction_to_mesh_like_save_predictions(tmp_path):
+    """data_util.save_predictions:278-281 on a synthetic sparse prediction: -inf fill, truncation - 0.1, .ply written."""
+    from sgnn_b200 import mesh
+    rng = np.random.default_rng(2)
+    dims = (24, 32, 28)
+    z, y, x = np.mgrid[0:dims[0], 0:dims[1], 0:dims[2]].astype(np.float32)
+    d = np.sqrt((x - 13.2) ** 2 + (y - 15.1) ** 2 + (z - 11.7) ** 2) - 8.4
+    keep = np.abs(d) < 3.0
+    locs = np.argwhere(keep)
+    vals = d[keep].astype(np.float32)
+    perm = rng.permutation(locs.shape[0])                       # the generator's rows are not in raster order
+    locs, vals = locs[perm], vals[perm]
+    out = str(tmp_path / 'pred-mesh.ply')
+    v, c, f = mesh.sparse_sdf_to_mesh(torch.from_numpy(locs).cuda(), torch.from_numpy(vals).cuda().view(-1, 1), dims,
+                                      truncation=3.0, output_filename=out)
+    dense = np.full(dims, -np.inf, dtype=np.float32)
+    dense[locs[:, 0], locs[:, 1], locs[:, 2]] = vals
+    V, F = mcubes.marching_cubes(dense, 0.0, 2.9, 10.0)
+    assert np.array_equal(v.numpy().view(np.uint32), V.view(np.uint32)) and np.array_equal(f.numpy(), F)
+    head = open(out).read(200)
+    assert head.startswith('ply') and 'element vertex %d' % V.shape[0] in head
