@@ -57,6 +57,21 @@ def test_host_merge_empty_and_degenerate():
     assert v.shape == (3, 3) and f.tolist() == [[0, 1, 2]]
 
 
+def test_mesh_writers_round_trip(tmp_path):
+    """.obj with vertex colours as marching_cubes.py:9-18 writes it, .ply with the same elements plyfile would write."""
+    from sgnn_b200 import mesh
+    v = np.array([[0, 0, 0], [1.5, 0, 0.25], [0, 2, 0]], dtype=np.float32)
+    c = np.full((3, 3), 220, dtype=np.uint8)
+    f = np.array([[0, 1, 2]], dtype=np.int32)
+    obj, ply = str(tmp_path / 'm.obj'), str(tmp_path / 'm.ply')
+    mesh.save_mesh(v, c, f, obj)
+    mesh.save_mesh(v, c, f, ply)
+    lines = open(obj).read().split('\n')
+    assert lines[1] == 'v 1.500000 0.000000 0.250000 220 220 220' and 'f 1 2 3' in lines
+    body = open(ply).read().split('end_header\n')[1].split('\n')
+    assert body[1].split()[:3] == ['1.500000', '0.000000', '0.250000'] and body[3] == '3 0 1 2'
+
+
 def _host_harness():
     """The kernels' per-cell code (csrc/mc_core.h) compiled for the host -- test infrastructure, see mc_host_harness.cpp."""
     import subprocess
