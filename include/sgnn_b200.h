@@ -158,6 +158,22 @@ size_t sgnn_conv_tc32_workspace_bytes(int32_t K, int32_t cin, int32_t child_mode
 size_t sgnn_conv_tc32_workspace_bytes_rows(int32_t K, int32_t cin, int32_t child_mode, int64_t n_in);
 int sgnn_conv_forward_tc32(const SgnnConvArgs* args, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- a2 + a3, unique-row form (csrc/conv_ur.cu).  A TILE PLAN re-expresses the submanifold rulebook of a site set per
+ * 128-row tile: the sorted list of DISTINCT input rows the tile's 27 filter offsets touch and a 27 x 128 table of 16-bit
+ * indices into that list (0xFFFF = absent) -- scn's per-offset (in,out) pair lists (upstream
+ * Metadata::getSubmanifoldRuleBook) regrouped so that a convolution stages every input row of a tile ONCE.  Built once per
+ * site set from its neighbour table, shared by every SubmanifoldConvolution on that set (model.py:38,40,179,186,254 ...).
+ * plan: dev, 256-byte aligned, sgnn_tile_plan_bytes(n_rows) bytes, opaque. */
+size_t sgnn_tile_plan_bytes(int64_t n_rows);
+int sgnn_tile_plan_build(const int32_t* nbr, int64_t nbr_stride, int64_t n_rows, void* plan, size_t plan_bytes,
+                         void* stream);
+/* sgnn_conv_forward_tc32 for K = 27, Cin <= 32, Cout = 16 with a tile plan of args->nbr: the distinct rows of a tile are
+ * fetched by TMA (cp.async.bulk, one per row) into shared memory, split into the bf16 planes once, and expanded filter
+ * offset by filter offset from shared memory into tensor memory for tcgen05.mma.  Same arithmetic and tolerance as
+ * sgnn_conv_forward_tc32; `workspace` as there (sgnn_conv_tc32_workspace_bytes(27, cin, 0)). */
+int sgnn_conv_forward_tc32_ur(const SgnnConvArgs* args, const void* plan, void* workspace, size_t workspace_bytes,
+                              void* stream);
+
 /* ---- scn.Deconvolution(3,Cin,Cout,2,2) (north_star operator surface; upstream Deconvolution_updateOutput)
  *   out[i] = in[parent[i] >> 3] @ W[parent[i] & 7]          (rows with parent < 0 get zeros) */
 int sgnn_deconv_forward(const void* in, int32_t ld_in, int32_t dtype, const int32_t* parent,
@@ -345,6 +361,9 @@ void sgnn_debug_set_conv_impl(int impl);
 
 /* Tuning hook: under SGNN_GEN_TC32 only convolutions with at least n output rows use the tensor-core path (default 60000). */
 void sgnn_debug_set_tc32_min_rows(int64_t n);
+/* Tuning hook: under SGNN_GEN_TC32 site sets with at least n rows get a tile plan and run their K = 27, Cout = 16
+ * convolutions through sgnn_conv_forward_tc32_ur (default 20000). */
+void sgnn_debug_set_ur_min_rows(int64_t n);
 
 /* Measures the sustained 3-register FFMA rate of the device (TFLOP/s): roofline denominator of the fp32 kernels. */
 int sgnn_debug_ffma_peak(int iters, double* tflops, void* stream);

@@ -102,6 +102,9 @@ SIGNATURES = {
     'sgnn_conv_tc32_workspace_bytes': (_Z, [_I, _I, _I]),
     'sgnn_conv_tc32_workspace_bytes_rows': (_Z, [_I, _I, _I, _L]),
     'sgnn_conv_forward_tc32': (_I, [C.POINTER(SgnnConvArgs), _P, _Z, _P]),
+    'sgnn_tile_plan_bytes': (_Z, [_L]),
+    'sgnn_tile_plan_build': (_I, [_P, _L, _L, _P, _Z, _P]),
+    'sgnn_conv_forward_tc32_ur': (_I, [C.POINTER(SgnnConvArgs), _P, _P, _Z, _P]),
     'sgnn_deconv_forward': (_I, [_P, _I, _I, _P, _P, _I, _I, _L, _E, _P]),
     'sgnn_unpool': (_I, [_P, _I, _P, _I, _L, _E, _P]),
     'sgnn_affine_relu': (_I, [_P, _I, _P, _I, _L, _I, _P, _P, _I, _P]),
@@ -130,6 +133,7 @@ SIGNATURES = {
     'sgnn_coords_to_i64': (_I, [_P, _L, _P, _P]),
     'sgnn_debug_set_conv_impl': (None, [_I]),
     'sgnn_debug_set_tc32_min_rows': (None, [_L]),
+    'sgnn_debug_set_ur_min_rows': (None, [_L]),
     'sgnn_debug_ffma_peak': (_I, [_I, C.POINTER(C.c_double), _P]),
     'sgnn_launch_count': (_L, []),
     'sgnn_version': (_I, []),

@@ -1,0 +1,537 @@
+// conv_ur.cu -- submanifold 3^3 convolution on tcgen05 with every DISTINCT input row of a tile staged once by TMA.
+// SURVEY §8 rows a2 / a3 (reference torch/model.py:32,38,40,179,186,254 and the FullyConvolutionalNet blocks);
+// the north_star's "TMA staging of the filter bank and per-offset input slices into shared memory".
+//
+// Why.  ncu on the round-1 kernels (profiles/r01_conv_tc32_*): every tensor-core generation moved 27 x 64..96 B per
+// output row from L2 in ~300 us -- the L2->SM gather was the common wall, and with the generator's row order a 128-row
+// tile touches only ~1.6 distinct input rows per output row (scratch/tile_stats.py: median 203, max 302 per tile).
+//
+// Two kernels.
+//  (1) tile_plan_kernel, once per site set (rulebook time): for every 128-row tile the sorted list of distinct input
+//      rows its 27 filter offsets touch (`urows`, by a shared-memory BITMAP over the tile's row-id span + popcount
+//      ranks -- no hash, no sort) and the 27 x 128 table of 16-bit LOCAL indices into that list (`lidx`, 0xFFFF =
+//      absent).  54 B of index per row instead of the 108 B of the k-major neighbour table, and consecutive output
+//      rows get consecutive local indices (conflict-free shared-memory reads).
+//  (2) conv_ur_kernel, one persistent CTA per SM, 14 warps in four roles:
+//        loader   (warp 13)   TMA: the prepared filter bank (one cp.async.bulk), the tile's lidx block (one bulk copy)
+//                             and its distinct input rows (one 64/128-byte cp.async.bulk per row) into a ring of
+//                             64-row chunks -- mbarrier complete_tx, no registers, runs up to a whole tile ahead;
+//        producers (warps 0-7) cut each landed row ONCE into the three bf16 planes (shared memory, chunk-major so that
+//                             consecutive rows are consecutive 16-byte units), then, tap by tap, thread r moves row
+//                             lidx[k][r]'s 96 x Q bytes shared memory -> TENSOR MEMORY (6Q LDS.128 + 3Q tcgen05.st);
+//                             absent taps read a zero row (no predicates); the two warp groups take alternate taps;
+//        MMA      (warp 12)   6Q tcgen05.mma (A in TMEM, B = resident filter bank) per tap into 7 main + 1 correction
+//                             accumulators (tc32_common.cuh), double-buffered accumulators (2 x 128 TMEM columns);
+//        epilogue (warps 8-11) tcgen05.ld, round-to-nearest sum of the partial accumulators, residual, two affine+ReLU
+//                             slots -- overlaps the next tile's taps.
+//      A tile with more distinct rows than the staging area takes several passes over the taps (same accumulators);
+//      a tile the plan could not describe (row-id span or distinct count over its caps) runs in DIRECT mode (rows
+//      gathered from global memory per tap, split in registers) -- correct for any input, never seen in the generator.
+// Arithmetic and MMA order are those of conv_tc32_kernel (exact 3-way bf16 split, tc32_common.cuh).
+#include "tc32_common.cuh"
+
+#define UR_PLAN_CAP 512          // distinct rows per tile the plan can list
+#define UR_BM_WORDS 4096         // bitmap words of the plan kernel: row-id span <= 131072 per tile
+#define UR_LIDX_BYTES (27 * 128 * 2)
+#define UR_CHUNK 64              // rows per ring chunk
+
+namespace {
+
+struct PlanView {
+  const int* ucount;             // [tiles]  distinct rows, or -1: direct mode
+  const int* urows;              // [tiles][UR_PLAN_CAP]
+  const unsigned short* lidx;    // [tiles][27][128]
+};
+
+size_t plan_align(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+tile_plan_kernel(const int* __restrict__ nbr, long long nbr_stride, long long n_rows, long long n_tiles,
+                 int* __restrict__ ucount, int* __restrict__ urows, unsigned short* __restrict__ lidx) {
+  __shared__ unsigned bm[UR_BM_WORDS];
+  __shared__ int pre[UR_BM_WORDS];
+  __shared__ int red_min[4], red_max[4], warp_sum[4];
+  __shared__ int s_min, s_max;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long j = tile * 128 + tid;
+    int idx[27];
+    int mn = 0x7fffffff, mx = -1;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      idx[k] = j < n_rows ? __ldg(nbr + (long long)k * nbr_stride + j) : -1;
+      if (idx[k] >= 0) { mn = min(mn, idx[k]); mx = max(mx, idx[k]); }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { red_min[warp] = mn; red_max[warp] = mx; }
+    __syncthreads();
+    if (tid == 0) {
+      s_min = min(min(red_min[0], red_min[1]), min(red_min[2], red_min[3]));
+      s_max = max(max(red_max[0], red_max[1]), max(red_max[2], red_max[3]));
+    }
+    __syncthreads();
+    const int lo = s_min, hi = s_max;
+    unsigned short* my_lidx = lidx + tile * (27 * 128);
+    if (hi < 0) {                                   // no neighbour at all (cannot happen for rows < n_rows)
+      if (tid == 0) ucount[tile] = 0;
+#pragma unroll
+      for (int k = 0; k < 27; ++k) my_lidx[k * 128 + tid] = 0xffff;
+      __syncthreads();
+      continue;
+    }
+    const long long span = (long long)hi - lo + 1;
+    if (span > (long long)UR_BM_WORDS * 32) {       // direct mode
+      if (tid == 0) ucount[tile] = -1;
+      __syncthreads();
+      continue;
+    }
+    const int nw = (int)((span + 31) >> 5);
+    for (int w = tid; w < nw; w += 128) bm[w] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 27; ++k)
+      if (idx[k] >= 0) {
+        const int o = idx[k] - lo;
+        atomicOr(&bm[o >> 5], 1u << (o & 31));
+      }
+    __syncthreads();
+    // exclusive scan of the word popcounts: thread t owns words [t*per, (t+1)*per)
+    const int per = (nw + 127) >> 7;
+    int local = 0;
+    for (int i = 0; i < per; ++i) {
+      const int w = tid * per + i;
+      if (w < nw) local += __popc(bm[w]);
+    }
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    int base = incl - local;
+    for (int w = 0; w < warp; ++w) base += warp_sum[w];
+    const int total = warp_sum[0] + warp_sum[1] + warp_sum[2] + warp_sum[3];
+    for (int i = 0; i < per; ++i) {
+      const int w = tid * per + i;
+      if (w < nw) { pre[w] = base; base += __popc(bm[w]); }
+    }
+    __syncthreads();
+    if (total > UR_PLAN_CAP) {                      // direct mode
+      if (tid == 0) ucount[tile] = -1;
+      __syncthreads();
+      continue;
+    }
+    if (tid == 0) ucount[tile] = total;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      unsigned short l = 0xffff;
+      if (idx[k] >= 0) {
+        const int o = idx[k] - lo;
+        l = (unsigned short)(pre[o >> 5] + __popc(bm[o >> 5] & ((1u << (o & 31)) - 1u)));
+      }
+      my_lidx[k * 128 + tid] = l;
+    }
+    int* my_rows = urows + tile * UR_PLAN_CAP;
+    for (int w = tid; w < nw; w += 128) {
+      unsigned bits = bm[w];
+      int at = pre[w];
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        my_rows[at++] = lo + w * 32 + b;
+      }
+    }
+    __syncthreads();                                // bm / pre are rebuilt by the next tile
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+
+// TMA, non-tensor form: `bytes` (multiple of 16) global -> shared, completion on the mbarrier's transaction count
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, unsigned bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+
+template <int Q>
+struct UrCfg {
+  static constexpr int US = Q == 1 ? 512 : 320;          // distinct rows staged per pass
+  static constexpr int PL_BUFS = Q == 1 ? 2 : 1;         // plane buffers
+  static constexpr int NRING = Q == 1 ? 8 : 6;           // landing ring, chunks of UR_CHUNK rows
+  static constexpr int NST = Q == 1 ? 8 : 4;             // A stages in tensor memory
+  static constexpr int ST_COLS = 256 / NST;              // TMEM columns per A stage (24 Q used)
+  static constexpr int ROWB = 64 * Q;                    // bytes of a landed fp32 row
+  static constexpr int NARR = 6 * Q;                     // 16-byte plane arrays: [slice][plane][half]
+  static constexpr int ASTR = (((US + 1) * 16 + 127) / 128) * 128 + 64;   // array stride: odd multiple of 64 B
+  static constexpr int BANK = 27 * Q * 3 * T32_BBLK;
+  static constexpr int PLANES = PL_BUFS * NARR * ASTR;
+  static constexpr int RING = NRING * UR_CHUNK * ROWB;
+  static constexpr int SMEM = BANK + PLANES + RING + 2 * UR_LIDX_BYTES;
+};
+
+#define UR_THREADS 448
+
+template <int Q>
+__global__ void __launch_bounds__(UR_THREADS, 1)
+conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
+  using C = UrCfg<Q>;
+  extern __shared__ __align__(1024) unsigned char sm[];
+  unsigned char* bank = sm;                               // [27][Q][3][512]
+  unsigned char* planes = bank + C::BANK;                 // [PL_BUFS][NARR][ASTR]
+  unsigned char* ring = planes + C::PLANES;               // [NRING][UR_CHUNK][ROWB]
+  unsigned short* lidx_s = reinterpret_cast<unsigned short*>(ring + C::RING);   // [2][27][128]
+  __shared__ __align__(8) unsigned long long w_full, lidx_full[2], lidx_empty[2], ring_full[C::NRING], ring_empty[C::NRING],
+      full[C::NST], empty[C::NST], acc_full[2], acc_empty[2];
+  __shared__ unsigned tmem_ptr_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 32) {
+    mbar_init(&w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&lidx_full[i], 1);
+      mbar_init(&lidx_empty[i], 8);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    for (int i = 0; i < C::NRING; ++i) {
+      mbar_init(&ring_full[i], 1);
+      mbar_init(&ring_empty[i], 8);
+    }
+    for (int i = 0; i < C::NST; ++i) {
+      mbar_init(&full[i], 4);
+      mbar_init(&empty[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::);
+  }
+  // zero rows of every plane array (index US): what an absent tap reads
+  for (int i = tid; i < C::PL_BUFS * C::NARR; i += UR_THREADS)
+    *reinterpret_cast<uint4*>(planes + (size_t)i * C::ASTR + C::US * 16) = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::);
+  const unsigned tmem = tmem_ptr_s;
+
+  const long long my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  constexpr int n_main = 7;
+  // bytes of a row the loader may copy: the row may be shorter than the 16 Q channels the kernel works on
+  const unsigned row_bytes = (unsigned)(min(16 * Q, p.ld_in) * 4);
+
+  if (warp < 8) {
+    // ---------------------------------------------------------------------------------- producers
+    const int g = warp >> 2;                            // warp group: takes the items with (it & 1) == g
+    const int r = (warp & 3) * 32 + lane;               // output row inside the tile == TMEM lane
+    const int pt = tid;                                 // 0..255: piece index of the split
+    const unsigned lane_base = tmem + ((unsigned)((warp & 3) * 32) << 16);
+    long long it = 0, ring_it = 0, tp = 0;
+    for (long long tl = 0; tl < my_tiles; ++tl) {
+      const long long tile = blockIdx.x + tl * gridDim.x;
+      const int u = __ldg(plan.ucount + tile);
+      const int lb = (int)(tl & 1);
+      const bool direct = u < 0;
+      const int npass = direct ? 1 : max(1, (u + C::US - 1) / C::US);
+      mbar_wait(&lidx_full[lb], (unsigned)((tl >> 1) & 1));
+      const unsigned short* my_lidx = lidx_s + lb * (27 * 128) + r;
+      const long long j = tile * T32_M + r;
+      for (int pass = 0; pass < npass; ++pass) {
+        unsigned char* pl = planes + (C::PL_BUFS == 2 ? (size_t)(tp & 1) * C::NARR * C::ASTR : 0);
+        if (!direct) {
+          if (C::PL_BUFS == 1) bar_sync(2, 256);        // every producer has left the previous tap loop
+          const int rows_this = min(C::US, u - pass * C::US);
+          const int nch = (rows_this + UR_CHUNK - 1) / UR_CHUNK;
+          for (int c = 0; c < nch; ++c, ++ring_it) {
+            const int slot = (int)(ring_it % C::NRING);
+            mbar_wait(&ring_full[slot], (unsigned)((ring_it / C::NRING) & 1));
+            const unsigned char* src = ring + (size_t)slot * UR_CHUNK * C::ROWB;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+              const int piece = pt + 256 * q;           // [row in chunk][16-byte piece of the row]
+              const int rr = piece / (4 * Q), c4 = piece % (4 * Q);
+              float4 v = *reinterpret_cast<const float4*>(src + (size_t)piece * 16);
+              const int ch = 4 * c4;
+              if (ch + 0 >= p.cin) v.x = 0.f;
+              if (ch + 1 >= p.cin) v.y = 0.f;
+              if (ch + 2 >= p.cin) v.z = 0.f;
+              if (ch + 3 >= p.cin) v.w = 0.f;
+              uint2 h, m, l;
+              split2(v.x, v.y, h.x, m.x, l.x);
+              split2(v.z, v.w, h.y, m.y, l.y);
+              const int row = c * UR_CHUNK + rr;
+              if (row < rows_this) {
+                unsigned char* d = pl + (size_t)((c4 >> 2) * 6 + ((c4 >> 1) & 1)) * C::ASTR + row * 16 + (c4 & 1) * 8;
+                *reinterpret_cast<uint2*>(d) = h;
+                *reinterpret_cast<uint2*>(d + 2 * C::ASTR) = m;
+                *reinterpret_cast<uint2*>(d + 4 * C::ASTR) = l;
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ring_empty[slot]);
+          }
+          bar_sync(1, 256);                             // planes of this pass complete
+          ++tp;
+        }
+        const unsigned base = (unsigned)(pass * C::US);
+#pragma unroll 1
+        for (int k = 0; k < 27; ++k, ++it) {
+          if ((int)(it & 1) != g) continue;
+          const int s = (int)(it % C::NST);
+          const long long n = it / C::NST;
+          unsigned rg[Q][3][8];
+          if (!direct) {
+            const unsigned l = my_lidx[k * 128];
+            const unsigned lw = min(l - base, (unsigned)C::US);      // absent / other pass -> the zero row
+            const unsigned char* a = pl + lw * 16;
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+#pragma unroll
+              for (int x = 0; x < 3; ++x) {
+                const uint4 lo4 = *reinterpret_cast<const uint4*>(a + (size_t)(q * 6 + x * 2) * C::ASTR);
+                const uint4 hi4 = *reinterpret_cast<const uint4*>(a + (size_t)(q * 6 + x * 2 + 1) * C::ASTR);
+                rg[q][x][0] = lo4.x; rg[q][x][1] = lo4.y; rg[q][x][2] = lo4.z; rg[q][x][3] = lo4.w;
+                rg[q][x][4] = hi4.x; rg[q][x][5] = hi4.y; rg[q][x][6] = hi4.z; rg[q][x][7] = hi4.w;
+              }
+          } else {
+            const int idx = j < p.n_rows ? __ldg(p.nbr + (long long)k * p.nbr_stride + j) : -1;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+              float x0[8], x1[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { x0[e] = 0.f; x1[e] = 0.f; }
+              if (idx >= 0) {
+                const float* src = p.in + (long long)idx * p.ld_in;
+                load8<false>(src, 16 * q, p.cin, x0);
+                load8<false>(src, 16 * q + 8, p.cin, x1);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                split2(x0[2 * i], x0[2 * i + 1], rg[q][0][i], rg[q][1][i], rg[q][2][i]);
+                split2(x1[2 * i], x1[2 * i + 1], rg[q][0][4 + i], rg[q][1][4 + i], rg[q][2][4 + i]);
+              }
+            }
+          }
+          if (n > 0) mbar_wait(&empty[s], (unsigned)((n - 1) & 1));   // the MMAs that read this A stage have completed
+          asm volatile("tcgen05.fence::after_thread_sync;" ::);
+          const unsigned a_stage = lane_base + 256u + (unsigned)(s * C::ST_COLS);
+#pragma unroll
+          for (int q = 0; q < Q; ++q)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) tmem_st8(a_stage + (unsigned)(q * 24 + x * 8), rg[q][x]);
+          asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[s]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&lidx_empty[lb]);
+    }
+  } else if (warp < 12) {
+    // ---------------------------------------------------------------------------------- epilogue
+    const int qd = warp & 3;
+    const unsigned lane_base = tmem + ((unsigned)(qd * 32) << 16);
+    for (long long tl = 0; tl < my_tiles; ++tl) {
+      const int ab = (int)(tl & 1);
+      mbar_wait(&acc_full[ab], (unsigned)((tl >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::);
+      unsigned v[16], vc[16];
+      const unsigned acc = lane_base + (unsigned)(ab * T32_COLS);
+      tmem_ld16(acc + T32_CORR, v);
+      for (int a = n_main - 1; a >= 0; --a) {
+        tmem_ld16(acc + 16u * (unsigned)a, vc);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(vc[c]));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      const long long j = (blockIdx.x + tl * gridDim.x) * T32_M + qd * 32 + lane;
+      if (j < p.n_rows) epilogue_row16(p, v, j);
+    }
+  } else if (warp == 12) {
+    // ---------------------------------------------------------------------------------- MMA issuer
+    mbar_wait(&w_full, 0u);
+    long long it = 0;
+    for (long long tl = 0; tl < my_tiles; ++tl) {
+      const long long tile = blockIdx.x + tl * gridDim.x;
+      const int u = __ldg(plan.ucount + tile);
+      const int npass = u < 0 ? 1 : max(1, (u + C::US - 1) / C::US);
+      const int ab = (int)(tl & 1);
+      if (tl >= 2) mbar_wait(&acc_empty[ab], (unsigned)(((tl >> 1) - 1) & 1));   // epilogue of tile tl-2 drained
+      const unsigned acc = tmem + (unsigned)(ab * T32_COLS);
+      for (int pass = 0; pass < npass; ++pass)
+        for (int k = 0; k < 27; ++k, ++it) {
+          const int s = (int)(it % C::NST);
+          mbar_wait(&full[s], (unsigned)((it / C::NST) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::);
+          if (elect_one()) {
+            const unsigned a_stage = tmem + 256u + (unsigned)(s * C::ST_COLS);
+#pragma unroll
+            for (int qc = 0; qc < Q; ++qc) {
+              const unsigned a = a_stage + (unsigned)(qc * 24);                            // planes at +0, +8, +16 columns
+              const unsigned b = smem_u32(bank + (size_t)(k * Q + qc) * 3 * T32_BBLK);     // planes at +0, +512, +1024 bytes
+              const unsigned first_corr = (pass == 0 && k == 0 && qc == 0) ? 0u : 1u;
+              const unsigned first_main = (pass == 0 && (k & 3) == 0 && qc == 0) ? 0u : 1u;
+              mma_bf16_ts(acc + T32_CORR, a + 16u, umma_desc(b), first_corr);                    // x2 w0
+              mma_bf16_ts(acc + T32_CORR, a + 8u, umma_desc(b + T32_BBLK), 1u);                  // x1 w1
+              mma_bf16_ts(acc + T32_CORR, a, umma_desc(b + 2 * T32_BBLK), 1u);                   // x0 w2
+              mma_bf16_ts(acc + T32_CORR, a + 8u, umma_desc(b), 1u);                             // x1 w0
+              mma_bf16_ts(acc + T32_CORR, a, umma_desc(b + T32_BBLK), 1u);                       // x0 w1
+              mma_bf16_ts(acc + 16u * (unsigned)(k >> 2), a, umma_desc(b), first_main);          // x0 w0
+            }
+            mma_commit(&empty[s]);
+            if (pass == npass - 1 && k == 26) mma_commit(&acc_full[ab]);
+          }
+          __syncwarp();
+        }
+    }
+  } else {
+    // ---------------------------------------------------------------------------------- loader (TMA)
+    if (lane == 0) {
+      mbar_expect_tx(&w_full, (unsigned)C::BANK);
+      bulk_g2s(bank, p.wsplit, (unsigned)C::BANK, &w_full);
+    }
+    long long ring_it = 0;
+    for (long long tl = 0; tl < my_tiles; ++tl) {
+      const long long tile = blockIdx.x + tl * gridDim.x;
+      const int u = __ldg(plan.ucount + tile);
+      const int lb = (int)(tl & 1);
+      if (tl >= 2) mbar_wait(&lidx_empty[lb], (unsigned)(((tl >> 1) - 1) & 1));
+      if (lane == 0) {
+        mbar_expect_tx(&lidx_full[lb], (unsigned)UR_LIDX_BYTES);
+        bulk_g2s(lidx_s + lb * (27 * 128), plan.lidx + tile * (27 * 128), (unsigned)UR_LIDX_BYTES, &lidx_full[lb]);
+      }
+      if (u <= 0) continue;
+      const int* rows = plan.urows + tile * UR_PLAN_CAP;
+      const int npass = (u + C::US - 1) / C::US;
+      for (int pass = 0; pass < npass; ++pass) {
+        const int rows_this = min(C::US, u - pass * C::US);
+        const int nch = (rows_this + UR_CHUNK - 1) / UR_CHUNK;
+        for (int c = 0; c < nch; ++c, ++ring_it) {
+          const int slot = (int)(ring_it % C::NRING);
+          const int first = pass * C::US + c * UR_CHUNK;
+          const int cnt = min(UR_CHUNK, rows_this - c * UR_CHUNK);
+          const int id0 = lane < cnt ? __ldg(rows + first + lane) : -1;
+          const int id1 = lane + 32 < cnt ? __ldg(rows + first + lane + 32) : -1;
+          if (ring_it >= C::NRING) mbar_wait(&ring_empty[slot], (unsigned)((ring_it / C::NRING - 1) & 1));
+          if (lane == 0) mbar_expect_tx(&ring_full[slot], (unsigned)cnt * row_bytes);
+          __syncwarp();
+          unsigned char* dst = ring + (size_t)slot * UR_CHUNK * C::ROWB;
+          if (id0 >= 0) bulk_g2s(dst + (size_t)lane * C::ROWB, p.in + (long long)id0 * p.ld_in, row_bytes, &ring_full[slot]);
+          if (id1 >= 0) bulk_g2s(dst + (size_t)(lane + 32) * C::ROWB, p.in + (long long)id1 * p.ld_in, row_bytes, &ring_full[slot]);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+template <int Q>
+int launch_ur(const Tc32Params& p, const PlanView& plan, cudaStream_t st) {
+  using C = UrCfg<Q>;
+  int dev = 0;
+  SGNN_CUDA(cudaGetDevice(&dev));
+  static bool attr_set[64] = {};
+  if (dev < 0 || dev >= 64) return SGNN_E_INVALID;
+  if (!attr_set[dev]) {
+    SGNN_CUDA(cudaFuncSetAttribute(conv_ur_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    SGNN_CUDA(cudaFuncSetAttribute(conv_ur_kernel<Q>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_set[dev] = true;
+  }
+  const long long tiles = (p.n_rows + T32_M - 1) / T32_M;
+  long long grid = 148;
+  if (grid > tiles) grid = tiles;
+  conv_ur_kernel<Q><<<(int)grid, UR_THREADS, C::SMEM, st>>>(p, plan, tiles);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+bool al(const void* p, uintptr_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
+
+PlanView plan_view(const void* plan, long long tiles) {
+  PlanView v;
+  const unsigned char* b = (const unsigned char*)plan;
+  v.ucount = (const int*)b;
+  b += plan_align((size_t)tiles * 4);
+  v.urows = (const int*)b;
+  b += plan_align((size_t)tiles * UR_PLAN_CAP * 4);
+  v.lidx = (const unsigned short*)b;
+  return v;
+}
+
+}  // namespace
+
+extern "C" size_t sgnn_tile_plan_bytes(int64_t n_rows) {
+  if (n_rows <= 0) return 256;
+  const size_t tiles = (size_t)((n_rows + 127) / 128);
+  return plan_align(tiles * 4) + plan_align(tiles * UR_PLAN_CAP * 4) + plan_align(tiles * UR_LIDX_BYTES);
+}
+
+extern "C" int sgnn_tile_plan_build(const int32_t* nbr, int64_t nbr_stride, int64_t n_rows, void* plan, size_t plan_bytes,
+                                    void* stream) {
+  if (n_rows < 0 || (n_rows > 0 && (!nbr || !plan))) return SGNN_E_INVALID;
+  if (n_rows == 0) return SGNN_OK;
+  if (plan_bytes < sgnn_tile_plan_bytes(n_rows)) return SGNN_E_NOMEM;
+  if (!al(plan, 256)) return SGNN_E_ALIGN;
+  const long long tiles = (n_rows + 127) / 128;
+  PlanView v = plan_view(plan, tiles);
+  long long grid = tiles < 148 * 8 ? tiles : 148 * 8;
+  tile_plan_kernel<<<(int)grid, 128, 0, (cudaStream_t)stream>>>(nbr, nbr_stride, n_rows, tiles, (int*)v.ucount, (int*)v.urows,
+                                                                 (unsigned short*)v.lidx);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+extern "C" int sgnn_conv_forward_tc32_ur(const SgnnConvArgs* a, const void* plan, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+  if (!a || a->n_out < 0 || a->cin <= 0 || !a->weight) return SGNN_E_INVALID;
+  if (a->dtype != SGNN_F32 || a->cout != 16 || a->cin > 32 || a->K != 27 || a->child_mode) return SGNN_E_UNSUPPORTED;
+  if (a->n_out == 0) return SGNN_OK;
+  if (!a->a.out && !a->b.out) return SGNN_E_INVALID;
+  if (!a->in || !a->nbr || !workspace || !plan) return SGNN_E_INVALID;
+  if (workspace_bytes < sgnn_conv_tc32_workspace_bytes(a->K, a->cin, 0)) return SGNN_E_NOMEM;
+  const SgnnEpilogue* eps[2] = {&a->a, &a->b};
+  for (int i = 0; i < 2; ++i) {
+    const SgnnEpilogue& e = *eps[i];
+    if (!e.out) continue;
+    if ((e.scale == nullptr) != (e.shift == nullptr)) return SGNN_E_INVALID;
+    if (!al(e.out, 16) || (e.ld & 3) || (e.scale && (!al(e.scale, 16) || !al(e.shift, 16)))) return SGNN_E_ALIGN;
+  }
+  if (!al(a->in, 16) || (a->ld_in & 3) || a->ld_in < a->cin || !al(workspace, 16) || !al(plan, 256)) return SGNN_E_ALIGN;
+  if (a->residual && (!al(a->residual, 16) || (a->ld_res & 3))) return SGNN_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Q = (a->cin + 15) / 16;
+  Tc32Params p;
+  p.in = (const float*)a->in; p.ld_in = a->ld_in; p.cin = a->cin;
+  p.nbr = a->nbr; p.nbr_stride = a->nbr_stride; p.K = a->K;
+  p.wsplit = (const unsigned char*)workspace;
+  p.planes = nullptr; p.n_in = a->n_in;
+  p.n_rows = a->n_out;
+  p.residual = (const float*)a->residual; p.ld_res = a->ld_res;
+  p.out_a = (float*)a->a.out; p.ld_a = a->a.ld; p.relu_a = a->a.relu; p.scale_a = a->a.scale; p.shift_a = a->a.shift;
+  p.out_b = (float*)a->b.out; p.ld_b = a->b.ld; p.relu_b = a->b.relu; p.scale_b = a->b.scale; p.shift_b = a->b.shift;
+  {
+    const int total = a->K * Q * 256;
+    tc32_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)a->weight, a->K, a->cin, Q, (unsigned char*)workspace);
+    SGNN_CHECK_LAUNCH();
+  }
+  const PlanView v = plan_view(plan, (a->n_out + 127) / 128);
+  return Q == 1 ? launch_ur<1>(p, v, st) : launch_ur<2>(p, v, st);
+}

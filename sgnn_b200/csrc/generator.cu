@@ -13,6 +13,9 @@
 extern int g_sgnn_conv_impl;   // conv.cu
 long long g_sgnn_tc32_min_rows = 60000;
 extern "C" void sgnn_debug_set_tc32_min_rows(int64_t n) { g_sgnn_tc32_min_rows = n; }
+// site sets with at least this many rows get a unique-row tile plan (conv_ur.cu) for their Cout = 16 submanifold convolutions
+long long g_sgnn_ur_min_rows = 20000;
+extern "C" void sgnn_debug_set_ur_min_rows(int64_t n) { g_sgnn_ur_min_rows = n; }
 
 namespace {
 
@@ -62,6 +65,7 @@ struct Level {
   SgnnGrid g;
   int32_t* coords;
   int32_t* nbr;
+  void* plan;      // unique-row tile plan of nbr (conv_ur.cu) or nullptr
   int64_t n;
   int dims[3];
 };
@@ -99,6 +103,17 @@ static void grid_shape(SgnnGrid* g, int nb, const int dims[3]) {
   g->n_words = (int64_t)nb * dims[0] * dims[1] * g->wx;
 }
 
+// unique-row tile plan of a level's neighbour table, when the level is large enough for the tensor-core path
+static int build_plan(Ctx& c, Level* L, int cout) {
+  L->plan = nullptr;
+  if (!c.tc32 || cout != 16 || !L->nbr || L->n < g_sgnn_ur_min_rows) return SGNN_OK;
+  const size_t pb = sgnn_tile_plan_bytes(L->n);
+  void* plan = c.ar.get(pb);
+  if (!plan) return SGNN_E_NOMEM;
+  L->plan = plan;
+  return sgnn_tile_plan_build(L->nbr, L->n, L->n, plan, pb, c.stream);
+}
+
 // a1 + a2: site set from explicit coordinates, with its 27-neighbour table
 static int build_level(Ctx& c, const void* coords, int is64, int64_t n, int nb, const int dims[3], int32_t* status,
                        Level* L) {
@@ -117,6 +132,7 @@ static int build_level(Ctx& c, const void* coords, int is64, int64_t n, int nb, 
   c.ar.off = mark;
   ALLOC(nbr, int32_t, 27 * n);
   L->nbr = nbr;
+  L->plan = nullptr;
   return sgnn_rulebook_submanifold(&L->g, ci32, n, nbr, c.stream);
 }
 
@@ -132,7 +148,7 @@ static int coarsen_begin(Ctx& c, const Level& f, Level* L) {
   ALLOC(mask, uint64_t, L->g.n_words);
   ALLOC(prefix, int32_t, L->g.n_words + 1);
   L->g.mask = mask; L->g.prefix = prefix; L->g.row_of_rank = nullptr;
-  L->n = -1; L->coords = nullptr; L->nbr = nullptr;
+  L->n = -1; L->coords = nullptr; L->nbr = nullptr; L->plan = nullptr;
   const size_t mark = c.ar.off;
   const size_t sb = sgnn_scan_scratch_bytes(L->g.n_words);
   ALLOC(scr, char, sb);
@@ -172,7 +188,7 @@ static int coarsen_finish(Ctx& c, const Level& f, Level* L, int32_t** parent, in
 
 static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr, int64_t nbr_stride, int K,
                 int child, const float* w, int cout, int64_t n_out, const float* res, int ld_res, const Epi& a,
-                const Epi& b, int64_t n_in = 0) {
+                const Epi& b, int64_t n_in = 0, const void* plan = nullptr) {
   SgnnConvArgs x;
   memset(&x, 0, sizeof(x));
   x.in = in; x.ld_in = ld_in; x.dtype = SGNN_F32; x.nbr = nbr; x.nbr_stride = nbr_stride; x.K = K;
@@ -188,7 +204,13 @@ static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr,
   }
   int rc = SGNN_E_UNSUPPORTED;
   bool used_tc = false;
-  if (c.tc32 && cout == 16 && cin >= 12 && cin <= 48 && (!child || cin == 48) && n_out >= g_sgnn_tc32_min_rows) {
+  if (c.tc32 && plan && K == 27 && !child && cout == 16 && cin >= 12 && cin <= 32) {
+    const size_t wb = sgnn_conv_tc32_workspace_bytes(K, cin, 0);
+    void* ws = c.ar.get(wb);
+    if (!ws) return SGNN_E_NOMEM;
+    rc = sgnn_conv_forward_tc32_ur(&x, plan, ws, wb, c.stream);
+    used_tc = rc == SGNN_OK;
+  } else if (c.tc32 && cout == 16 && cin >= 12 && cin <= 48 && (!child || cin == 48) && n_out >= g_sgnn_tc32_min_rows) {
     // room for the pre-split input planes only when that kernel generation is selected (hook 27)
     const size_t wb = g_sgnn_conv_impl == 27 ? sgnn_conv_tc32_workspace_bytes_rows(K, cin, child, x.n_in)
                                              : sgnn_conv_tc32_workspace_bytes(K, cin, child);
@@ -211,8 +233,8 @@ static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr,
 static int res_block(Ctx& c, const Level& lv, const SgnnResBlockW& rb, int ch, const float* x_raw, const float* x_bn,
                      const Epi& a, const Epi& b) {
   ALLOC(mid, float, lv.n * ch);
-  RC(conv(c, x_bn, ch, ch, lv.nbr, lv.n, 27, 0, rb.w0, ch, lv.n, nullptr, 0, epi_bn(mid, ch, rb.bn1), kNoEpi));
-  return conv(c, mid, ch, ch, lv.nbr, lv.n, 27, 0, rb.w1, ch, lv.n, x_raw, ch, a, b);
+  RC(conv(c, x_bn, ch, ch, lv.nbr, lv.n, 27, 0, rb.w0, ch, lv.n, nullptr, 0, epi_bn(mid, ch, rb.bn1), kNoEpi, 0, lv.plan));
+  return conv(c, mid, ch, ch, lv.nbr, lv.n, 27, 0, rb.w1, ch, lv.n, x_raw, ch, a, b, 0, lv.plan);
 }
 
 // FullyConvolutionalNet(reps 1, [c,c,c], residual) + BatchNormReLU(3c): J0 [n, 3c]   (model.py:180-181,255-256)
@@ -234,6 +256,8 @@ static int fcn(Ctx& c, const Level& lv0, const SgnnFcnW& f, const float* x_raw, 
   }
   RC(coarsen_finish(c, lv0, &lv1, &par01, &chi01, true));
   RC(coarsen_finish(c, lv1, &lv2, &par12, &chi12, true));
+  RC(build_plan(c, &lv1, ch));
+  RC(build_plan(c, &lv2, ch));
   rows[1] = lv1.n;
   rows[2] = lv2.n;
   ALLOC(y0_bn, float, lv0.n * ch);
@@ -317,6 +341,9 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
     GEN(coarsen_finish(c, enc_lv[0], &enc_lv[1], &enc_par[0], &enc_chi[0], true));
     GEN(coarsen_finish(c, enc_lv[1], &enc_lv[2], &enc_par[1], &enc_chi[1], true));
     GEN(coarsen_finish(c, enc_lv[2], &enc_lv[3], &enc_par[2], &enc_chi[2], false));
+    GEN(build_plan(c, &lv, w->enc[0].c));
+    GEN(build_plan(c, &enc_lv[1], w->enc[1].c));
+    GEN(build_plan(c, &enc_lv[2], w->enc[2].c));
     bool enc_ok = true;
     for (int l = 0; l < 3 && enc_ok; ++l) {
       const SgnnEncLevelW& e = w->enc[l];
@@ -325,7 +352,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       GALLOC(a_raw, float, lv.n * ch);
       GALLOC(a_bn, float, lv.n * ch);
       GEN(conv(c, x, ld_x, e.cin, lv.nbr, lv.n, 27, 0, e.w_in, ch, lv.n, nullptr, 0, epi(a_raw, ch),
-               epi_bn(a_bn, ch, e.res.bn0)));
+               epi_bn(a_bn, ch, e.res.bn0), 0, lv.plan));
       GALLOC(skip, float, lv.n * ch);
       GEN(res_block(c, lv, e.res, ch, a_raw, a_bn, epi_bn(skip, ch, e.bn_out), kNoEpi));
       skips[l].g = lv.g; skips[l].f = skip; skips[l].c = ch; skips[l].n = lv.n;
@@ -425,10 +452,11 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       Level rl;
       GEN(build_level(c, locs, 0, m, nb, rdims, nullptr, &rl));
       const int ch = R.c;
+      GEN(build_plan(c, &rl, ch));
       GALLOC(a_raw, float, m * ch);
       GALLOC(a_bn, float, m * ch);
       GEN(conv(c, fts, ld_f, R.cin, rl.nbr, m, 27, 0, R.w_in, ch, m, nullptr, 0, epi(a_raw, ch),
-               epi_bn(a_bn, ch, R.fcn.blk[0].bn0)));
+               epi_bn(a_bn, ch, R.fcn.blk[0].bn0), 0, rl.plan));
       float* J0 = nullptr;
       GEN(fcn(c, rl, R.fcn, a_raw, a_bn, &J0, &out->rows[4 + 3 * h]));
       // a9: 8 children per site, never materialised: n1 in child mode + n2, heads, mask, compaction
@@ -473,10 +501,11 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       Level sl;
       GEN(build_level(c, locs, 0, m, nb, rdims, nullptr, &sl));
       const int ch = S.c;
+      GEN(build_plan(c, &sl, ch));
       GALLOC(a_raw, float, m * ch);
       GALLOC(a_bn, float, m * ch);
       GEN(conv(c, fts, ld_f, S.cin, sl.nbr, m, 27, 0, S.w_in, ch, m, nullptr, 0, epi(a_raw, ch),
-               epi_bn(a_bn, ch, S.fcn.blk[0].bn0)));
+               epi_bn(a_bn, ch, S.fcn.blk[0].bn0), 0, sl.plan));
       float* J0 = nullptr;
       GEN(fcn(c, sl, S.fcn, a_raw, a_bn, &J0, &out->rows[13]));
       GALLOC(sdf, float, m);

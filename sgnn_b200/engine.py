@@ -9,7 +9,7 @@ from . import _lib
 from ._lib import lib, check, SgnnGrid, SgnnEpilogue, SgnnConvArgs
 
 __all__ = ['Grid', 'build_grid', 'coarsen', 'rulebook_submanifold', 'rulebook_strided',
-           'conv', 'deconv', 'unpool', 'affine_relu', 'add_rows', 'copy_cols', 'linear',
+           'conv', 'tile_plan', 'deconv', 'unpool', 'affine_relu', 'add_rows', 'copy_cols', 'linear',
            'sparse_to_dense', 'dense_to_sparse', 'heads_compact', 'children_coords',
            'concat_skip', 'coords_to_i64', 'grid_lookup', 'fold_bn', 'dense_conv']
 
@@ -148,7 +148,7 @@ def _epilogue(out, scale=None, shift=None, relu=False):
 
 
 def conv(x, nbr, weight, n_out, out_a, child_mode=False, residual=None, scale_a=None, shift_a=None,
-         relu_a=False, out_b=None, scale_b=None, shift_b=None, relu_b=False, tc32=False):
+         relu_a=False, out_b=None, scale_b=None, shift_b=None, relu_b=False, tc32=False, plan=None):
     """a3/a4/a9: out[j] = sum_k x[nbr[k][j]] @ W[k]  (+residual, affine, relu; two output slots).
     x / out_* may be column views of wider row-major buffers (stride(1) == 1).
     tc32=True: the tensor-core path for fp32 features (sgnn_conv_forward_tc32: Cout = 16, Cin <= 48; fp32 accuracy,
@@ -181,7 +181,12 @@ def conv(x, nbr, weight, n_out, out_a, child_mode=False, residual=None, scale_a=
     a.b = _epilogue(out_b, scale_b, shift_b, relu_b)
     ctx = PROFILER.conv(x, nbr, weight, int(n_out), child_mode, residual is not None,
                         out_b is not None) if PROFILER is not None else None
-    if tc32:
+    if plan is not None:
+        wb = lib.sgnn_conv_tc32_workspace_bytes(K, cin, 0)
+        ws = _scratch(wb, x.device)
+        check(lib.sgnn_conv_forward_tc32_ur(C.byref(a), _ptr(plan), C.c_void_p(ws.data_ptr()), wb, _stream()),
+              'sgnn_conv_forward_tc32_ur')
+    elif tc32:
         wb = lib.sgnn_conv_tc32_workspace_bytes_rows(K, cin, a.child_mode, a.n_in)
         ws = _scratch(wb, x.device)
         check(lib.sgnn_conv_forward_tc32(C.byref(a), C.c_void_p(ws.data_ptr()), wb, _stream()), 'sgnn_conv_forward_tc32')
@@ -190,6 +195,17 @@ def conv(x, nbr, weight, n_out, out_a, child_mode=False, residual=None, scale_a=
     if ctx is not None:
         ctx.done()
     return out_a
+
+
+def tile_plan(nbr, n_rows):
+    """Unique-row tile plan of a [27, n] neighbour table (sgnn_tile_plan_build); pass it to conv(..., plan=)."""
+    _need_cuda(nbr)
+    assert nbr.dtype == torch.int32 and nbr.shape[0] == 27 and nbr.stride(1) == 1
+    nb = lib.sgnn_tile_plan_bytes(int(n_rows))
+    plan = _scratch(nb, nbr.device)
+    assert plan.data_ptr() % 256 == 0
+    check(lib.sgnn_tile_plan_build(_ptr(nbr), nbr.stride(0), int(n_rows), _ptr(plan), nb, _stream()), 'sgnn_tile_plan_build')
+    return plan
 
 
 def deconv(x, parent, weight, out, scale=None, shift=None, relu=False):
