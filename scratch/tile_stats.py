@@ -12,16 +12,17 @@ from helpers import nbr_table
 def analyse(tag, coords, tile=128):
     nbr = nbr_table(coords)
     n = coords.shape[0]
-    us, spans = [], []
+    us, spans, runs = [], [], []
     for t0 in range(0, n, tile):
         blk = nbr[:, t0:t0 + tile]
         present = blk[blk >= 0]
         u = np.unique(present)
         us.append(u.size); spans.append(int(u.max() - u.min() + 1) if u.size else 0)
-    us = np.array(us); spans = np.array(spans)
+        runs.append(int((np.diff(u) != 1).sum()) + 1 if u.size else 0)
+    us = np.array(us); spans = np.array(spans); runs = np.array(runs)
     q = lambda a: ' '.join('%d' % np.percentile(a, p) for p in (50, 90, 99, 100))
-    print('%-30s rows %7d tiles %5d  U p50/90/99/max: %s   span p50/90/99/max: %s  frac U>256: %.3f >384: %.3f >512: %.3f' % (
-        tag, n, len(us), q(us), q(spans), (us > 256).mean(), (us > 384).mean(), (us > 512).mean()))
+    print('%-30s rows %7d tiles %5d  U p50/90/99/max: %s   span p50/90/99/max: %s  runs p50/90/99/max: %s  frac U>256: %.3f >384: %.3f >512: %.3f' % (
+        tag, n, len(us), q(us), q(spans), q(runs), (us > 256).mean(), (us > 384).mean(), (us > 512).mean()))
 
 def main():
     nb = int(sys.argv[1]) if len(sys.argv) > 1 else 2

@@ -153,26 +153,71 @@ tile_plan_kernel(const int* __restrict__ nbr, long long nbr_stride, long long n_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Barrier / TMA helpers on 32-bit shared-window addresses (computed once: going through generic pointers makes the
+// compiler rebuild the window address from SR_CgaCtaId around every use).
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mb_init(unsigned a, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count));
 }
-
+__device__ __forceinline__ void mb_arrive(unsigned a) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mb_expect_tx(unsigned a, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_wait(unsigned a, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(a), "r"(parity), "r"(0x989680)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mma_commit_a(unsigned a) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(a) : "memory");
+}
 // TMA, non-tensor form: `bytes` (multiple of 16) global -> shared, completion on the mbarrier's transaction count
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, unsigned bytes, unsigned long long* b) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-               "l"(src), "r"(bytes), "r"(smem_u32(b))
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(mbar)
                : "memory");
 }
+__device__ __forceinline__ uint4 lds128(unsigned a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned lds16(unsigned a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void mma_ts(unsigned tmem_d, unsigned tmem_a, unsigned long long db, bool acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(T32_IDESC), "r"(acc ? 1u : 0u));
+}
 
+// A work ITEM = KG consecutive filter offsets of one (tile, pass); item i of a pass uses A stage i % NST of tensor memory
+// and is produced by warp group (i + tp) & 1 (tp = running tile-pass count, so the odd item alternates between the groups).
 template <int Q>
 struct UrCfg {
   static constexpr int US = Q == 1 ? 512 : 320;          // distinct rows staged per pass
   static constexpr int PL_BUFS = Q == 1 ? 2 : 1;         // plane buffers
   static constexpr int NRING = Q == 1 ? 8 : 6;           // landing ring, chunks of UR_CHUNK rows
-  static constexpr int NST = Q == 1 ? 8 : 4;             // A stages in tensor memory
-  static constexpr int ST_COLS = 256 / NST;              // TMEM columns per A stage (24 Q used)
+  static constexpr int KG = Q == 1 ? 3 : 1;              // filter offsets per item
+  static constexpr int NI = (27 + KG - 1) / KG;          // items per pass
+  static constexpr int ST_COLS = KG * Q * 24;            // TMEM columns of an A stage
+  static constexpr int NST = 256 / ST_COLS;              // A stages (3 x 72 / 5 x 48 columns)
   static constexpr int ROWB = 64 * Q;                    // bytes of a landed fp32 row
   static constexpr int NARR = 6 * Q;                     // 16-byte plane arrays: [slice][plane][half]
   static constexpr int ASTR = (((US + 1) * 16 + 127) / 128) * 128 + 64;   // array stride: odd multiple of 64 B
@@ -180,22 +225,29 @@ struct UrCfg {
   static constexpr int PLANES = PL_BUFS * NARR * ASTR;
   static constexpr int RING = NRING * UR_CHUNK * ROWB;
   static constexpr int SMEM = BANK + PLANES + RING + 2 * UR_LIDX_BYTES;
+  // uses of stage s per pass, and the parity of a stage's use counter at item i of tile-pass tp
+  static __host__ __device__ constexpr int upp(int s) { return (NI - s + NST - 1) / NST; }
 };
 
 #define UR_THREADS 448
+#define UR_NBAR (1 + 2 + 2 + 2 + 2 + 8 + 8 + 8 + 8)   // w_full, lidx f/e, acc f/e, ring f/e (<= 8), stage f/e (<= 8)
 
 template <int Q>
 __global__ void __launch_bounds__(UR_THREADS, 1)
 conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
   using C = UrCfg<Q>;
+  static_assert(C::NRING <= 8 && C::NST <= 8, "barrier table");
   extern __shared__ __align__(1024) unsigned char sm[];
-  unsigned char* bank = sm;                               // [27][Q][3][512]
-  unsigned char* planes = bank + C::BANK;                 // [PL_BUFS][NARR][ASTR]
-  unsigned char* ring = planes + C::PLANES;               // [NRING][UR_CHUNK][ROWB]
-  unsigned short* lidx_s = reinterpret_cast<unsigned short*>(ring + C::RING);   // [2][27][128]
-  __shared__ __align__(8) unsigned long long w_full, lidx_full[2], lidx_empty[2], ring_full[C::NRING], ring_empty[C::NRING],
-      full[C::NST], empty[C::NST], acc_full[2], acc_empty[2];
+  __shared__ __align__(8) unsigned long long bars[UR_NBAR];
   __shared__ unsigned tmem_ptr_s;
+  const unsigned sm_a = smem_u32(sm);
+  const unsigned bank_a = sm_a;                                   // [27][Q][3][512]
+  const unsigned planes_a = bank_a + C::BANK;                     // [PL_BUFS][NARR][ASTR]
+  const unsigned ring_a = planes_a + C::PLANES;                   // [NRING][UR_CHUNK][ROWB]
+  const unsigned lidx_a = ring_a + C::RING;                       // [2][27][128] u16
+  const unsigned bar_a = smem_u32(bars);
+  const unsigned w_full = bar_a, lidx_full = bar_a + 8, lidx_empty = bar_a + 24, acc_full = bar_a + 40, acc_empty = bar_a + 56,
+                 ring_full = bar_a + 72, ring_empty = bar_a + 136, st_full = bar_a + 200, st_empty = bar_a + 264;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 0) {
@@ -203,26 +255,26 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   if (tid == 32) {
-    mbar_init(&w_full, 1);
+    mb_init(w_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&lidx_full[i], 1);
-      mbar_init(&lidx_empty[i], 8);
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);
+      mb_init(lidx_full + 8 * i, 1);
+      mb_init(lidx_empty + 8 * i, 8);
+      mb_init(acc_full + 8 * i, 1);
+      mb_init(acc_empty + 8 * i, 4);
     }
     for (int i = 0; i < C::NRING; ++i) {
-      mbar_init(&ring_full[i], 1);
-      mbar_init(&ring_empty[i], 8);
+      mb_init(ring_full + 8 * i, 1);
+      mb_init(ring_empty + 8 * i, 8);
     }
     for (int i = 0; i < C::NST; ++i) {
-      mbar_init(&full[i], 4);
-      mbar_init(&empty[i], 1);
+      mb_init(st_full + 8 * i, 4);
+      mb_init(st_empty + 8 * i, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::);
   }
   // zero rows of every plane array (index US): what an absent tap reads
   for (int i = tid; i < C::PL_BUFS * C::NARR; i += UR_THREADS)
-    *reinterpret_cast<uint4*>(planes + (size_t)i * C::ASTR + C::US * 16) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(sm + C::BANK + (size_t)i * C::ASTR + C::US * 16) = make_uint4(0u, 0u, 0u, 0u);
   asm volatile("tcgen05.fence::before_thread_sync;" ::);
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::);
@@ -232,38 +284,43 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
   constexpr int n_main = 7;
   // bytes of a row the loader may copy: the row may be shorter than the 16 Q channels the kernel works on
   const unsigned row_bytes = (unsigned)(min(16 * Q, p.ld_in) * 4);
+  // rows whose stride in memory equals the copied bytes are packed at that stride in the ring, so that a run of consecutive
+  // row ids is ONE bulk copy; otherwise (a column view of wider rows) every row is its own copy at the full stride
+  const bool coalesce = (unsigned)p.ld_in * 4u == row_bytes;
+  const unsigned rstride = coalesce ? row_bytes : (unsigned)C::ROWB;
 
   if (warp < 8) {
     // ---------------------------------------------------------------------------------- producers
-    const int g = warp >> 2;                            // warp group: takes the items with (it & 1) == g
+    const int g = warp >> 2;                            // warp group
     const int r = (warp & 3) * 32 + lane;               // output row inside the tile == TMEM lane
     const int pt = tid;                                 // 0..255: piece index of the split
-    const unsigned lane_base = tmem + ((unsigned)((warp & 3) * 32) << 16);
-    long long it = 0, ring_it = 0, tp = 0;
+    const unsigned lane_base = tmem + ((unsigned)((warp & 3) * 32) << 16) + 256u;
+    unsigned ring_it = 0, tp = 0;
     for (long long tl = 0; tl < my_tiles; ++tl) {
       const long long tile = blockIdx.x + tl * gridDim.x;
       const int u = __ldg(plan.ucount + tile);
       const int lb = (int)(tl & 1);
       const bool direct = u < 0;
       const int npass = direct ? 1 : max(1, (u + C::US - 1) / C::US);
-      mbar_wait(&lidx_full[lb], (unsigned)((tl >> 1) & 1));
-      const unsigned short* my_lidx = lidx_s + lb * (27 * 128) + r;
+      mb_wait(lidx_full + 8 * lb, (unsigned)((tl >> 1) & 1));
+      const unsigned my_lidx = lidx_a + (unsigned)(lb * UR_LIDX_BYTES + r * 2);
       const long long j = tile * T32_M + r;
-      for (int pass = 0; pass < npass; ++pass) {
-        unsigned char* pl = planes + (C::PL_BUFS == 2 ? (size_t)(tp & 1) * C::NARR * C::ASTR : 0);
+      for (int pass = 0; pass < npass; ++pass, ++tp) {
+        const unsigned pl_a = planes_a + (C::PL_BUFS == 2 ? (tp & 1u) * (unsigned)(C::NARR * C::ASTR) : 0u);
         if (!direct) {
           if (C::PL_BUFS == 1) bar_sync(2, 256);        // every producer has left the previous tap loop
           const int rows_this = min(C::US, u - pass * C::US);
           const int nch = (rows_this + UR_CHUNK - 1) / UR_CHUNK;
+          unsigned char* pl = sm + (pl_a - sm_a);
           for (int c = 0; c < nch; ++c, ++ring_it) {
-            const int slot = (int)(ring_it % C::NRING);
-            mbar_wait(&ring_full[slot], (unsigned)((ring_it / C::NRING) & 1));
-            const unsigned char* src = ring + (size_t)slot * UR_CHUNK * C::ROWB;
+            const unsigned slot = ring_it % C::NRING;
+            mb_wait(ring_full + 8 * slot, (ring_it / C::NRING) & 1u);
+            const unsigned char* src = sm + (ring_a - sm_a) + (size_t)slot * UR_CHUNK * C::ROWB;
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
               const int piece = pt + 256 * q;           // [row in chunk][16-byte piece of the row]
               const int rr = piece / (4 * Q), c4 = piece % (4 * Q);
-              float4 v = *reinterpret_cast<const float4*>(src + (size_t)piece * 16);
+              float4 v = *reinterpret_cast<const float4*>(src + (size_t)rr * rstride + c4 * 16);
               const int ch = 4 * c4;
               if (ch + 0 >= p.cin) v.x = 0.f;
               if (ch + 1 >= p.cin) v.y = 0.f;
@@ -281,65 +338,91 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
               }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ring_empty[slot]);
+            if (lane == 0) mb_arrive(ring_empty + 8 * slot);
           }
           bar_sync(1, 256);                             // planes of this pass complete
-          ++tp;
         }
         const unsigned base = (unsigned)(pass * C::US);
+        if (!direct) {
+#pragma unroll
+          for (int i = 0; i < C::NI; ++i) {
+            if (((i + tp) & 1u) != (unsigned)g) continue;
+            constexpr int dummy = 0; (void)dummy;
+            const int s = i % C::NST;
+            unsigned rg[C::KG][Q][3][8];
+            unsigned la[C::KG];
+#pragma unroll
+            for (int kk = 0; kk < C::KG; ++kk)
+              if (i * C::KG + kk < 27) la[kk] = lds16(my_lidx + (unsigned)((i * C::KG + kk) * 256));
+#pragma unroll
+            for (int kk = 0; kk < C::KG; ++kk)
+              if (i * C::KG + kk < 27) {
+                const unsigned lw = min(la[kk] - base, (unsigned)C::US);      // absent / other pass -> the zero row
+                const unsigned a = pl_a + lw * 16;
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+#pragma unroll
+                  for (int x = 0; x < 3; ++x) {
+                    const uint4 lo4 = lds128(a + (unsigned)((q * 6 + x * 2) * C::ASTR));
+                    const uint4 hi4 = lds128(a + (unsigned)((q * 6 + x * 2 + 1) * C::ASTR));
+                    rg[kk][q][x][0] = lo4.x; rg[kk][q][x][1] = lo4.y; rg[kk][q][x][2] = lo4.z; rg[kk][q][x][3] = lo4.w;
+                    rg[kk][q][x][4] = hi4.x; rg[kk][q][x][5] = hi4.y; rg[kk][q][x][6] = hi4.z; rg[kk][q][x][7] = hi4.w;
+                  }
+              }
+            const unsigned n = tp * (unsigned)C::upp(s) + (unsigned)(i / C::NST);   // uses of stage s before this one
+            if (n > 0) mb_wait(st_empty + 8 * s, (n - 1) & 1u);                     // the MMAs that read this A stage completed
+            asm volatile("tcgen05.fence::after_thread_sync;" ::);
+            const unsigned a_stage = lane_base + (unsigned)(s * C::ST_COLS);
+#pragma unroll
+            for (int kk = 0; kk < C::KG; ++kk)
+              if (i * C::KG + kk < 27) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+#pragma unroll
+                  for (int x = 0; x < 3; ++x) tmem_st8(a_stage + (unsigned)((kk * Q + q) * 24 + x * 8), rg[kk][q][x]);
+              }
+            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::);
+            __syncwarp();
+            if (lane == 0) mb_arrive(st_full + 8 * s);
+          }
+        } else {
+          // DIRECT mode: the tile's rows straight from global memory, split in registers (same item protocol)
 #pragma unroll 1
-        for (int k = 0; k < 27; ++k, ++it) {
-          if ((int)(it & 1) != g) continue;
-          const int s = (int)(it % C::NST);
-          const long long n = it / C::NST;
-          unsigned rg[Q][3][8];
-          if (!direct) {
-            const unsigned l = my_lidx[k * 128];
-            const unsigned lw = min(l - base, (unsigned)C::US);      // absent / other pass -> the zero row
-            const unsigned char* a = pl + lw * 16;
+          for (int i = 0; i < C::NI; ++i) {
+            if (((i + tp) & 1u) != (unsigned)g) continue;
+            const int s = i % C::NST;
+            const unsigned n = tp * (unsigned)C::upp(s) + (unsigned)(i / C::NST);
+            if (n > 0) mb_wait(st_empty + 8 * s, (n - 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::);
+            const unsigned a_stage = lane_base + (unsigned)(s * C::ST_COLS);
+#pragma unroll 1
+            for (int kk = 0; kk < C::KG; ++kk) {
+              const int k = i * C::KG + kk;
+              if (k >= 27) break;
+              const int idx = j < p.n_rows ? __ldg(p.nbr + (long long)k * p.nbr_stride + j) : -1;
 #pragma unroll
-            for (int q = 0; q < Q; ++q)
+              for (int q = 0; q < Q; ++q) {
+                float x0[8], x1[8];
 #pragma unroll
-              for (int x = 0; x < 3; ++x) {
-                const uint4 lo4 = *reinterpret_cast<const uint4*>(a + (size_t)(q * 6 + x * 2) * C::ASTR);
-                const uint4 hi4 = *reinterpret_cast<const uint4*>(a + (size_t)(q * 6 + x * 2 + 1) * C::ASTR);
-                rg[q][x][0] = lo4.x; rg[q][x][1] = lo4.y; rg[q][x][2] = lo4.z; rg[q][x][3] = lo4.w;
-                rg[q][x][4] = hi4.x; rg[q][x][5] = hi4.y; rg[q][x][6] = hi4.z; rg[q][x][7] = hi4.w;
-              }
-          } else {
-            const int idx = j < p.n_rows ? __ldg(p.nbr + (long long)k * p.nbr_stride + j) : -1;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-              float x0[8], x1[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) { x0[e] = 0.f; x1[e] = 0.f; }
-              if (idx >= 0) {
-                const float* src = p.in + (long long)idx * p.ld_in;
-                load8<false>(src, 16 * q, p.cin, x0);
-                load8<false>(src, 16 * q + 8, p.cin, x1);
-              }
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                split2(x0[2 * i], x0[2 * i + 1], rg[q][0][i], rg[q][1][i], rg[q][2][i]);
-                split2(x1[2 * i], x1[2 * i + 1], rg[q][0][4 + i], rg[q][1][4 + i], rg[q][2][4 + i]);
+                for (int e = 0; e < 8; ++e) { x0[e] = 0.f; x1[e] = 0.f; }
+                if (idx >= 0) {
+                  const float* src = p.in + (long long)idx * p.ld_in;
+                  load8<false>(src, 16 * q, p.cin, x0);
+                  load8<false>(src, 16 * q + 8, p.cin, x1);
+                }
+                split16_tmem(x0, x1, a_stage + (unsigned)((kk * Q + q) * 24));
               }
             }
+            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::);
+            __syncwarp();
+            if (lane == 0) mb_arrive(st_full + 8 * s);
           }
-          if (n > 0) mbar_wait(&empty[s], (unsigned)((n - 1) & 1));   // the MMAs that read this A stage have completed
-          asm volatile("tcgen05.fence::after_thread_sync;" ::);
-          const unsigned a_stage = lane_base + 256u + (unsigned)(s * C::ST_COLS);
-#pragma unroll
-          for (int q = 0; q < Q; ++q)
-#pragma unroll
-            for (int x = 0; x < 3; ++x) tmem_st8(a_stage + (unsigned)(q * 24 + x * 8), rg[q][x]);
-          asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-          asm volatile("tcgen05.fence::before_thread_sync;" ::);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full[s]);
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&lidx_empty[lb]);
+      if (lane == 0) mb_arrive(lidx_empty + 8 * lb);
     }
   } else if (warp < 12) {
     // ---------------------------------------------------------------------------------- epilogue
@@ -347,7 +430,7 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
     const unsigned lane_base = tmem + ((unsigned)(qd * 32) << 16);
     for (long long tl = 0; tl < my_tiles; ++tl) {
       const int ab = (int)(tl & 1);
-      mbar_wait(&acc_full[ab], (unsigned)((tl >> 1) & 1));
+      mb_wait(acc_full + 8 * ab, (unsigned)((tl >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::);
       unsigned v[16], vc[16];
       const unsigned acc = lane_base + (unsigned)(ab * T32_COLS);
@@ -359,62 +442,73 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      if (lane == 0) mb_arrive(acc_empty + 8 * ab);
       const long long j = (blockIdx.x + tl * gridDim.x) * T32_M + qd * 32 + lane;
       if (j < p.n_rows) epilogue_row16(p, v, j);
     }
   } else if (warp == 12) {
     // ---------------------------------------------------------------------------------- MMA issuer
-    mbar_wait(&w_full, 0u);
-    long long it = 0;
+    mb_wait(w_full, 0u);
+    const unsigned long long bdesc0 = umma_desc(bank_a);          // + 32 per 512-byte B block
+    unsigned tp = 0;
     for (long long tl = 0; tl < my_tiles; ++tl) {
       const long long tile = blockIdx.x + tl * gridDim.x;
       const int u = __ldg(plan.ucount + tile);
       const int npass = u < 0 ? 1 : max(1, (u + C::US - 1) / C::US);
       const int ab = (int)(tl & 1);
-      if (tl >= 2) mbar_wait(&acc_empty[ab], (unsigned)(((tl >> 1) - 1) & 1));   // epilogue of tile tl-2 drained
+      if (tl >= 2) mb_wait(acc_empty + 8 * ab, (unsigned)(((tl >> 1) - 1) & 1));   // epilogue of tile tl-2 drained
       const unsigned acc = tmem + (unsigned)(ab * T32_COLS);
-      for (int pass = 0; pass < npass; ++pass)
-        for (int k = 0; k < 27; ++k, ++it) {
-          const int s = (int)(it % C::NST);
-          mbar_wait(&full[s], (unsigned)((it / C::NST) & 1));
+      for (int pass = 0; pass < npass; ++pass, ++tp) {
+        const bool first = pass == 0;
+#pragma unroll
+        for (int i = 0; i < C::NI; ++i) {
+          const int s = i % C::NST;
+          const unsigned n = tp * (unsigned)C::upp(s) + (unsigned)(i / C::NST);
+          mb_wait(st_full + 8 * s, n & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::);
           if (elect_one()) {
             const unsigned a_stage = tmem + 256u + (unsigned)(s * C::ST_COLS);
 #pragma unroll
-            for (int qc = 0; qc < Q; ++qc) {
-              const unsigned a = a_stage + (unsigned)(qc * 24);                            // planes at +0, +8, +16 columns
-              const unsigned b = smem_u32(bank + (size_t)(k * Q + qc) * 3 * T32_BBLK);     // planes at +0, +512, +1024 bytes
-              const unsigned first_corr = (pass == 0 && k == 0 && qc == 0) ? 0u : 1u;
-              const unsigned first_main = (pass == 0 && (k & 3) == 0 && qc == 0) ? 0u : 1u;
-              mma_bf16_ts(acc + T32_CORR, a + 16u, umma_desc(b), first_corr);                    // x2 w0
-              mma_bf16_ts(acc + T32_CORR, a + 8u, umma_desc(b + T32_BBLK), 1u);                  // x1 w1
-              mma_bf16_ts(acc + T32_CORR, a, umma_desc(b + 2 * T32_BBLK), 1u);                   // x0 w2
-              mma_bf16_ts(acc + T32_CORR, a + 8u, umma_desc(b), 1u);                             // x1 w0
-              mma_bf16_ts(acc + T32_CORR, a, umma_desc(b + T32_BBLK), 1u);                       // x0 w1
-              mma_bf16_ts(acc + 16u * (unsigned)(k >> 2), a, umma_desc(b), first_main);          // x0 w0
+            for (int kk = 0; kk < C::KG; ++kk) {
+              const int k = i * C::KG + kk;
+              if (k < 27) {
+#pragma unroll
+                for (int qc = 0; qc < Q; ++qc) {
+                  const unsigned a = a_stage + (unsigned)((kk * Q + qc) * 24);           // planes at +0, +8, +16 columns
+                  const unsigned long long b = bdesc0 + (unsigned long long)((k * Q + qc) * 3 * 32);   // planes at +32, +64
+                  const bool acc_corr = !(first && k == 0 && qc == 0);
+                  const bool acc_main = !(first && (k & 3) == 0 && qc == 0);
+                  mma_ts(acc + T32_CORR, a + 16u, b, acc_corr);                 // x2 w0
+                  mma_ts(acc + T32_CORR, a + 8u, b + 32, true);                 // x1 w1
+                  mma_ts(acc + T32_CORR, a, b + 64, true);                      // x0 w2
+                  mma_ts(acc + T32_CORR, a + 8u, b, true);                      // x1 w0
+                  mma_ts(acc + T32_CORR, a, b + 32, true);                      // x0 w1
+                  mma_ts(acc + 16u * (unsigned)(k >> 2), a, b, acc_main);       // x0 w0
+                }
+              }
             }
-            mma_commit(&empty[s]);
-            if (pass == npass - 1 && k == 26) mma_commit(&acc_full[ab]);
+            mma_commit_a(st_empty + 8 * s);
+            if (pass == npass - 1 && i == C::NI - 1) mma_commit_a(acc_full + 8 * ab);
           }
           __syncwarp();
         }
+      }
     }
   } else {
     // ---------------------------------------------------------------------------------- loader (TMA)
     if (lane == 0) {
-      mbar_expect_tx(&w_full, (unsigned)C::BANK);
-      bulk_g2s(bank, p.wsplit, (unsigned)C::BANK, &w_full);
+      mb_expect_tx(w_full, (unsigned)C::BANK);
+      bulk_g2s(bank_a, p.wsplit, (unsigned)C::BANK, w_full);
     }
-    long long ring_it = 0;
+    unsigned ring_it = 0;
     for (long long tl = 0; tl < my_tiles; ++tl) {
       const long long tile = blockIdx.x + tl * gridDim.x;
       const int u = __ldg(plan.ucount + tile);
       const int lb = (int)(tl & 1);
-      if (tl >= 2) mbar_wait(&lidx_empty[lb], (unsigned)(((tl >> 1) - 1) & 1));
+      if (tl >= 2) mb_wait(lidx_empty + 8 * lb, (unsigned)(((tl >> 1) - 1) & 1));
       if (lane == 0) {
-        mbar_expect_tx(&lidx_full[lb], (unsigned)UR_LIDX_BYTES);
-        bulk_g2s(lidx_s + lb * (27 * 128), plan.lidx + tile * (27 * 128), (unsigned)UR_LIDX_BYTES, &lidx_full[lb]);
+        mb_expect_tx(lidx_full + 8 * lb, (unsigned)UR_LIDX_BYTES);
+        bulk_g2s(lidx_a + lb * UR_LIDX_BYTES, plan.lidx + tile * (27 * 128), (unsigned)UR_LIDX_BYTES, lidx_full + 8 * lb);
       }
       if (u <= 0) continue;
       const int* rows = plan.urows + tile * UR_PLAN_CAP;
@@ -422,18 +516,36 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
       for (int pass = 0; pass < npass; ++pass) {
         const int rows_this = min(C::US, u - pass * C::US);
         const int nch = (rows_this + UR_CHUNK - 1) / UR_CHUNK;
+        // ids of chunk c are loaded one chunk ahead of their copies
+        int nid0 = lane < rows_this ? __ldg(rows + pass * C::US + lane) : -1;
+        int nid1 = lane + 32 < rows_this ? __ldg(rows + pass * C::US + lane + 32) : -1;
         for (int c = 0; c < nch; ++c, ++ring_it) {
-          const int slot = (int)(ring_it % C::NRING);
-          const int first = pass * C::US + c * UR_CHUNK;
+          const unsigned slot = ring_it % C::NRING;
           const int cnt = min(UR_CHUNK, rows_this - c * UR_CHUNK);
-          const int id0 = lane < cnt ? __ldg(rows + first + lane) : -1;
-          const int id1 = lane + 32 < cnt ? __ldg(rows + first + lane + 32) : -1;
-          if (ring_it >= C::NRING) mbar_wait(&ring_empty[slot], (unsigned)((ring_it / C::NRING - 1) & 1));
-          if (lane == 0) mbar_expect_tx(&ring_full[slot], (unsigned)cnt * row_bytes);
+          const int id[2] = {nid0, nid1};
+          if (c + 1 < nch) {
+            const int nf = pass * C::US + (c + 1) * UR_CHUNK, left = rows_this - (c + 1) * UR_CHUNK;
+            nid0 = lane < left ? __ldg(rows + nf + lane) : -1;
+            nid1 = lane + 32 < left ? __ldg(rows + nf + lane + 32) : -1;
+          }
+          if (ring_it >= C::NRING) mb_wait(ring_empty + 8 * slot, (ring_it / C::NRING - 1) & 1u);
+          if (lane == 0) mb_expect_tx(ring_full + 8 * slot, (unsigned)cnt * row_bytes);
           __syncwarp();
-          unsigned char* dst = ring + (size_t)slot * UR_CHUNK * C::ROWB;
-          if (id0 >= 0) bulk_g2s(dst + (size_t)lane * C::ROWB, p.in + (long long)id0 * p.ld_in, row_bytes, &ring_full[slot]);
-          if (id1 >= 0) bulk_g2s(dst + (size_t)(lane + 32) * C::ROWB, p.in + (long long)id1 * p.ld_in, row_bytes, &ring_full[slot]);
+          const unsigned dst = ring_a + slot * (unsigned)(UR_CHUNK * C::ROWB);
+          // consecutive row ids are consecutive in memory when the row stride equals the copied bytes: one bulk copy per RUN
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int cnt_h = min(32, max(0, cnt - 32 * h));
+            const int prev = __shfl_up_sync(0xffffffffu, id[h], 1);
+            const bool start = lane < cnt_h && (lane == 0 || !coalesce || id[h] != prev + 1);
+            const unsigned mask = __ballot_sync(0xffffffffu, start);
+            if (start) {
+              const unsigned higher = mask & ~((2u << lane) - 1u);
+              const int end = higher ? __ffs(higher) - 1 : cnt_h;
+              bulk_g2s(dst + (unsigned)(32 * h + lane) * rstride, p.in + (long long)id[h] * p.ld_in,
+                       (unsigned)(end - lane) * row_bytes, ring_full + 8 * slot);
+            }
+          }
         }
       }
     }

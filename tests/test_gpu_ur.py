@@ -118,6 +118,23 @@ def test_ur_wide_rows_padded_ld():
     _check(out, want, _bound(xbuf[:, :26], nbr, w, n))
 
 
+def test_ur_input_is_column_view_of_wider_rows():
+    """x = 16 columns of 48-float rows: the row stride exceeds the copied bytes, so every row is its own bulk copy."""
+    E = _E()
+    rng = np.random.default_rng(8)
+    c = random_coords(rng, 2, (16, 16, 16), 0.3)
+    n = c.shape[0]
+    wide = torch.full((n, 48), float('nan'), dtype=torch.float32)
+    wide[:, 16:32] = torch.from_numpy(rng.standard_normal((n, 16)).astype(np.float32))
+    w = torch.from_numpy((rng.standard_normal((27, 16, 16)) * 0.1).astype(np.float32))
+    nbr = torch.from_numpy(nbr_table(c))
+    want = o3.conv(wide[:, 16:32], nbr, w, n)
+    out = torch.empty((n, 16), device='cuda')
+    nbr_d = nbr.cuda()
+    E.conv(wide.cuda()[:, 16:32], nbr_d, w.cuda(), n, out, plan=E.tile_plan(nbr_d, n))
+    _check(out, want, _bound(wide[:, 16:32], nbr, w, n))
+
+
 def test_ur_epilogues_residual_dual_slot_views():
     E = _E()
     rng = np.random.default_rng(5)
