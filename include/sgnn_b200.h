@@ -365,6 +365,10 @@ void sgnn_debug_set_tc32_min_rows(int64_t n);
  * convolutions through sgnn_conv_forward_tc32_ur (default 20000). */
 void sgnn_debug_set_ur_min_rows(int64_t n);
 
+/* Watchdog record of sgnn_conv_forward_tc32_ur: a barrier wait that exceeds ~2 s traps the kernel (the call chain then
+ * reports SGNN_E_CUDA) after writing where it stood; out128[0] != 0 when a record exists (128 words, see csrc/conv_ur.cu). */
+int sgnn_debug_ur_diag(uint64_t* out128);
+
 /* Measures the sustained 3-register FFMA rate of the device (TFLOP/s): roofline denominator of the fp32 kernels. */
 int sgnn_debug_ffma_peak(int iters, double* tflops, void* stream);
 

@@ -11,8 +11,11 @@ from sgnn_b200.synth import fill_parameters, synthetic_batch
 from helpers import nbr_table
 
 US = 512
-def wavefronts(units):           # units [8] ints (unit index), -1 absent -> zero row at unit US
-    u = np.where(units >= 0, units, US)
+PRED = False
+def wavefronts(units):           # units [8] ints (unit index), -1 absent -> zero row at unit US (or predicated off)
+    u = units[units >= 0] if PRED else np.where(units >= 0, units, US)
+    if u.size == 0:
+        return 0
     uniq = np.unique(u)
     return np.bincount(uniq % 8, minlength=8).max()
 
@@ -42,5 +45,8 @@ m = OracleGenModel(); fill_parameters(m, 0); m.eval()
 with torch.no_grad():
     (out_locs, out_sdf), levels = m(locs, feats)
 analyse('surface rows', out_locs.numpy()[:20000], maps)
+PRED = True
+analyse('surface rows, absent lanes predicated off', out_locs.numpy()[:20000], {'identity': maps['identity']})
+PRED = False
 c = levels[2][0].numpy(); kept = (torch.sigmoid(levels[2][1][:, 0]) > 0.5).numpy()
 analyse('level 2 kept', c[kept], maps)

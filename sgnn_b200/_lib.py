@@ -134,6 +134,7 @@ SIGNATURES = {
     'sgnn_debug_set_conv_impl': (None, [_I]),
     'sgnn_debug_set_tc32_min_rows': (None, [_L]),
     'sgnn_debug_set_ur_min_rows': (None, [_L]),
+    'sgnn_debug_ur_diag': (_I, [_P]),
     'sgnn_debug_ffma_peak': (_I, [_I, C.POINTER(C.c_double), _P]),
     'sgnn_launch_count': (_L, []),
     'sgnn_version': (_I, []),

@@ -165,20 +165,55 @@ __device__ __forceinline__ void mb_arrive(unsigned a) {
 __device__ __forceinline__ void mb_expect_tx(unsigned a, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mb_wait(unsigned a, unsigned parity) {
-  unsigned ok;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(a), "r"(parity), "r"(0x989680)
-        : "memory");
-  } while (!ok);
+// Watchdog: a wait that does not complete within 3 s (%globaltimer) records where it stood in the
+// mapped host buffer `g_ur_diag` and traps -- a protocol error must fail loudly, not hang the device.
+__device__ unsigned long long* g_ur_diag_dev = nullptr;
+__device__ __noinline__ void mb_timeout(unsigned a, unsigned parity, unsigned site, unsigned bar0, bool fatal) {
+  unsigned long long* d = g_ur_diag_dev;
+  if (d) {
+    const unsigned long long me = (unsigned long long)blockIdx.x + 1;
+    const unsigned long long owner = atomicCAS(d, 0ull, me);
+    if (owner == 0ull || owner == me) {          // one block records: 4 words per warp
+      unsigned long long* w = d + 4 + 4 * (threadIdx.x >> 5);
+      unsigned long long state;
+      asm volatile("ld.shared.b64 %0, [%1];" : "=l"(state) : "r"(a));
+      w[0] = ((unsigned long long)site << 32) | parity;
+      w[1] = ((unsigned long long)threadIdx.x << 32) | (a - bar0);
+      w[2] = state;
+      __threadfence_system();
+    }
+  }
+  if (fatal) { __threadfence_system(); __trap(); }
 }
+__device__ __forceinline__ bool mb_try(unsigned a, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(a), "r"(parity), "r"(0x989680)
+      : "memory");
+  return ok != 0;
+}
+// slow path of a wait, out of line so that the unrolled role loops stay small
+__device__ __noinline__ void mb_wait_slow(unsigned a, unsigned parity, unsigned site, unsigned bar0) {
+  unsigned long long t0 = 0;
+  bool noted = false;
+  while (!mb_try(a, parity)) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 3000000000ull) mb_timeout(a, parity, site, bar0, true);
+    else if (now - t0 > 1500000000ull && !noted) { noted = true; mb_timeout(a, parity, site, bar0, false); }
+  }
+}
+__device__ __forceinline__ void mb_wait_site(unsigned a, unsigned parity, unsigned site, unsigned bar0) {
+  if (!mb_try(a, parity)) mb_wait_slow(a, parity, site, bar0);
+}
+#define mb_wait(a, parity) mb_wait_site((a), (parity), (unsigned)__LINE__, bar_a)
 __device__ __forceinline__ void mma_commit_a(unsigned a) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(a) : "memory");
 }
@@ -191,6 +226,23 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 __device__ __forceinline__ uint4 lds128(unsigned a) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+// predicated form: lanes with pred == 0 issue no shared-memory request (fewer bank conflicts than reading a common zero row)
+__device__ __forceinline__ uint4 lds128_if(unsigned a, unsigned pred) {
+  uint4 v;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.u32 p, %5, 0;\n\t"
+      "mov.b32 %0, 0;\n\t"
+      "mov.b32 %1, 0;\n\t"
+      "mov.b32 %2, 0;\n\t"
+      "mov.b32 %3, 0;\n\t"
+      "@p ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n\t"
+      "}\n"
+      : "=&r"(v.x), "=&r"(v.y), "=&r"(v.z), "=&r"(v.w)
+      : "r"(a), "r"(pred));
   return v;
 }
 __device__ __forceinline__ unsigned lds16(unsigned a) {
@@ -207,8 +259,8 @@ __device__ __forceinline__ void mma_ts(unsigned tmem_d, unsigned tmem_a, unsigne
       "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(T32_IDESC), "r"(acc ? 1u : 0u));
 }
 
-// A work ITEM = KG consecutive filter offsets of one (tile, pass); item i of a pass uses A stage i % NST of tensor memory
-// and is produced by warp group (i + tp) & 1 (tp = running tile-pass count, so the odd item alternates between the groups).
+// A work ITEM = KG consecutive filter offsets of one (tile, pass); the items of a CTA are numbered G = tp * NI + i (tp = running
+// tile-pass count); item G uses A stage G % NST of tensor memory and is produced by warp group G & 1.
 template <int Q>
 struct UrCfg {
   static constexpr int US = Q == 1 ? 512 : 320;          // distinct rows staged per pass
@@ -217,7 +269,12 @@ struct UrCfg {
   static constexpr int KG = Q == 1 ? 3 : 1;              // filter offsets per item
   static constexpr int NI = (27 + KG - 1) / KG;          // items per pass
   static constexpr int ST_COLS = KG * Q * 24;            // TMEM columns of an A stage
-  static constexpr int NST = 256 / ST_COLS;              // A stages (3 x 72 / 5 x 48 columns)
+  // A stages (3 x 72 / 5 x 48 columns).  Stage, use count and producer group of an item are functions of the RUNNING item
+  // count G = tp * NI + i (stage G % NST, use G / NST, group G & 1): consecutive uses of a stage are then exactly NST items
+  // apart also across pass boundaries, and no waiter can be two mbarrier phases away from its barrier.  (Numbering the
+  // stages per pass, i % NST with NI % NST != 0, let a group lap the other at a pass boundary and alias the parity wait: a
+  // rare deadlock, reproduced by scratch/ur_protocol_sim.py.)
+  static constexpr int NST = 256 / ST_COLS;
   static constexpr int ROWB = 64 * Q;                    // bytes of a landed fp32 row
   static constexpr int NARR = 6 * Q;                     // 16-byte plane arrays: [slice][plane][half]
   static constexpr int ASTR = (((US + 1) * 16 + 127) / 128) * 128 + 64;   // array stride: odd multiple of 64 B
@@ -225,18 +282,17 @@ struct UrCfg {
   static constexpr int PLANES = PL_BUFS * NARR * ASTR;
   static constexpr int RING = NRING * UR_CHUNK * ROWB;
   static constexpr int SMEM = BANK + PLANES + RING + 2 * UR_LIDX_BYTES;
-  // uses of stage s per pass, and the parity of a stage's use counter at item i of tile-pass tp
-  static __host__ __device__ constexpr int upp(int s) { return (NI - s + NST - 1) / NST; }
 };
 
-#define UR_THREADS 448
+#define UR_THREADS 480
 #define UR_NBAR (1 + 2 + 2 + 2 + 2 + 8 + 8 + 8 + 8)   // w_full, lidx f/e, acc f/e, ring f/e (<= 8), stage f/e (<= 8)
 
 template <int Q>
 __global__ void __launch_bounds__(UR_THREADS, 1)
-conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
+conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
   using C = UrCfg<Q>;
   static_assert(C::NRING <= 8 && C::NST <= 8, "barrier table");
+  static_assert(C::NST >= 2 && C::NST * C::ST_COLS <= 256, "stage protocol");
   extern __shared__ __align__(1024) unsigned char sm[];
   __shared__ __align__(8) unsigned long long bars[UR_NBAR];
   __shared__ unsigned tmem_ptr_s;
@@ -344,11 +400,11 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
         }
         const unsigned base = (unsigned)(pass * C::US);
         if (!direct) {
-#pragma unroll
+#pragma unroll 1
           for (int i = 0; i < C::NI; ++i) {
-            if (((i + tp) & 1u) != (unsigned)g) continue;
-            constexpr int dummy = 0; (void)dummy;
-            const int s = i % C::NST;
+            const unsigned G = tp * (unsigned)C::NI + (unsigned)i;          // running item count
+            if ((G & 1u) != (unsigned)g) continue;
+            const unsigned s = G % C::NST, n = G / C::NST;                  // A stage, uses of it before this one
             unsigned rg[C::KG][Q][3][8];
             unsigned la[C::KG];
 #pragma unroll
@@ -357,22 +413,23 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
 #pragma unroll
             for (int kk = 0; kk < C::KG; ++kk)
               if (i * C::KG + kk < 27) {
-                const unsigned lw = min(la[kk] - base, (unsigned)C::US);      // absent / other pass -> the zero row
-                const unsigned a = pl_a + lw * 16;
+                const unsigned lw = la[kk] - base;                            // absent (0xFFFF) / other pass: out of range
+                const unsigned here = (lw < (unsigned)C::US || (dbg & 2)) ? 1u : 0u;
+                if (dbg & 2) { if (lw >= (unsigned)C::US) { /* zero row */ } }
+                const unsigned a = pl_a + ((dbg & 2) ? min(lw, (unsigned)C::US) : lw) * 16;
 #pragma unroll
                 for (int q = 0; q < Q; ++q)
 #pragma unroll
                   for (int x = 0; x < 3; ++x) {
-                    const uint4 lo4 = lds128(a + (unsigned)((q * 6 + x * 2) * C::ASTR));
-                    const uint4 hi4 = lds128(a + (unsigned)((q * 6 + x * 2 + 1) * C::ASTR));
+                    const uint4 lo4 = lds128_if(a + (unsigned)((q * 6 + x * 2) * C::ASTR), here);
+                    const uint4 hi4 = lds128_if(a + (unsigned)((q * 6 + x * 2 + 1) * C::ASTR), here);
                     rg[kk][q][x][0] = lo4.x; rg[kk][q][x][1] = lo4.y; rg[kk][q][x][2] = lo4.z; rg[kk][q][x][3] = lo4.w;
                     rg[kk][q][x][4] = hi4.x; rg[kk][q][x][5] = hi4.y; rg[kk][q][x][6] = hi4.z; rg[kk][q][x][7] = hi4.w;
                   }
               }
-            const unsigned n = tp * (unsigned)C::upp(s) + (unsigned)(i / C::NST);   // uses of stage s before this one
             if (n > 0) mb_wait(st_empty + 8 * s, (n - 1) & 1u);                     // the MMAs that read this A stage completed
             asm volatile("tcgen05.fence::after_thread_sync;" ::);
-            const unsigned a_stage = lane_base + (unsigned)(s * C::ST_COLS);
+            const unsigned a_stage = lane_base + s * (unsigned)C::ST_COLS;
 #pragma unroll
             for (int kk = 0; kk < C::KG; ++kk)
               if (i * C::KG + kk < 27) {
@@ -390,12 +447,12 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
           // DIRECT mode: the tile's rows straight from global memory, split in registers (same item protocol)
 #pragma unroll 1
           for (int i = 0; i < C::NI; ++i) {
-            if (((i + tp) & 1u) != (unsigned)g) continue;
-            const int s = i % C::NST;
-            const unsigned n = tp * (unsigned)C::upp(s) + (unsigned)(i / C::NST);
+            const unsigned G = tp * (unsigned)C::NI + (unsigned)i;
+            if ((G & 1u) != (unsigned)g) continue;
+            const unsigned s = G % C::NST, n = G / C::NST;
             if (n > 0) mb_wait(st_empty + 8 * s, (n - 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::);
-            const unsigned a_stage = lane_base + (unsigned)(s * C::ST_COLS);
+            const unsigned a_stage = lane_base + s * (unsigned)C::ST_COLS;
 #pragma unroll 1
             for (int kk = 0; kk < C::KG; ++kk) {
               const int k = i * C::KG + kk;
@@ -460,14 +517,14 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
       const unsigned acc = tmem + (unsigned)(ab * T32_COLS);
       for (int pass = 0; pass < npass; ++pass, ++tp) {
         const bool first = pass == 0;
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < C::NI; ++i) {
-          const int s = i % C::NST;
-          const unsigned n = tp * (unsigned)C::upp(s) + (unsigned)(i / C::NST);
+          const unsigned G = tp * (unsigned)C::NI + (unsigned)i;
+          const unsigned s = G % C::NST, n = G / C::NST;
           mb_wait(st_full + 8 * s, n & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::);
           if (elect_one()) {
-            const unsigned a_stage = tmem + 256u + (unsigned)(s * C::ST_COLS);
+            const unsigned a_stage = tmem + 256u + s * (unsigned)C::ST_COLS;
 #pragma unroll
             for (int kk = 0; kk < C::KG; ++kk) {
               const int k = i * C::KG + kk;
@@ -495,8 +552,9 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
       }
     }
   } else {
-    // ---------------------------------------------------------------------------------- loader (TMA)
-    if (lane == 0) {
+    // ---------------------------------------------------------------------------------- loaders (TMA), warps 13 and 14
+    const unsigned ldr = (unsigned)(warp - 13);           // two loader warps take alternate chunks; warp 13 also the rest
+    if (lane == 0 && ldr == 0) {
       mb_expect_tx(w_full, (unsigned)C::BANK);
       bulk_g2s(bank_a, p.wsplit, (unsigned)C::BANK, w_full);
     }
@@ -505,8 +563,8 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
       const long long tile = blockIdx.x + tl * gridDim.x;
       const int u = __ldg(plan.ucount + tile);
       const int lb = (int)(tl & 1);
-      if (tl >= 2) mb_wait(lidx_empty + 8 * lb, (unsigned)(((tl >> 1) - 1) & 1));
-      if (lane == 0) {
+      if (ldr == 0 && tl >= 2) mb_wait(lidx_empty + 8 * lb, (unsigned)(((tl >> 1) - 1) & 1));
+      if (lane == 0 && ldr == 0) {
         mb_expect_tx(lidx_full + 8 * lb, (unsigned)UR_LIDX_BYTES);
         bulk_g2s(lidx_a + lb * UR_LIDX_BYTES, plan.lidx + tile * (27 * 128), (unsigned)UR_LIDX_BYTES, lidx_full + 8 * lb);
       }
@@ -516,18 +574,12 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
       for (int pass = 0; pass < npass; ++pass) {
         const int rows_this = min(C::US, u - pass * C::US);
         const int nch = (rows_this + UR_CHUNK - 1) / UR_CHUNK;
-        // ids of chunk c are loaded one chunk ahead of their copies
-        int nid0 = lane < rows_this ? __ldg(rows + pass * C::US + lane) : -1;
-        int nid1 = lane + 32 < rows_this ? __ldg(rows + pass * C::US + lane + 32) : -1;
         for (int c = 0; c < nch; ++c, ++ring_it) {
+          if ((dbg & 1) ? (ldr != 0) : ((ring_it & 1u) != ldr)) continue;
           const unsigned slot = ring_it % C::NRING;
           const int cnt = min(UR_CHUNK, rows_this - c * UR_CHUNK);
-          const int id[2] = {nid0, nid1};
-          if (c + 1 < nch) {
-            const int nf = pass * C::US + (c + 1) * UR_CHUNK, left = rows_this - (c + 1) * UR_CHUNK;
-            nid0 = lane < left ? __ldg(rows + nf + lane) : -1;
-            nid1 = lane + 32 < left ? __ldg(rows + nf + lane + 32) : -1;
-          }
+          const int first = pass * C::US + c * UR_CHUNK;
+          const int id[2] = {lane < cnt ? __ldg(rows + first + lane) : -1, lane + 32 < cnt ? __ldg(rows + first + lane + 32) : -1};
           if (ring_it >= C::NRING) mb_wait(ring_empty + 8 * slot, (ring_it / C::NRING - 1) & 1u);
           if (lane == 0) mb_expect_tx(ring_full + 8 * slot, (unsigned)cnt * row_bytes);
           __syncwarp();
@@ -555,9 +607,18 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
+unsigned long long* g_ur_diag_host = nullptr;   // mapped pinned host memory, 128 words (sgnn_debug_ur_diag reads it)
+
 template <int Q>
 int launch_ur(const Tc32Params& p, const PlanView& plan, cudaStream_t st) {
   using C = UrCfg<Q>;
+  if (!g_ur_diag_host) {
+    SGNN_CUDA(cudaHostAlloc((void**)&g_ur_diag_host, 128 * 8, cudaHostAllocMapped));
+    for (int i = 0; i < 128; ++i) g_ur_diag_host[i] = 0;
+    unsigned long long* dptr = nullptr;
+    SGNN_CUDA(cudaHostGetDevicePointer((void**)&dptr, g_ur_diag_host, 0));
+    SGNN_CUDA(cudaMemcpyToSymbol(g_ur_diag_dev, &dptr, sizeof(dptr)));
+  }
   int dev = 0;
   SGNN_CUDA(cudaGetDevice(&dev));
   static bool attr_set[64] = {};
@@ -570,7 +631,9 @@ int launch_ur(const Tc32Params& p, const PlanView& plan, cudaStream_t st) {
   const long long tiles = (p.n_rows + T32_M - 1) / T32_M;
   long long grid = 148;
   if (grid > tiles) grid = tiles;
-  conv_ur_kernel<Q><<<(int)grid, UR_THREADS, C::SMEM, st>>>(p, plan, tiles);
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("SGNN_UR_DBG"); dbg = e ? atoi(e) : 0; }
+  conv_ur_kernel<Q><<<(int)grid, UR_THREADS, C::SMEM, st>>>(p, plan, tiles, dbg);
   SGNN_CHECK_LAUNCH();
   return SGNN_OK;
 }
@@ -589,6 +652,13 @@ PlanView plan_view(const void* plan, long long tiles) {
 }
 
 }  // namespace
+
+// Diagnostic record of a watchdog trap in conv_ur_kernel (128 words; word 0 = recording block + 1, then 4 words per warp: line<<32|parity, tid<<32|barrier offset, barrier state).
+extern "C" int sgnn_debug_ur_diag(uint64_t* out64) {
+  if (!out64) return SGNN_E_INVALID;
+  for (int i = 0; i < 128; ++i) out64[i] = g_ur_diag_host ? g_ur_diag_host[i] : 0;
+  return SGNN_OK;
+}
 
 extern "C" size_t sgnn_tile_plan_bytes(int64_t n_rows) {
   if (n_rows <= 0) return 256;
