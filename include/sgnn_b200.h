@@ -167,7 +167,7 @@ int sgnn_conv_forward_tc32(const SgnnConvArgs* args, void* workspace, size_t wor
 size_t sgnn_tile_plan_bytes(int64_t n_rows);
 int sgnn_tile_plan_build(const int32_t* nbr, int64_t nbr_stride, int64_t n_rows, void* plan, size_t plan_bytes,
                          void* stream);
-/* sgnn_conv_forward_tc32 for K = 27, Cin <= 32, Cout = 16 with a tile plan of args->nbr: the distinct rows of a tile are
+/* sgnn_conv_forward_tc32 for K = 27, Cin <= 32 (ld_in % 4 == 0), Cout in {8, 12, 16} with a tile plan of args->nbr: the distinct rows of a tile are
  * fetched by TMA (cp.async.bulk, one per row) into shared memory, split into the bf16 planes once, and expanded filter
  * offset by filter offset from shared memory into tensor memory for tcgen05.mma.  Same arithmetic and tolerance as
  * sgnn_conv_forward_tc32; `workspace` as there (sgnn_conv_tc32_workspace_bytes(27, cin, 0)). */
@@ -362,7 +362,7 @@ void sgnn_debug_set_conv_impl(int impl);
 /* Tuning hook: under SGNN_GEN_TC32 only convolutions with at least n output rows use the tensor-core path (default 60000). */
 void sgnn_debug_set_tc32_min_rows(int64_t n);
 /* Tuning hook: under SGNN_GEN_TC32 site sets with at least n rows get a tile plan and run their K = 27, Cout = 16
- * convolutions through sgnn_conv_forward_tc32_ur (default 20000). */
+ * convolutions through sgnn_conv_forward_tc32_ur (default 1000). */
 void sgnn_debug_set_ur_min_rows(int64_t n);
 
 /* Watchdog record of sgnn_conv_forward_tc32_ur: a barrier wait that exceeds ~2 s traps the kernel (the call chain then

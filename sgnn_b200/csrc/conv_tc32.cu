@@ -1413,7 +1413,7 @@ extern "C" int sgnn_conv_forward_tc32(const SgnnConvArgs* a, void* workspace, si
   cudaStream_t st = (cudaStream_t)stream;
   const int Q = (a->cin + 15) / 16;
   Tc32Params p;
-  p.in = (const float*)a->in; p.ld_in = a->ld_in; p.cin = a->cin;
+  p.in = (const float*)a->in; p.ld_in = a->ld_in; p.cin = a->cin; p.cout = 16;
   p.nbr = a->nbr; p.nbr_stride = a->nbr_stride; p.K = a->K;
   p.wsplit = (const unsigned char*)workspace;
   p.planes = nullptr; p.n_in = a->n_in;
@@ -1457,7 +1457,7 @@ extern "C" int sgnn_conv_forward_tc32(const SgnnConvArgs* a, void* workspace, si
   }
   {
     const int total = a->K * Q * 256;
-    tc32_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)a->weight, a->K, a->cin, Q, (unsigned char*)workspace);
+    tc32_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)a->weight, a->K, a->cin, 16, Q, (unsigned char*)workspace);
     SGNN_CHECK_LAUNCH();
   }
   if (g_sgnn_conv_impl == 28 && Q == 1 && a->K == 27) return launch_ur(p, st);   // EXPERIMENTAL: distinct rows staged once per tile

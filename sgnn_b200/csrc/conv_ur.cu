@@ -684,7 +684,8 @@ extern "C" int sgnn_tile_plan_build(const int32_t* nbr, int64_t nbr_stride, int6
 extern "C" int sgnn_conv_forward_tc32_ur(const SgnnConvArgs* a, const void* plan, void* workspace, size_t workspace_bytes,
                                          void* stream) {
   if (!a || a->n_out < 0 || a->cin <= 0 || !a->weight) return SGNN_E_INVALID;
-  if (a->dtype != SGNN_F32 || a->cout != 16 || a->cin > 32 || a->K != 27 || a->child_mode) return SGNN_E_UNSUPPORTED;
+  if (a->dtype != SGNN_F32 || (a->cout != 16 && a->cout != 12 && a->cout != 8) || a->cin > 32 || a->K != 27 || a->child_mode)
+    return SGNN_E_UNSUPPORTED;
   if (a->n_out == 0) return SGNN_OK;
   if (!a->a.out && !a->b.out) return SGNN_E_INVALID;
   if (!a->in || !a->nbr || !workspace || !plan) return SGNN_E_INVALID;
@@ -701,7 +702,7 @@ extern "C" int sgnn_conv_forward_tc32_ur(const SgnnConvArgs* a, const void* plan
   cudaStream_t st = (cudaStream_t)stream;
   const int Q = (a->cin + 15) / 16;
   Tc32Params p;
-  p.in = (const float*)a->in; p.ld_in = a->ld_in; p.cin = a->cin;
+  p.in = (const float*)a->in; p.ld_in = a->ld_in; p.cin = a->cin; p.cout = a->cout;
   p.nbr = a->nbr; p.nbr_stride = a->nbr_stride; p.K = a->K;
   p.wsplit = (const unsigned char*)workspace;
   p.planes = nullptr; p.n_in = a->n_in;
@@ -711,7 +712,7 @@ extern "C" int sgnn_conv_forward_tc32_ur(const SgnnConvArgs* a, const void* plan
   p.out_b = (float*)a->b.out; p.ld_b = a->b.ld; p.relu_b = a->b.relu; p.scale_b = a->b.scale; p.shift_b = a->b.shift;
   {
     const int total = a->K * Q * 256;
-    tc32_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)a->weight, a->K, a->cin, Q, (unsigned char*)workspace);
+    tc32_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)a->weight, a->K, a->cin, a->cout, Q, (unsigned char*)workspace);
     SGNN_CHECK_LAUNCH();
   }
   const PlanView v = plan_view(plan, (a->n_out + 127) / 128);

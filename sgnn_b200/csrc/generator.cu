@@ -14,7 +14,7 @@ extern int g_sgnn_conv_impl;   // conv.cu
 long long g_sgnn_tc32_min_rows = 60000;
 extern "C" void sgnn_debug_set_tc32_min_rows(int64_t n) { g_sgnn_tc32_min_rows = n; }
 // site sets with at least this many rows get a unique-row tile plan (conv_ur.cu) for their Cout = 16 submanifold convolutions
-long long g_sgnn_ur_min_rows = 20000;
+long long g_sgnn_ur_min_rows = 1000;
 extern "C" void sgnn_debug_set_ur_min_rows(int64_t n) { g_sgnn_ur_min_rows = n; }
 
 namespace {
@@ -106,6 +106,8 @@ static void grid_shape(SgnnGrid* g, int nb, const int dims[3]) {
 // unique-row tile plan of a level's neighbour table, when the level is large enough for the tensor-core path
 static int build_plan(Ctx& c, Level* L, int cout) {
   L->plan = nullptr;
+  // (the kernel also takes Cout 8 / 12, but on the 5 %-occupancy encoder levels its per-tile overhead loses to the FFMA kernel:
+  // 87-95 us against 68-72 us for 420 k rows, measured)
   if (!c.tc32 || cout != 16 || !L->nbr || L->n < g_sgnn_ur_min_rows) return SGNN_OK;
   const size_t pb = sgnn_tile_plan_bytes(L->n);
   void* plan = c.ar.get(pb);
@@ -204,7 +206,7 @@ static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr,
   }
   int rc = SGNN_E_UNSUPPORTED;
   bool used_tc = false;
-  if (c.tc32 && plan && K == 27 && !child && cout == 16 && cin >= 12 && cin <= 32) {
+  if (c.tc32 && plan && K == 27 && !child && (cout == 16 || cout == 12 || cout == 8) && cin >= 8 && cin <= 32) {
     const size_t wb = sgnn_conv_tc32_workspace_bytes(K, cin, 0);
     void* ws = c.ar.get(wb);
     if (!ws) return SGNN_E_NOMEM;

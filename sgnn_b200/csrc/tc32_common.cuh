@@ -13,7 +13,7 @@
 extern int g_sgnn_conv_impl;
 
 struct Tc32Params {
-  const float* in; int ld_in; int cin;
+  const float* in; int ld_in; int cin; int cout;   // cout: 16, or 8 / 12 (unique-row kernel: accumulator columns >= cout are zero)
   const int* nbr; long long nbr_stride; int K;
   const unsigned char* wsplit;
   const unsigned char* planes;   // pre-split input rows [3][Q][n_in][16] bf16 (conv_tc32_pm_kernel), else NULL
@@ -151,6 +151,7 @@ __device__ __forceinline__ void load8(const float* __restrict__ src, int c0, int
 __device__ __forceinline__ void epilogue_row16(const Tc32Params& p, const unsigned (&v)[16], long long j) {
 #pragma unroll
   for (int c = 0; c < 16; c += 4) {
+    if (c >= p.cout) break;
     float4 a = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]),
                            __uint_as_float(v[c + 3]));
     if (p.residual) {
@@ -207,12 +208,12 @@ __device__ __forceinline__ void store_w_split(unsigned char* blk3, int co, int c
   *reinterpret_cast<unsigned short*>(blk3 + 2 * T32_BBLK + off) = (unsigned short)(__float_as_uint(s) >> 16);
 }
 
-__global__ void tc32_prep_kernel(const float* __restrict__ w, int K, int cin, int Q, unsigned char* __restrict__ out) {
+__global__ void tc32_prep_kernel(const float* __restrict__ w, int K, int cin, int cout, int Q, unsigned char* __restrict__ out) {
   const int total = K * Q * 256;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int co = idx & 15, cil = (idx >> 4) & 15, kq = idx >> 8, qc = kq % Q, k = kq / Q;
     const int ci = qc * 16 + cil;
-    const float v = ci < cin ? __ldg(w + ((size_t)k * cin + ci) * 16 + co) : 0.f;
+    const float v = (ci < cin && co < cout) ? __ldg(w + ((size_t)k * cin + ci) * cout + co) : 0.f;
     store_w_split(out + (size_t)kq * 3 * T32_BBLK, co, cil, v);
   }
 }

@@ -101,6 +101,31 @@ def test_ur_submanifold(cin, nb, dims, occ):
     _check(out, want, _bound(x, nbr, w, n))
 
 
+@pytest.mark.parametrize('cin,cout', [(8, 8), (8, 12), (12, 12), (16, 8)])
+def test_ur_narrow_outputs(cin, cout):
+    """The encoder's 8- and 12-channel layers: accumulator columns >= cout are zero and never stored."""
+    E = _E()
+    rng = np.random.default_rng(cin * 31 + cout)
+    c = random_coords(rng, 3, (20, 18, 22), 0.12)
+    n = c.shape[0]
+    x = torch.from_numpy(rng.standard_normal((n, cin)).astype(np.float32))
+    r = torch.from_numpy(rng.standard_normal((n, cout)).astype(np.float32))
+    w = torch.from_numpy((rng.standard_normal((27, cin, cout)) * 0.1).astype(np.float32))
+    s, t = torch.rand(cout) + 0.5, torch.rand(cout) - 0.5
+    nbr = torch.from_numpy(nbr_table(c))
+    want_a = o3.conv(x, nbr, w, n, residual=r)
+    want_b = o3.conv(x, nbr, w, n, residual=r, scale=s, shift=t, relu=True)
+    wide = torch.full((n, cout + 8), -3.0, device='cuda')          # guard columns around the output slot
+    ob = torch.empty((n, cout), device='cuda')
+    nbr_d = nbr.cuda()
+    E.conv(x.cuda(), nbr_d, w.cuda(), n, wide[:, 4:4 + cout], residual=r.cuda(), out_b=ob, scale_b=s.cuda(), shift_b=t.cuda(),
+           relu_b=True, plan=E.tile_plan(nbr_d, n))
+    bound = _bound(x, nbr, w, n) + r.abs()
+    _check(wide[:, 4:4 + cout], want_a, bound)
+    _check(ob, want_b, bound * s.abs() + 1e-6)
+    assert (wide[:, :4] == -3).all() and (wide[:, 4 + cout:] == -3).all()
+
+
 def test_ur_wide_rows_padded_ld():
     """Joined feature rows as the generator lays them out: cin 26 in 32-float rows (128-byte TMA copies), junk in the pad."""
     E = _E()
@@ -275,5 +300,5 @@ def test_ur_rejects_unsupported_shapes():
         E.conv(torch.zeros((4, 48), device='cuda'), nbr, torch.zeros((27, 48, 16), device='cuda'), 4,
                torch.empty((4, 16), device='cuda'), plan=plan)
     with pytest.raises(SgnnError):
-        E.conv(torch.zeros((4, 16), device='cuda'), nbr, torch.zeros((27, 16, 8), device='cuda'), 4,
-               torch.empty((4, 8), device='cuda'), plan=plan)
+        E.conv(torch.zeros((4, 16), device='cuda'), nbr, torch.zeros((27, 16, 4), device='cuda'), 4,
+               torch.empty((4, 4), device='cuda'), plan=plan)
