@@ -141,7 +141,11 @@ typedef struct SgnnConvArgs {
   int32_t ld_res;
   int32_t n_in;           /* rows of `in`, or 0 if not stated (only the pre-split tensor-core kernel needs it) */
   SgnnEpilogue a, b;
+  int32_t flags;          /* SGNN_CONV_* bits */
+  int32_t reserved;
 } SgnnConvArgs;
+/* tensor-core calls: `workspace` already holds this weight's prepared filter bank (sgnn_conv_tc32_prepare): skip the preparation */
+#define SGNN_CONV_PREPARED 1
 int sgnn_conv_forward(const SgnnConvArgs* args, void* stream);
 
 /* ---- a3 / a4 / a9 on the tensor cores: the same operation as sgnn_conv_forward for fp32 features with Cout = 16
@@ -157,6 +161,11 @@ size_t sgnn_conv_tc32_workspace_bytes(int32_t K, int32_t cin, int32_t child_mode
  * of this size and args->n_in set, the call may split the rows once per layer instead of once per (row, filter offset). */
 size_t sgnn_conv_tc32_workspace_bytes_rows(int32_t K, int32_t cin, int32_t child_mode, int64_t n_in);
 int sgnn_conv_forward_tc32(const SgnnConvArgs* args, void* workspace, size_t workspace_bytes, void* stream);
+/* The filter-bank preparation of the two tensor-core calls on its own (fp32 [K][cin][cout] -> split bf16 planes in the
+ * tensor core's operand layout; child mode: pre-summed per child and parent offset).  Weights do not change between
+ * forward passes, so a caller may prepare once and pass SGNN_CONV_PREPARED afterwards. */
+int sgnn_conv_tc32_prepare(const void* weight, int32_t K, int32_t cin, int32_t cout, int32_t child_mode, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 /* ---- a2 + a3, unique-row form (csrc/conv_ur.cu).  A TILE PLAN re-expresses the submanifold rulebook of a site set per
  * 128-row tile: the sorted list of DISTINCT input rows the tile's 27 filter offsets touch and a 27 x 128 table of 16-bit
@@ -294,6 +303,8 @@ typedef struct SgnnGeneratorW {
   int32_t nf_coarse, reserved;
   SgnnRefineW ref[3];
   SgnnSurfaceW surf;
+  void* prepared;                   /* dev, sgnn_generator_prepared_bytes() bytes, filled by sgnn_generator_prepare; or NULL */
+  size_t prepared_bytes;
 } SgnnGeneratorW;
 typedef struct SgnnGeneratorOut {
   int64_t n_out;        int32_t* out_locs;  float* out_sdf;        /* [n_out,4], [n_out,1] */
@@ -306,6 +317,10 @@ typedef struct SgnnGeneratorOut {
 #define SGNN_GEN_CAND_LOCS 1        /* materialise the candidate coordinates of every level (model.py:247,336) */
 #define SGNN_GEN_PROFILE 2          /* time every convolution launch with CUDA events (adds one sync at the end) */
 #define SGNN_GEN_TC32 4             /* run the Cout = 16 convolutions through sgnn_conv_forward_tc32 (tensor cores) */
+/* Prepared tensor-core filter banks of every Cout = 16 convolution of the generator, built once per weight set: with
+ * w->prepared set, SGNN_GEN_TC32 passes launch no preparation kernels (~30 launches per pass otherwise). */
+size_t sgnn_generator_prepared_bytes(const SgnnGeneratorW* w);
+int sgnn_generator_prepare(const SgnnGeneratorW* w, void* stream);
 int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coords, int coords_i64, const float* feats,
                            int64_t n, int32_t nb, const int32_t* dims3, void* arena, size_t arena_bytes, int flags,
                            SgnnGeneratorOut* out, void* stream);

@@ -9,6 +9,7 @@ class MBar:
         if self.pending == 0: self.pending = self.count; self.phase += 1
     def test(self, parity): return (self.phase & 1) != parity     # true iff the phase with that parity has completed
 
+NG = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 def sim(Q, tiles_passes, seed):
     KG = 3 if Q == 1 else 1
     NI = (27 + KG - 1) // KG
@@ -24,7 +25,7 @@ def sim(Q, tiles_passes, seed):
             for p in range(npass):
                 for i in range(NI):
                     G = tp * NI + i
-                    if (G & 1) != g: continue
+                    if G % NG != g: continue
                     s, n = (G % NST, G // NST) if not PER_PASS else (i % NST, tp * upp(i % NST) + i // NST)
                     if n > 0:
                         while not st_empty[s].test((n - 1) & 1): yield ('st_empty', s, n)
@@ -55,8 +56,8 @@ def sim(Q, tiles_passes, seed):
             yield None
             acc_empty[ab].arrive()
     # each producer warp is its own agent (4 per group), 4 epilogue warps
-    agents = [producer(g) for g in (0, 1) for _ in range(4)] + [mma()] + [epi() for _ in range(4)]
-    names = ['p%d.%d' % (g, w) for g in (0, 1) for w in range(4)] + ['mma'] + ['epi%d' % w for w in range(4)]
+    agents = [producer(g) for g in range(NG) for _ in range(4)] + [mma()] + [epi() for _ in range(4)]
+    names = ['p%d.%d' % (g, w) for g in range(NG) for w in range(4)] + ['mma'] + ['epi%d' % w for w in range(4)]
     alive = list(range(len(agents)))
     last = {}
     idle = 0

@@ -32,7 +32,7 @@ class SgnnConvArgs(C.Structure):
                 ('child_mode', C.c_int32), ('weight', C.c_void_p), ('cin', C.c_int32),
                 ('cout', C.c_int32), ('n_out', C.c_int64), ('residual', C.c_void_p),
                 ('ld_res', C.c_int32), ('n_in', C.c_int32),
-                ('a', SgnnEpilogue), ('b', SgnnEpilogue)]
+                ('a', SgnnEpilogue), ('b', SgnnEpilogue), ('flags', C.c_int32), ('reserved', C.c_int32)]
 
 
 class SgnnBnFold(C.Structure):
@@ -71,7 +71,8 @@ class SgnnSurfaceW(C.Structure):
 
 class SgnnGeneratorW(C.Structure):
     _fields_ = [('enc', SgnnEncLevelW * 3), ('dense', SgnnDenseLayerW * 6), ('w_heads', C.c_void_p),
-                ('nf_coarse', C.c_int32), ('reserved', C.c_int32), ('ref', SgnnRefineW * 3), ('surf', SgnnSurfaceW)]
+                ('nf_coarse', C.c_int32), ('reserved', C.c_int32), ('ref', SgnnRefineW * 3), ('surf', SgnnSurfaceW),
+                ('prepared', C.c_void_p), ('prepared_bytes', C.c_size_t)]
 
 
 class SgnnGeneratorOut(C.Structure):
@@ -102,6 +103,9 @@ SIGNATURES = {
     'sgnn_conv_tc32_workspace_bytes': (_Z, [_I, _I, _I]),
     'sgnn_conv_tc32_workspace_bytes_rows': (_Z, [_I, _I, _I, _L]),
     'sgnn_conv_forward_tc32': (_I, [C.POINTER(SgnnConvArgs), _P, _Z, _P]),
+    'sgnn_conv_tc32_prepare': (_I, [_P, _I, _I, _I, _I, _P, _Z, _P]),
+    'sgnn_generator_prepared_bytes': (_Z, [C.POINTER(SgnnGeneratorW)]),
+    'sgnn_generator_prepare': (_I, [C.POINTER(SgnnGeneratorW), _P]),
     'sgnn_tile_plan_bytes': (_Z, [_L]),
     'sgnn_tile_plan_build': (_I, [_P, _L, _L, _P, _Z, _P]),
     'sgnn_conv_forward_tc32_ur': (_I, [C.POINTER(SgnnConvArgs), _P, _P, _Z, _P]),

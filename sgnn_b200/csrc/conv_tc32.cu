@@ -1390,6 +1390,24 @@ extern "C" size_t sgnn_conv_tc32_workspace_bytes(int32_t K, int32_t cin, int32_t
   return child_mode ? (size_t)64 * 3 * 3 * T32_BBLK : (size_t)K * Q * 3 * T32_BBLK;
 }
 
+extern "C" int sgnn_conv_tc32_prepare(const void* weight, int32_t K, int32_t cin, int32_t cout, int32_t child_mode, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  if (!weight || !workspace || cin <= 0 || cin > 48) return SGNN_E_INVALID;
+  if ((K != 27 && K != 8) || (cout != 16 && cout != 12 && cout != 8)) return SGNN_E_UNSUPPORTED;
+  if (child_mode && (K != 27 || cin != 48 || cout != 16)) return SGNN_E_UNSUPPORTED;
+  if (workspace_bytes < sgnn_conv_tc32_workspace_bytes(K, cin, child_mode)) return SGNN_E_NOMEM;
+  if (!al(workspace, 16)) return SGNN_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (child_mode) {
+    tc32_prep_child_kernel<<<96, 512, 0, st>>>((const float*)weight, cin, (unsigned char*)workspace);
+  } else {
+    const int Q = (cin + 15) / 16, total = K * Q * 256;
+    tc32_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)weight, K, cin, cout, Q, (unsigned char*)workspace);
+  }
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
 extern "C" int sgnn_conv_forward_tc32(const SgnnConvArgs* a, void* workspace, size_t workspace_bytes, void* stream) {
   if (!a || a->n_out < 0 || a->cin <= 0 || !a->weight) return SGNN_E_INVALID;
   if (a->dtype != SGNN_F32 || a->cout != 16 || a->cin > 48) return SGNN_E_UNSUPPORTED;
@@ -1421,9 +1439,12 @@ extern "C" int sgnn_conv_forward_tc32(const SgnnConvArgs* a, void* workspace, si
   p.residual = (const float*)a->residual; p.ld_res = a->ld_res;
   p.out_a = (float*)a->a.out; p.ld_a = a->a.ld; p.relu_a = a->a.relu; p.scale_a = a->a.scale; p.shift_a = a->a.shift;
   p.out_b = (float*)a->b.out; p.ld_b = a->b.ld; p.relu_b = a->b.relu; p.scale_b = a->b.scale; p.shift_b = a->b.shift;
+  const bool prepared = (a->flags & SGNN_CONV_PREPARED) != 0;
   if (a->child_mode) {
-    tc32_prep_child_kernel<<<96, 512, 0, st>>>((const float*)a->weight, a->cin, (unsigned char*)workspace);
-    SGNN_CHECK_LAUNCH();
+    if (!prepared) {
+      tc32_prep_child_kernel<<<96, 512, 0, st>>>((const float*)a->weight, a->cin, (unsigned char*)workspace);
+      SGNN_CHECK_LAUNCH();
+    }
     if (g_sgnn_conv_impl != 25) {   // default: warp-specialised kernel; 25 = single-role kernel (A/B)
       constexpr size_t smem_ws = (size_t)2 * (3 * 3 * T32_ABLK + 4 * 3 * 3 * T32_BBLK);
       static int ctas_ws = 0;
@@ -1455,7 +1476,7 @@ extern "C" int sgnn_conv_forward_tc32(const SgnnConvArgs* a, void* workspace, si
     SGNN_CHECK_LAUNCH();
     return SGNN_OK;
   }
-  {
+  if (!prepared) {
     const int total = a->K * Q * 256;
     tc32_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)a->weight, a->K, a->cin, 16, Q, (unsigned char*)workspace);
     SGNN_CHECK_LAUNCH();

@@ -260,17 +260,17 @@ __device__ __forceinline__ void mma_ts(unsigned tmem_d, unsigned tmem_a, unsigne
 }
 
 // A work ITEM = KG consecutive filter offsets of one (tile, pass); the items of a CTA are numbered G = tp * NI + i (tp = running
-// tile-pass count); item G uses A stage G % NST of tensor memory and is produced by warp group G & 1.
+// tile-pass count); item G uses A stage G % NST of tensor memory and is produced by warp group G % UR_NG.
 template <int Q>
 struct UrCfg {
   static constexpr int US = Q == 1 ? 512 : 320;          // distinct rows staged per pass
   static constexpr int PL_BUFS = Q == 1 ? 2 : 1;         // plane buffers
   static constexpr int NRING = Q == 1 ? 8 : 6;           // landing ring, chunks of UR_CHUNK rows
-  static constexpr int KG = Q == 1 ? 3 : 1;              // filter offsets per item
+  static constexpr int KG = Q == 1 ? 3 : 1;              // filter offsets per item (3 groups x 2 offsets measured slower: 192 vs 155 us)
   static constexpr int NI = (27 + KG - 1) / KG;          // items per pass
   static constexpr int ST_COLS = KG * Q * 24;            // TMEM columns of an A stage
   // A stages (3 x 72 / 5 x 48 columns).  Stage, use count and producer group of an item are functions of the RUNNING item
-  // count G = tp * NI + i (stage G % NST, use G / NST, group G & 1): consecutive uses of a stage are then exactly NST items
+  // count G = tp * NI + i (stage G % NST, use G / NST, group G % UR_NG): consecutive uses of a stage are then exactly NST items
   // apart also across pass boundaries, and no waiter can be two mbarrier phases away from its barrier.  (Numbering the
   // stages per pass, i % NST with NI % NST != 0, let a group lap the other at a pass boundary and alias the parity wait: a
   // rare deadlock, reproduced by scratch/ur_protocol_sim.py.)
@@ -284,7 +284,10 @@ struct UrCfg {
   static constexpr int SMEM = BANK + PLANES + RING + 2 * UR_LIDX_BYTES;
 };
 
-#define UR_THREADS 480
+#define UR_NG 2                                  // producer warp groups (4 warps each)
+#define UR_NPW (4 * UR_NG)                        // producer warps
+#define UR_NPT (128 * UR_NG)                      // producer threads
+#define UR_THREADS (UR_NPT + 128 + 32 + 64)       // + 4 epilogue warps, the MMA warp, 2 loader warps
 #define UR_NBAR (1 + 2 + 2 + 2 + 2 + 8 + 8 + 8 + 8)   // w_full, lidx f/e, acc f/e, ring f/e (<= 8), stage f/e (<= 8)
 
 template <int Q>
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(UR_THREADS, 1)
 conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
   using C = UrCfg<Q>;
   static_assert(C::NRING <= 8 && C::NST <= 8, "barrier table");
-  static_assert(C::NST >= 2 && C::NST * C::ST_COLS <= 256, "stage protocol");
+  static_assert(C::NST >= UR_NG && C::NST * C::ST_COLS <= 256, "stage protocol");   // NST >= groups: no parity aliasing
   extern __shared__ __align__(1024) unsigned char sm[];
   __shared__ __align__(8) unsigned long long bars[UR_NBAR];
   __shared__ unsigned tmem_ptr_s;
@@ -314,13 +317,13 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
     mb_init(w_full, 1);
     for (int i = 0; i < 2; ++i) {
       mb_init(lidx_full + 8 * i, 1);
-      mb_init(lidx_empty + 8 * i, 8);
+      mb_init(lidx_empty + 8 * i, UR_NPW);
       mb_init(acc_full + 8 * i, 1);
       mb_init(acc_empty + 8 * i, 4);
     }
     for (int i = 0; i < C::NRING; ++i) {
       mb_init(ring_full + 8 * i, 1);
-      mb_init(ring_empty + 8 * i, 8);
+      mb_init(ring_empty + 8 * i, UR_NPW);
     }
     for (int i = 0; i < C::NST; ++i) {
       mb_init(st_full + 8 * i, 4);
@@ -345,11 +348,11 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
   const bool coalesce = (unsigned)p.ld_in * 4u == row_bytes;
   const unsigned rstride = coalesce ? row_bytes : (unsigned)C::ROWB;
 
-  if (warp < 8) {
+  if (warp < UR_NPW) {
     // ---------------------------------------------------------------------------------- producers
     const int g = warp >> 2;                            // warp group
     const int r = (warp & 3) * 32 + lane;               // output row inside the tile == TMEM lane
-    const int pt = tid;                                 // 0..255: piece index of the split
+    const int pt = tid;                                 // 0..UR_NPT-1: piece index of the split
     const unsigned lane_base = tmem + ((unsigned)((warp & 3) * 32) << 16) + 256u;
     unsigned ring_it = 0, tp = 0;
     for (long long tl = 0; tl < my_tiles; ++tl) {
@@ -364,7 +367,7 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
       for (int pass = 0; pass < npass; ++pass, ++tp) {
         const unsigned pl_a = planes_a + (C::PL_BUFS == 2 ? (tp & 1u) * (unsigned)(C::NARR * C::ASTR) : 0u);
         if (!direct) {
-          if (C::PL_BUFS == 1) bar_sync(2, 256);        // every producer has left the previous tap loop
+          if (C::PL_BUFS == 1) bar_sync(2, UR_NPT);     // every producer has left the previous tap loop
           const int rows_this = min(C::US, u - pass * C::US);
           const int nch = (rows_this + UR_CHUNK - 1) / UR_CHUNK;
           unsigned char* pl = sm + (pl_a - sm_a);
@@ -372,9 +375,7 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
             const unsigned slot = ring_it % C::NRING;
             mb_wait(ring_full + 8 * slot, (ring_it / C::NRING) & 1u);
             const unsigned char* src = sm + (ring_a - sm_a) + (size_t)slot * UR_CHUNK * C::ROWB;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-              const int piece = pt + 256 * q;           // [row in chunk][16-byte piece of the row]
+            for (int piece = pt; piece < 256 * Q; piece += UR_NPT) {   // [row in chunk][16-byte piece of the row]
               const int rr = piece / (4 * Q), c4 = piece % (4 * Q);
               float4 v = *reinterpret_cast<const float4*>(src + (size_t)rr * rstride + c4 * 16);
               const int ch = 4 * c4;
@@ -396,14 +397,14 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
             __syncwarp();
             if (lane == 0) mb_arrive(ring_empty + 8 * slot);
           }
-          bar_sync(1, 256);                             // planes of this pass complete
+          bar_sync(1, UR_NPT);                          // planes of this pass complete
         }
         const unsigned base = (unsigned)(pass * C::US);
         if (!direct) {
 #pragma unroll 1
           for (int i = 0; i < C::NI; ++i) {
             const unsigned G = tp * (unsigned)C::NI + (unsigned)i;          // running item count
-            if ((G & 1u) != (unsigned)g) continue;
+            if (G % UR_NG != (unsigned)g) continue;
             const unsigned s = G % C::NST, n = G / C::NST;                  // A stage, uses of it before this one
             unsigned rg[C::KG][Q][3][8];
             unsigned la[C::KG];
@@ -448,7 +449,7 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
 #pragma unroll 1
           for (int i = 0; i < C::NI; ++i) {
             const unsigned G = tp * (unsigned)C::NI + (unsigned)i;
-            if ((G & 1u) != (unsigned)g) continue;
+            if (G % UR_NG != (unsigned)g) continue;
             const unsigned s = G % C::NST, n = G / C::NST;
             if (n > 0) mb_wait(st_empty + 8 * s, (n - 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::);
@@ -481,7 +482,7 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
       __syncwarp();
       if (lane == 0) mb_arrive(lidx_empty + 8 * lb);
     }
-  } else if (warp < 12) {
+  } else if (warp < UR_NPW + 4) {
     // ---------------------------------------------------------------------------------- epilogue
     const int qd = warp & 3;
     const unsigned lane_base = tmem + ((unsigned)(qd * 32) << 16);
@@ -503,7 +504,7 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
       const long long j = (blockIdx.x + tl * gridDim.x) * T32_M + qd * 32 + lane;
       if (j < p.n_rows) epilogue_row16(p, v, j);
     }
-  } else if (warp == 12) {
+  } else if (warp == UR_NPW + 4) {
     // ---------------------------------------------------------------------------------- MMA issuer
     mb_wait(w_full, 0u);
     const unsigned long long bdesc0 = umma_desc(bank_a);          // + 32 per 512-byte B block
@@ -552,8 +553,8 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
       }
     }
   } else {
-    // ---------------------------------------------------------------------------------- loaders (TMA), warps 13 and 14
-    const unsigned ldr = (unsigned)(warp - 13);           // two loader warps take alternate chunks; warp 13 also the rest
+    // ---------------------------------------------------------------------------------- loaders (TMA), the last two warps
+    const unsigned ldr = (unsigned)(warp - (UR_NPW + 5));           // two loader warps take alternate chunks; warp 13 also the rest
     if (lane == 0 && ldr == 0) {
       mb_expect_tx(w_full, (unsigned)C::BANK);
       bulk_g2s(bank_a, p.wsplit, (unsigned)C::BANK, w_full);
@@ -710,7 +711,7 @@ extern "C" int sgnn_conv_forward_tc32_ur(const SgnnConvArgs* a, const void* plan
   p.residual = (const float*)a->residual; p.ld_res = a->ld_res;
   p.out_a = (float*)a->a.out; p.ld_a = a->a.ld; p.relu_a = a->a.relu; p.scale_a = a->a.scale; p.shift_a = a->a.shift;
   p.out_b = (float*)a->b.out; p.ld_b = a->b.ld; p.relu_b = a->b.relu; p.scale_b = a->b.scale; p.shift_b = a->b.shift;
-  {
+  if (!(a->flags & SGNN_CONV_PREPARED)) {
     const int total = a->K * Q * 256;
     tc32_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)a->weight, a->K, a->cin, a->cout, Q, (unsigned char*)workspace);
     SGNN_CHECK_LAUNCH();

@@ -40,6 +40,7 @@ struct Ctx {
   bool profile;
   bool tc32;
   int n_ev;
+  const SgnnGeneratorW* w;
 };
 
 // event pool for SGNN_GEN_PROFILE (pairs around every sgnn_conv_forward of the pass)
@@ -188,6 +189,48 @@ static int coarsen_finish(Ctx& c, const Level& f, Level* L, int32_t** parent, in
   return SGNN_OK;
 }
 
+// ---- prepared tensor-core filter banks (one per Cout = 16 convolution weight of the generator, fixed enumeration order)
+struct ConvW { const float* w; int K, cin, cout, child; };
+static int enumerate_convs(const SgnnGeneratorW* w, ConvW* out) {
+  int n = 0;
+  auto add = [&](const float* p, int K, int cin, int cout, int child) {
+    ConvW c; c.w = p; c.K = K; c.cin = cin; c.cout = cout; c.child = child; out[n++] = c;
+  };
+  auto res = [&](const SgnnResBlockW& r, int c) { add(r.w0, 27, c, c, 0); add(r.w1, 27, c, c, 0); };
+  auto fcnw = [&](const SgnnFcnW& f) {
+    for (int b = 0; b < 3; ++b) res(f.blk[b], f.c);
+    for (int d = 0; d < 2; ++d) add(f.w_down[d], 8, f.c, f.c, 0);
+  };
+  for (int l = 0; l < 3; ++l) {
+    const SgnnEncLevelW& e = w->enc[l];
+    add(e.w_in, 27, e.cin, e.c, 0); res(e.res, e.c); add(e.w_down, 8, e.c, e.c, 0);
+  }
+  for (int h = 0; h < 3; ++h) {
+    const SgnnRefineW& r = w->ref[h];
+    add(r.w_in, 27, r.cin, r.c, 0); fcnw(r.fcn); add(r.w_up, 27, 3 * r.c, r.c, 1);
+  }
+  add(w->surf.w_in, 27, w->surf.cin, w->surf.c, 0); fcnw(w->surf.fcn);
+  return n;   // 12 + 3 * 10 + 9 = 51
+}
+static bool bank_eligible(const ConvW& c) { return c.cout == 16 && c.cin >= 12 && c.cin <= 48 && (!c.child || c.cin == 48); }
+static size_t bank_bytes(const ConvW& c) {
+  return (sgnn_conv_tc32_workspace_bytes(c.K, c.cin, c.child) + 255) & ~(size_t)255;
+}
+// prepared bank of weight `p` inside w->prepared, or nullptr
+static void* prepared_bank(const SgnnGeneratorW* w, const float* p, int K, int child) {
+  if (!w->prepared) return nullptr;
+  ConvW cv[64];
+  const int n = enumerate_convs(w, cv);
+  size_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!bank_eligible(cv[i])) continue;
+    if (cv[i].w == p && cv[i].K == K && cv[i].child == child) return off + bank_bytes(cv[i]) <= w->prepared_bytes ? (char*)w->prepared + off : nullptr;
+    off += bank_bytes(cv[i]);
+  }
+  return nullptr;
+}
+
+
 static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr, int64_t nbr_stride, int K,
                 int child, const float* w, int cout, int64_t n_out, const float* res, int ld_res, const Epi& a,
                 const Epi& b, int64_t n_in = 0, const void* plan = nullptr) {
@@ -208,7 +251,9 @@ static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr,
   bool used_tc = false;
   if (c.tc32 && plan && K == 27 && !child && (cout == 16 || cout == 12 || cout == 8) && cin >= 8 && cin <= 32) {
     const size_t wb = sgnn_conv_tc32_workspace_bytes(K, cin, 0);
-    void* ws = c.ar.get(wb);
+    void* ws = prepared_bank(c.w, w, K, 0);
+    if (ws) x.flags |= SGNN_CONV_PREPARED;
+    else ws = c.ar.get(wb);
     if (!ws) return SGNN_E_NOMEM;
     rc = sgnn_conv_forward_tc32_ur(&x, plan, ws, wb, c.stream);
     used_tc = rc == SGNN_OK;
@@ -216,7 +261,9 @@ static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr,
     // room for the pre-split input planes only when that kernel generation is selected (hook 27)
     const size_t wb = g_sgnn_conv_impl == 27 ? sgnn_conv_tc32_workspace_bytes_rows(K, cin, child, x.n_in)
                                              : sgnn_conv_tc32_workspace_bytes(K, cin, child);
-    void* ws = c.ar.get(wb);
+    void* ws = g_sgnn_conv_impl == 27 ? nullptr : prepared_bank(c.w, w, K, child);
+    if (ws) x.flags |= SGNN_CONV_PREPARED;
+    else ws = c.ar.get(wb);
     if (!ws) return SGNN_E_NOMEM;
     rc = sgnn_conv_forward_tc32(&x, ws, wb, c.stream);
     used_tc = rc == SGNN_OK;
@@ -296,6 +343,30 @@ struct Skip { SgnnGrid g; const float* f; int c; int64_t n; };
 
 }  // namespace
 
+extern "C" size_t sgnn_generator_prepared_bytes(const SgnnGeneratorW* w) {
+  if (!w) return 0;
+  ConvW cv[64];
+  const int n = enumerate_convs(w, cv);
+  size_t b = 0;
+  for (int i = 0; i < n; ++i)
+    if (bank_eligible(cv[i])) b += bank_bytes(cv[i]);
+  return b;
+}
+
+extern "C" int sgnn_generator_prepare(const SgnnGeneratorW* w, void* stream) {
+  if (!w || !w->prepared) return SGNN_E_INVALID;
+  if (w->prepared_bytes < sgnn_generator_prepared_bytes(w)) return SGNN_E_NOMEM;
+  ConvW cv[64];
+  const int n = enumerate_convs(w, cv);
+  size_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!bank_eligible(cv[i])) continue;
+    RC(sgnn_conv_tc32_prepare(cv[i].w, cv[i].K, cv[i].cin, cv[i].cout, cv[i].child, (char*)w->prepared + off, bank_bytes(cv[i]), stream));
+    off += bank_bytes(cv[i]);
+  }
+  return SGNN_OK;
+}
+
 extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coords, int coords_i64,
                                       const float* feats, int64_t n, int32_t nb, const int32_t* dims3, void* arena,
                                       size_t arena_bytes, int flags, SgnnGeneratorOut* out, void* stream) {
@@ -306,6 +377,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
   c.st = (cudaStream_t)stream; c.stream = stream;
   c.profile = (flags & SGNN_GEN_PROFILE) != 0; c.n_ev = 0;
   c.tc32 = (flags & SGNN_GEN_TC32) != 0;
+  c.w = w;
   int rc = SGNN_OK;
   do {
 #define GEN(call)                 \

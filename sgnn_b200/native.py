@@ -65,6 +65,13 @@ class _Weights(object):
         s.w_in = self.conv(m.p1)
         self.fcn(s.fcn, m.p2, m.p3)
         s.w_lin, s.b_lin = self.t(m.linear.weight), self.t(m.linear.bias)
+        # tensor-core filter banks, prepared once per weight set (sgnn_generator_prepare)
+        nb = lib.sgnn_generator_prepared_bytes(C.byref(w))
+        self.prepared = torch.empty(max(int(nb), 256), dtype=torch.uint8, device=self.dev)
+        w.prepared, w.prepared_bytes = self.prepared.data_ptr(), int(nb)
+        with torch.cuda.device(self.dev):
+            check(lib.sgnn_generator_prepare(C.byref(w), C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)),
+                  'sgnn_generator_prepare')
 
     @staticmethod
     def version_key(model):
