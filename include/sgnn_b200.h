@@ -183,6 +183,14 @@ int sgnn_tile_plan_build(const int32_t* nbr, int64_t nbr_stride, int64_t n_rows,
 int sgnn_conv_forward_tc32_ur(const SgnnConvArgs* args, const void* plan, void* workspace, size_t workspace_bytes,
                               void* stream);
 
+/* Child mode (generative upsampling, model.py:192-207,224-225) of the unique-row form: args->child_mode = 1, Cin = 48, Cout = 16,
+ * `plan` = the tile plan of the PARENT site set (args->nbr).  Distinct parent rows of a 128-parent tile are staged once by TMA,
+ * the pre-summed child filters stream through a shared-memory ring, children that are consecutive in the accumulator share
+ * one tcgen05.mma.  `workspace`: 64 * 4608 bytes; sgnn_conv_urc_prepare fills it once per weight (then SGNN_CONV_PREPARED). */
+int sgnn_conv_urc_prepare(const void* weight, int32_t cin, void* workspace, size_t workspace_bytes, void* stream);
+int sgnn_conv_forward_tc32_urc(const SgnnConvArgs* args, const void* plan, void* workspace, size_t workspace_bytes,
+                               void* stream);
+
 /* ---- scn.Deconvolution(3,Cin,Cout,2,2) (north_star operator surface; upstream Deconvolution_updateOutput)
  *   out[i] = in[parent[i] >> 3] @ W[parent[i] & 7]          (rows with parent < 0 get zeros) */
 int sgnn_deconv_forward(const void* in, int32_t ld_in, int32_t dtype, const int32_t* parent,

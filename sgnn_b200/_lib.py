@@ -109,6 +109,8 @@ SIGNATURES = {
     'sgnn_tile_plan_bytes': (_Z, [_L]),
     'sgnn_tile_plan_build': (_I, [_P, _L, _L, _P, _Z, _P]),
     'sgnn_conv_forward_tc32_ur': (_I, [C.POINTER(SgnnConvArgs), _P, _P, _Z, _P]),
+    'sgnn_conv_urc_prepare': (_I, [_P, _I, _P, _Z, _P]),
+    'sgnn_conv_forward_tc32_urc': (_I, [C.POINTER(SgnnConvArgs), _P, _P, _Z, _P]),
     'sgnn_deconv_forward': (_I, [_P, _I, _I, _P, _P, _I, _I, _L, _E, _P]),
     'sgnn_unpool': (_I, [_P, _I, _P, _I, _L, _E, _P]),
     'sgnn_affine_relu': (_I, [_P, _I, _P, _I, _L, _I, _P, _P, _I, _P]),

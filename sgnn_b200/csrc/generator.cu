@@ -213,9 +213,9 @@ static int enumerate_convs(const SgnnGeneratorW* w, ConvW* out) {
   return n;   // 12 + 3 * 10 + 9 = 51
 }
 static bool bank_eligible(const ConvW& c) { return c.cout == 16 && c.cin >= 12 && c.cin <= 48 && (!c.child || c.cin == 48); }
-static size_t bank_bytes(const ConvW& c) {
-  return (sgnn_conv_tc32_workspace_bytes(c.K, c.cin, c.child) + 255) & ~(size_t)255;
-}
+// child-mode weights carry two banks: the round-1 kernel's layout, then the unique-row kernel's (conv_urc.cu)
+static size_t bank_half(const ConvW& c) { return (sgnn_conv_tc32_workspace_bytes(c.K, c.cin, c.child) + 255) & ~(size_t)255; }
+static size_t bank_bytes(const ConvW& c) { return c.child ? 2 * bank_half(c) : bank_half(c); }
 // prepared bank of weight `p` inside w->prepared, or nullptr
 static void* prepared_bank(const SgnnGeneratorW* w, const float* p, int K, int child) {
   if (!w->prepared) return nullptr;
@@ -249,7 +249,15 @@ static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr,
   }
   int rc = SGNN_E_UNSUPPORTED;
   bool used_tc = false;
-  if (c.tc32 && plan && K == 27 && !child && (cout == 16 || cout == 12 || cout == 8) && cin >= 8 && cin <= 32) {
+  if (c.tc32 && plan && K == 27 && child && cout == 16 && cin == 48) {
+    const size_t wb = (size_t)64 * 4608;
+    char* bank = (char*)prepared_bank(c.w, w, K, 1);
+    void* ws = bank ? bank + ((sgnn_conv_tc32_workspace_bytes(K, cin, 1) + 255) & ~(size_t)255) : c.ar.get(wb);
+    if (bank) x.flags |= SGNN_CONV_PREPARED;
+    if (!ws) return SGNN_E_NOMEM;
+    rc = sgnn_conv_forward_tc32_urc(&x, plan, ws, wb, c.stream);
+    used_tc = rc == SGNN_OK;
+  } else if (c.tc32 && plan && K == 27 && !child && (cout == 16 || cout == 12 || cout == 8) && cin >= 8 && cin <= 32) {
     const size_t wb = sgnn_conv_tc32_workspace_bytes(K, cin, 0);
     void* ws = prepared_bank(c.w, w, K, 0);
     if (ws) x.flags |= SGNN_CONV_PREPARED;
@@ -361,7 +369,9 @@ extern "C" int sgnn_generator_prepare(const SgnnGeneratorW* w, void* stream) {
   size_t off = 0;
   for (int i = 0; i < n; ++i) {
     if (!bank_eligible(cv[i])) continue;
-    RC(sgnn_conv_tc32_prepare(cv[i].w, cv[i].K, cv[i].cin, cv[i].cout, cv[i].child, (char*)w->prepared + off, bank_bytes(cv[i]), stream));
+    RC(sgnn_conv_tc32_prepare(cv[i].w, cv[i].K, cv[i].cin, cv[i].cout, cv[i].child, (char*)w->prepared + off, bank_half(cv[i]), stream));
+    if (cv[i].child)
+      RC(sgnn_conv_urc_prepare(cv[i].w, cv[i].cin, (char*)w->prepared + off + bank_half(cv[i]), bank_half(cv[i]), stream));
     off += bank_bytes(cv[i]);
   }
   return SGNN_OK;
@@ -536,7 +546,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       // a9: 8 children per site, never materialised: n1 in child mode + n2, heads, mask, compaction
       const int64_t ncand = 8 * m;
       GALLOC(xc, float, ncand * ch);
-      GEN(conv(c, J0, 3 * ch, 3 * ch, rl.nbr, m, 27, 1, R.w_up, ch, ncand, nullptr, 0, epi_bn(xc, ch, R.bn_up), kNoEpi));
+      GEN(conv(c, J0, 3 * ch, 3 * ch, rl.nbr, m, 27, 1, R.w_up, ch, ncand, nullptr, 0, epi_bn(xc, ch, R.bn_up), kNoEpi, m, rl.plan));
       GALLOC(cand, float, ncand * 2);
       GALLOC(flg, uint8_t, ncand);
       GALLOC(offs, int32_t, ncand + 1);

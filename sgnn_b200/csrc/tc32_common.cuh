@@ -254,4 +254,21 @@ __device__ __forceinline__ void split16_tmem(const float (&x0)[8], const float (
   tmem_st8(taddr + 16u, l);
 }
 
+
+// child mode: parent offset reached from child c (z-major bit order) by filter offset d -- same arithmetic as
+// conv_src_row() in conv.cu
+__host__ __device__ __forceinline__ int child_parent_offset(int c, int d) {
+  const int dz = d / 9 - 1, dy = (d / 3) % 3 - 1, dx = d % 3 - 1;
+  const int pz = (((c >> 2) & 1) + dz + 2) / 2 - 1;
+  const int py = (((c >> 1) & 1) + dy + 2) / 2 - 1;
+  const int px = ((c & 1) + dx + 2) / 2 - 1;
+  return (pz + 1) * 9 + (py + 1) * 3 + (px + 1);
+}
+// does child c read parent offset e at all?  (axis value -1 needs child bit 0, +1 needs child bit 1)
+__host__ __device__ __forceinline__ bool child_uses(int c, int e) {
+  const int ez = e / 9 - 1, ey = (e / 3) % 3 - 1, ex = e % 3 - 1;
+  const int cz = (c >> 2) & 1, cy = (c >> 1) & 1, cx = c & 1;
+  return (ez == 0 || ez == 2 * cz - 1) && (ey == 0 || ey == 2 * cy - 1) && (ex == 0 || ex == 2 * cx - 1);
+}
+
 }  // namespace

@@ -181,7 +181,12 @@ def conv(x, nbr, weight, n_out, out_a, child_mode=False, residual=None, scale_a=
     a.b = _epilogue(out_b, scale_b, shift_b, relu_b)
     ctx = PROFILER.conv(x, nbr, weight, int(n_out), child_mode, residual is not None,
                         out_b is not None) if PROFILER is not None else None
-    if plan is not None:
+    if plan is not None and child_mode:
+        wb = 64 * 4608
+        ws = _scratch(wb, x.device)
+        check(lib.sgnn_conv_forward_tc32_urc(C.byref(a), _ptr(plan), C.c_void_p(ws.data_ptr()), wb, _stream()),
+              'sgnn_conv_forward_tc32_urc')
+    elif plan is not None:
         wb = lib.sgnn_conv_tc32_workspace_bytes(K, cin, 0)
         ws = _scratch(wb, x.device)
         check(lib.sgnn_conv_forward_tc32_ur(C.byref(a), _ptr(plan), C.c_void_p(ws.data_ptr()), wb, _stream()),

@@ -302,3 +302,52 @@ def test_ur_rejects_unsupported_shapes():
     with pytest.raises(SgnnError):
         E.conv(torch.zeros((4, 16), device='cuda'), nbr, torch.zeros((27, 16, 4), device='cuda'), 4,
                torch.empty((4, 4), device='cuda'), plan=plan)
+
+
+# ------------------------------------------------------------------------------------------------ child mode (conv_urc.cu)
+def _child_case(E, rng, c, scale=True):
+    n = c.shape[0]
+    x = torch.from_numpy(rng.standard_normal((n, 48)).astype(np.float32))
+    w = torch.from_numpy((rng.standard_normal((27, 48, 16)) * 0.05).astype(np.float32))
+    s, t = torch.rand(16) + 0.5, torch.rand(16) - 0.5
+    nbr = torch.from_numpy(nbr_table(c))
+    want = o3.conv(x, nbr, w, 8 * n, child_mode=True, scale=s, shift=t, relu=True)
+    out = torch.full((8 * n, 16), float('nan'), device='cuda')
+    nbr_d = nbr.cuda()
+    plan = E.tile_plan(nbr_d, n)
+    E.conv(x.cuda(), nbr_d, w.cuda(), 8 * n, out, child_mode=True, scale_a=s.cuda(), shift_a=t.cuda(), relu_a=True, plan=plan)
+    bound = o3.conv(x.abs(), nbr, w.abs(), 8 * n, child_mode=True) * s.abs() + 1e-6
+    _check(out, want, bound)
+    return plan, n
+
+
+@pytest.mark.parametrize('dims,occ', [((7, 6, 9), 0.4), ((16, 16, 16), 0.15), ((3, 3, 3), 1.0), ((24, 20, 28), 0.3)])
+def test_urc_child_mode(dims, occ):
+    """Generative upsampling on the unique-row kernel: centre rounds first, children of a round merged into N = 16 x run MMAs."""
+    E = _E()
+    rng = np.random.default_rng(9 + dims[0])
+    _child_case(E, rng, random_coords(rng, 2, dims, occ))
+
+
+def test_urc_large_persistent_multi_tile():
+    """Several tiles per CTA: filter ring, row ring, index double buffer and the single accumulator set all wrap around."""
+    E = _E()
+    rng = np.random.default_rng(21)
+    c = random_coords(rng, 12, (32, 32, 32), 0.12)
+    assert c.shape[0] > 148 * 2 * 128
+    _child_case(E, rng, c)
+
+
+def test_urc_multi_pass_and_direct():
+    """Shuffled parents: tiles with more than 256 distinct rows take two passes, tiles over the plan cap run in direct mode."""
+    E = _E()
+    rng = np.random.default_rng(33)
+    a = _shuffled(rng, 1, (14, 14, 14), 0.2)               # U ~ 390 per tile: two passes
+    b = _shuffled(rng, 1, (16, 16, 16), 0.6)               # U > 512: direct mode
+    b[:, 3] = 1
+    d = random_coords(rng, 1, (16, 16, 16), 0.3)           # planned, single pass
+    d[:, 3] = 2
+    c = np.ascontiguousarray(np.concatenate([a, b, d]))
+    plan, n = _child_case(E, rng, c)
+    ucount, _, _ = _parse_plan(plan, n)
+    assert (ucount > 256).any() and (ucount == -1).any() and ((ucount >= 0) & (ucount <= 256)).any()
