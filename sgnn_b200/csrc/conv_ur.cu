@@ -174,7 +174,7 @@ struct UrCfg {
 
 template <int Q>
 __global__ void __launch_bounds__(UR_THREADS, 1)
-conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
+conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
   using C = UrCfg<Q>;
   static_assert(C::NRING <= 8 && C::NST <= 8, "barrier table");
   static_assert(C::NST >= UR_NG && C::NST * C::ST_COLS <= 256, "stage protocol");   // NST >= groups: no parity aliasing
@@ -232,6 +232,7 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
 
   if (warp < UR_NPW) {
     // ---------------------------------------------------------------------------------- producers
+    constexpr int ROLE_ID = 0;
     const int g = warp >> 2;                            // warp group
     const int r = (warp & 3) * 32 + lane;               // output row inside the tile == TMEM lane
     const int pt = tid;                                 // 0..UR_NPT-1: piece index of the split
@@ -297,9 +298,8 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
             for (int kk = 0; kk < C::KG; ++kk)
               if (i * C::KG + kk < 27) {
                 const unsigned lw = la[kk] - base;                            // absent (0xFFFF) / other pass: out of range
-                const unsigned here = (lw < (unsigned)C::US || (dbg & 2)) ? 1u : 0u;
-                if (dbg & 2) { if (lw >= (unsigned)C::US) { /* zero row */ } }
-                const unsigned a = pl_a + ((dbg & 2) ? min(lw, (unsigned)C::US) : lw) * 16;
+                const unsigned here = lw < (unsigned)C::US ? 1u : 0u;
+                const unsigned a = pl_a + lw * 16;
 #pragma unroll
                 for (int q = 0; q < Q; ++q)
 #pragma unroll
@@ -366,6 +366,7 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
     }
   } else if (warp < UR_NPW + 4) {
     // ---------------------------------------------------------------------------------- epilogue
+    constexpr int ROLE_ID = 1;
     const int qd = warp & 3;
     const unsigned lane_base = tmem + ((unsigned)(qd * 32) << 16);
     for (long long tl = 0; tl < my_tiles; ++tl) {
@@ -388,6 +389,7 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
     }
   } else if (warp == UR_NPW + 4) {
     // ---------------------------------------------------------------------------------- MMA issuer
+    constexpr int ROLE_ID = 2;
     mb_wait(w_full, 0u);
     const unsigned long long bdesc0 = umma_desc(bank_a);          // + 32 per 512-byte B block
     unsigned tp = 0;
@@ -436,6 +438,7 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
     }
   } else {
     // ---------------------------------------------------------------------------------- loaders (TMA), the last two warps
+    constexpr int ROLE_ID = 3;
     const unsigned ldr = (unsigned)(warp - (UR_NPW + 5));           // two loader warps take alternate chunks; warp 13 also the rest
     if (lane == 0 && ldr == 0) {
       mb_expect_tx(w_full, (unsigned)C::BANK);
@@ -458,7 +461,7 @@ conv_ur_kernel(Tc32Params p, PlanView plan, long long n_tiles, int dbg) {
         const int rows_this = min(C::US, u - pass * C::US);
         const int nch = (rows_this + UR_CHUNK - 1) / UR_CHUNK;
         for (int c = 0; c < nch; ++c, ++ring_it) {
-          if ((dbg & 1) ? (ldr != 0) : ((ring_it & 1u) != ldr)) continue;
+          if ((ring_it & 1u) != ldr) continue;
           const unsigned slot = ring_it % C::NRING;
           const int cnt = min(UR_CHUNK, rows_this - c * UR_CHUNK);
           const int first = pass * C::US + c * UR_CHUNK;
@@ -507,9 +510,7 @@ int launch_ur(const Tc32Params& p, const PlanView& plan, cudaStream_t st) {
   const long long tiles = (p.n_rows + T32_M - 1) / T32_M;
   long long grid = 148;
   if (grid > tiles) grid = tiles;
-  static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("SGNN_UR_DBG"); dbg = e ? atoi(e) : 0; }
-  conv_ur_kernel<Q><<<(int)grid, UR_THREADS, C::SMEM, st>>>(p, plan, tiles, dbg);
+  conv_ur_kernel<Q><<<(int)grid, UR_THREADS, C::SMEM, st>>>(p, plan, tiles);
   SGNN_CHECK_LAUNCH();
   return SGNN_OK;
 }

@@ -9,8 +9,9 @@
 //   * the tile plan of the PARENT site set (conv_ur.cu: sorted distinct rows + 16-bit local indices per 128-parent tile) is
 //     shared with the parents' own unique-row convolutions;
 //   * loader warp 0: TMA (cp.async.bulk, one per run of consecutive rows) of the tile's distinct parent rows (192 B each) into
-//     a ring of 64-row chunks, and of its index block; loader warp 1: TMA of the pre-summed filters of each round (<= 4
-//     children x 4.6 KB) into a 3-stage ring -- the 295 KB bank does not fit in shared memory;
+//     a ring of 64-row chunks, and of its index block; loader warp 1: TMA of the pre-summed filters of each round (1, 2 or 4
+//     children x 4.6 KB) into a 16-slot ring that runs ~7 rounds ahead of the MMAs -- the 295 KB bank does not fit in shared
+//     memory, and fetched round by round in lock-step with the 3 A stages the L2 latency was exposed (240 us -> see DESIGN);
 //   * producers (8 warps): split each landed row once into bf16 planes, then per ROUND (parent offset e; the centre offset,
 //     read by all 8 children, takes two rounds) move row lidx[e][r] shared memory -> tensor memory (18 LDS.128 + 9 tcgen05.st);
 //   * MMA warp: children of a round that are consecutive in the accumulator (z-major child index) share ONE tcgen05.mma of
@@ -27,15 +28,30 @@ struct UrcRound {
   int e, np, nruns, w_off;               // parent offset, children in the round, MMA runs, first (e,c) pair of the round
   int child[4];                          // children, ascending
   int run_c0[4], run_j0[4], run_len[4];  // runs of consecutive children: first child, its index in the round, length
+  int slot, dep;                         // first 4608-byte slot in the filter ring; rounds back to the last item whose slots it reuses
 };
 #define URC_ROUNDS 28
 __constant__ UrcRound c_rounds[URC_ROUNDS];
 
+#define URC_WSLOTS 16                    // filter ring: 16 slots of one (e,c) pair; 64 pairs per pass = 4 laps exactly
+
+// Round order: the two centre rounds (children 0-3, 4-7), the 6 face offsets (4 children each), the 12 edge offsets (2), the 8
+// corner offsets (1).  Sizes descend, so a round's slots never straddle the end of the ring, and the ring position of a round
+// is the same in every pass.
 void build_rounds(UrcRound* r) {
+  int order[URC_ROUNDS], n = 0;
+  order[n++] = 13; order[n++] = 13;
+  for (int want = 4; want >= 1; want >>= 1)
+    for (int e = 0; e < 27; ++e) {
+      if (e == 13) continue;
+      int np = 0;
+      for (int c = 0; c < 8; ++c) np += child_uses(c, e) ? 1 : 0;
+      if (np == want) order[n++] = e;
+    }
   int w_off = 0;
   for (int i = 0; i < URC_ROUNDS; ++i) {
     UrcRound& R = r[i];
-    R.e = i < 2 ? 13 : (i - 2 < 13 ? i - 2 : i - 1);
+    R.e = order[i];
     R.np = 0;
     for (int c = 0; c < 8; ++c) {
       if (!child_uses(c, R.e)) continue;
@@ -48,7 +64,17 @@ void build_rounds(UrcRound* r) {
       R.run_c0[R.nruns] = R.child[j]; R.run_j0[R.nruns] = j; R.run_len[R.nruns] = 1; ++R.nruns;
     }
     R.w_off = w_off;
+    R.slot = w_off % URC_WSLOTS;
     w_off += R.np;
+  }
+  // dep: item G may overwrite its slots once item G - dep (the LAST earlier item touching any of them) has been consumed
+  for (int i = 0; i < URC_ROUNDS; ++i) {
+    int dep = 0;
+    for (int back = 1; back <= URC_ROUNDS && !dep; ++back) {
+      const UrcRound& P = r[((i - back) % URC_ROUNDS + URC_ROUNDS) % URC_ROUNDS];
+      if (P.slot < r[i].slot + r[i].np && r[i].slot < P.slot + P.np) dep = back;
+    }
+    r[i].dep = dep;
   }
 }
 
@@ -86,22 +112,23 @@ struct UrcCfg {
   static constexpr int Q = 3;
   static constexpr int US = 256;                         // distinct parent rows staged per pass
   static constexpr int NRING = 4;                        // landing ring, chunks of UR_CHUNK rows
-  static constexpr int NST = 3;                          // A stages in tensor memory == filter stages in shared memory
+  static constexpr int NST = 3;                          // A stages in tensor memory
   static constexpr int ST_COLS = Q * 24;                 // 72
   static constexpr int ROWB = 64 * Q;                    // 192
   static constexpr int NARR = 6 * Q;                     // 18
   static constexpr int ASTR = (((US + 1) * 16 + 127) / 128) * 128 + 64;
   static constexpr int PLANES = NARR * ASTR;
   static constexpr int RING = NRING * UR_CHUNK * ROWB;
-  static constexpr int WST = 4 * URC_PAIR_BYTES;         // one filter stage: <= 4 children
-  static constexpr int SMEM = PLANES + RING + NST * WST + 2 * UR_LIDX_BYTES;
+  static constexpr int WRING = URC_WSLOTS * URC_PAIR_BYTES;   // filter ring
+  static constexpr int SMEM = PLANES + RING + WRING + 2 * UR_LIDX_BYTES;
 };
 
 #define URC_NG 2
 #define URC_NPW (4 * URC_NG)
 #define URC_NPT (128 * URC_NG)
 #define URC_THREADS (URC_NPT + 128 + 32 + 64)
-#define URC_NBAR (2 + 2 + 1 + 1 + 4 + 4 + 3 + 3 + 3)   // lidx f/e, acc f/e, ring f/e, stage f/e, filter full
+#define URC_NWB 16                       // filter barriers: one pair per item in flight (items run <= 12 ahead)
+#define URC_NBAR (2 + 2 + 1 + 1 + 4 + 4 + 3 + 3 + 2 * URC_NWB)   // lidx f/e, acc f/e, ring f/e, stage f/e, filter f/e
 #define URC_IDESC(N) ((1u << 4) | (1u << 7) | (1u << 10) | (((unsigned)(N) >> 3) << 17) | ((128u >> 4) << 24))
 
 __device__ __forceinline__ void mma_ts_n(unsigned tmem_d, unsigned tmem_a, unsigned long long db, unsigned idesc, bool acc) {
@@ -123,11 +150,12 @@ conv_urc_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
   const unsigned sm_a = smem_u32(sm);
   const unsigned planes_a = sm_a;                                 // [NARR][ASTR]
   const unsigned ring_a = planes_a + C::PLANES;                   // [NRING][UR_CHUNK][ROWB]
-  const unsigned wst_a = ring_a + C::RING;                        // [NST][WST]
-  const unsigned lidx_a = wst_a + C::NST * C::WST;                // [2][27][128] u16
+  const unsigned wst_a = ring_a + C::RING;                        // [URC_WSLOTS][4608]
+  const unsigned lidx_a = wst_a + C::WRING;                       // [2][27][128] u16
   const unsigned bar_a = smem_u32(bars);
   const unsigned lidx_full = bar_a, lidx_empty = bar_a + 16, acc_full = bar_a + 32, acc_empty = bar_a + 40, ring_full = bar_a + 48,
-                 ring_empty = bar_a + 80, st_full = bar_a + 112, st_empty = bar_a + 136, w_full = bar_a + 160;
+                 ring_empty = bar_a + 80, st_full = bar_a + 112, st_empty = bar_a + 136, w_full = bar_a + 160,
+                 w_empty = bar_a + 160 + 8 * URC_NWB;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 0) {
@@ -148,7 +176,10 @@ conv_urc_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
     for (int i = 0; i < C::NST; ++i) {
       mb_init(st_full + 8 * i, 4);
       mb_init(st_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < URC_NWB; ++i) {
       mb_init(w_full + 8 * i, 1);
+      mb_init(w_empty + 8 * i, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::);
   }
@@ -164,6 +195,7 @@ conv_urc_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
 
   if (warp < URC_NPW) {
     // ---------------------------------------------------------------------------------- producers
+    constexpr int ROLE_ID = 0;
     const int g = warp >> 2;
     const int r = (warp & 3) * 32 + lane;               // parent row inside the tile == TMEM lane
     const int pt = tid;
@@ -269,6 +301,7 @@ conv_urc_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
     }
   } else if (warp < URC_NPW + 4) {
     // ---------------------------------------------------------------------------------- epilogue
+    constexpr int ROLE_ID = 1;
     const int qd = warp & 3;
     const unsigned lane_base = tmem + ((unsigned)(qd * 32) << 16);
     for (long long tl = 0; tl < my_tiles; ++tl) {
@@ -290,6 +323,7 @@ conv_urc_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
     }
   } else if (warp == URC_NPW + 4) {
     // ---------------------------------------------------------------------------------- MMA issuer
+    constexpr int ROLE_ID = 2;
     unsigned tp = 0;
     for (long long tl = 0; tl < my_tiles; ++tl) {
       const long long tile = blockIdx.x + tl * gridDim.x;
@@ -301,12 +335,13 @@ conv_urc_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
         for (int rd = 0; rd < URC_ROUNDS; ++rd) {
           const unsigned G = tp * (unsigned)URC_ROUNDS + (unsigned)rd;
           const unsigned s = G % C::NST, n = G / C::NST;
+          const unsigned wb = G % URC_NWB, wn = G / URC_NWB;
           mb_wait(st_full + 8 * s, n & 1u);
-          mb_wait(w_full + 8 * s, n & 1u);
+          mb_wait(w_full + 8 * wb, wn & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::);
           if (elect_one()) {
             const unsigned a_stage = tmem + 256u + s * (unsigned)C::ST_COLS;
-            const unsigned long long wdesc = umma_desc(wst_a + s * (unsigned)C::WST);
+            const unsigned long long wdesc = umma_desc(wst_a + (unsigned)(c_rounds[rd].slot * URC_PAIR_BYTES));
             const int np = c_rounds[rd].np, nruns = c_rounds[rd].nruns;
             const bool fresh = pass == 0 && rd < 2;               // the centre rounds of the first pass overwrite
             for (int ri = 0; ri < nruns; ++ri) {
@@ -329,6 +364,7 @@ conv_urc_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
               }
             }
             mma_commit_a(st_empty + 8 * s);
+            mma_commit_a(w_empty + 8 * wb);
             if (pass == npass - 1 && rd == URC_ROUNDS - 1) mma_commit_a(acc_full);
           }
           __syncwarp();
@@ -337,6 +373,7 @@ conv_urc_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
     }
   } else if (warp == URC_NPW + 5) {
     // ---------------------------------------------------------------------------------- loader 0 (TMA): index blocks + parent rows
+    constexpr int ROLE_ID = 3;
     unsigned ring_it = 0;
     for (long long tl = 0; tl < my_tiles; ++tl) {
       const long long tile = blockIdx.x + tl * gridDim.x;
@@ -380,6 +417,7 @@ conv_urc_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
     }
   } else {
     // ---------------------------------------------------------------------------------- loader 1 (TMA): the round's filters
+    constexpr int ROLE_ID = 4;
     unsigned tp = 0;
     for (long long tl = 0; tl < my_tiles; ++tl) {
       const long long tile = blockIdx.x + tl * gridDim.x;
@@ -389,12 +427,17 @@ conv_urc_kernel(Tc32Params p, PlanView plan, long long n_tiles) {
 #pragma unroll 1
         for (int rd = 0; rd < URC_ROUNDS; ++rd) {
           const unsigned G = tp * (unsigned)URC_ROUNDS + (unsigned)rd;
-          const unsigned s = G % C::NST, n = G / C::NST;
-          if (n > 0) mb_wait(st_empty + 8 * s, (n - 1) & 1u);      // the MMAs that read this filter stage completed
+          const unsigned dep = (unsigned)c_rounds[rd].dep;
+          if (G >= dep) {                                          // the last item that used these slots has been consumed
+            const unsigned X = G - dep;
+            mb_wait(w_empty + 8 * (X % URC_NWB), (X / URC_NWB) & 1u);
+          }
           if (lane == 0) {
             const unsigned bytes = (unsigned)(c_rounds[rd].np * URC_PAIR_BYTES);
-            mb_expect_tx(w_full + 8 * s, bytes);
-            bulk_g2s(wst_a + s * (unsigned)C::WST, p.wsplit + (size_t)c_rounds[rd].w_off * URC_PAIR_BYTES, bytes, w_full + 8 * s);
+            const unsigned wb = G % URC_NWB;
+            mb_expect_tx(w_full + 8 * wb, bytes);
+            bulk_g2s(wst_a + (unsigned)(c_rounds[rd].slot * URC_PAIR_BYTES), p.wsplit + (size_t)c_rounds[rd].w_off * URC_PAIR_BYTES, bytes,
+                     w_full + 8 * wb);
           }
           __syncwarp();
         }

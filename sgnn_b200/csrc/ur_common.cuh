@@ -60,15 +60,17 @@ __device__ __forceinline__ bool mb_try(unsigned a, unsigned parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(a), "r"(parity), "r"(0x989680)
+      : "r"(a), "r"(parity)
       : "memory");
   return ok != 0;
 }
 // slow path of a wait, out of line so that the unrolled role loops stay small
+// one out-of-line copy per warp role (ROLE_ID of the calling scope), so that profiler samples of the waits separate by role
+template <int ROLE>
 __device__ __noinline__ void mb_wait_slow(unsigned a, unsigned parity, unsigned site, unsigned bar0) {
   unsigned long long t0 = 0;
   bool noted = false;
@@ -80,10 +82,11 @@ __device__ __noinline__ void mb_wait_slow(unsigned a, unsigned parity, unsigned 
     else if (now - t0 > 1500000000ull && !noted) { noted = true; mb_timeout(a, parity, site, bar0, false); }
   }
 }
+template <int ROLE>
 __device__ __forceinline__ void mb_wait_site(unsigned a, unsigned parity, unsigned site, unsigned bar0) {
-  if (!mb_try(a, parity)) mb_wait_slow(a, parity, site, bar0);
+  if (!mb_try(a, parity)) mb_wait_slow<ROLE>(a, parity, site, bar0);
 }
-#define mb_wait(a, parity) mb_wait_site((a), (parity), (unsigned)__LINE__, bar_a)
+#define mb_wait(a, parity) mb_wait_site<ROLE_ID>((a), (parity), (unsigned)__LINE__, bar_a)
 __device__ __forceinline__ void mma_commit_a(unsigned a) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(a) : "memory");
 }
