@@ -41,10 +41,10 @@ def parse():
     ap.add_argument('--cpu-reps', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ledger', default='', help='write the per-layer ledger JSON here')
-    ap.add_argument('--conv-impl', type=int, default=0, help='sgnn_debug_set_conv_impl (kernel A/B runs)')
     ap.add_argument('--conv-mode', default='tc32', choices=['exact', 'tc32'],
                     help="exact: fixed-order FFMA convolutions; tc32: Cout=16 convolutions on tcgen05 (3-way bf16 split)")
-    ap.add_argument('--tc32-min-rows', type=int, default=-1, help='sgnn_debug_set_tc32_min_rows (A/B runs)')
+    ap.add_argument('--tc32-min-rows', type=int, default=0, help='GenModel.tc32_min_rows (A/B runs; 0 = default)')
+    ap.add_argument('--ur-min-rows', type=int, default=0, help='GenModel.ur_min_rows (A/B runs; 0 = default)')
     return ap.parse_args()
 
 
@@ -209,9 +209,6 @@ def run_b200(args):
             os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: ONE JSON line
         dist.init_process_group('nccl', device_id=dev)
     ones = np.ones(5, dtype=np.float32)
-    lib.sgnn_debug_set_conv_impl(args.conv_impl)
-    if args.tc32_min_rows >= 0:
-        lib.sgnn_debug_set_tc32_min_rows(args.tc32_min_rows)
 
     model = sgnn_b200.GenModel(8, 64, 1, 16, 16, 4, True, True, 1, 1)
     if rank == 0:
@@ -220,6 +217,7 @@ def run_b200(args):
     shard.broadcast_parameters(model, src=0)          # the one collective of the path (2.57 MB)
     model.return_long = True
     model.conv_mode = args.conv_mode
+    model.tc32_min_rows, model.ur_min_rows = args.tc32_min_rows, args.ur_min_rows
 
     # inputs: `sets` distinct batches per rank (global block id = (set*world + rank)*blocks + i), resident in HBM
     host, resident = [], []

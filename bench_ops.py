@@ -208,23 +208,18 @@ def bench_tc32(args, E, lib, dev, flush, hbm):
     res = {'bench': 'tc32 kernel generations', 'rows': n, 'rules_per_row': rules / n}
     alg = (2 * n * 16) * 4 + 8 * rules + 27 * 256 * 4
     res['ms_regular_ffma_exact'] = timed(lambda: E.conv(x, nbr, w, n, out), args.reps, flush)
-    hooks = [(0, 'v2_single_role'), (23, 'warp_specialised'), (24, 'tmem_operand'), (27, 'presplit_planes')]
-    if os.environ.get('SGNN_EXPERIMENTAL'):
-        hooks.append((28, 'unique_rows_experimental'))
-    for impl, name in hooks:
-        lib.sgnn_debug_set_conv_impl(impl)
-        res['ms_regular_' + name] = timed(lambda: E.conv(x, nbr, w, n, out, tc32=True), args.reps, flush)
-    lib.sgnn_debug_set_conv_impl(0)
+    res['ms_regular_tc32_round1'] = timed(lambda: E.conv(x, nbr, w, n, out, tc32=True), args.reps, flush)
+    plan = E.tile_plan(nbr, n)
+    res['ms_tile_plan'] = timed(lambda: E.tile_plan(nbr, n), args.reps, flush)
+    res['ms_regular_unique_rows'] = timed(lambda: E.conv(x, nbr, w, n, out, plan=plan), args.reps, flush)
     res['regular_best_GBps_algorithmic'] = alg / (min(v for k, v in res.items() if k.startswith('ms_regular')) * 1e-3) / 1e9
     # child mode: the same sites as parents, 48 -> 16 on their 8 children
     x48 = torch.randn((n, 48), device=dev)
     w48 = torch.randn((27, 48, 16), device=dev) * 0.05
     outc = torch.empty((8 * n, 16), device=dev)
     res['ms_child_ffma_exact'] = timed(lambda: E.conv(x48, nbr, w48, 8 * n, outc, child_mode=True), args.reps, flush)
-    for impl, name in ((0, 'warp_specialised'), (25, 'single_role')):
-        lib.sgnn_debug_set_conv_impl(impl)
-        res['ms_child_' + name] = timed(lambda: E.conv(x48, nbr, w48, 8 * n, outc, child_mode=True, tc32=True), args.reps, flush)
-    lib.sgnn_debug_set_conv_impl(0)
+    res['ms_child_tc32_round1'] = timed(lambda: E.conv(x48, nbr, w48, 8 * n, outc, child_mode=True, tc32=True), args.reps, flush)
+    res['ms_child_unique_rows'] = timed(lambda: E.conv(x48, nbr, w48, 8 * n, outc, child_mode=True, plan=plan), args.reps, flush)
     res['hbm_peak_GBps'] = hbm
     print(json.dumps(res))
 

@@ -10,7 +10,7 @@
  * Conventions
  *   - every pointer marked "dev" is a CUDA device pointer owned by the caller;
  *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it
- *     (no host synchronisation, no allocation, no global state) and is re-entrant for
+ *     (no host synchronisation, no allocation, no mutable global state: tuning lives in argument structs) and is re-entrant for
  *     distinct (buffers, stream) pairs;
  *   - return value: SGNN_OK or a negative SGNN_E_* code; nothing throws across the ABI;
  *   - features are row-major [n_rows, ld] with `ld` (elements) >= channels;
@@ -139,7 +139,7 @@ typedef struct SgnnConvArgs {
   int64_t n_out;          /* output rows (8 * parent rows in child mode) */
   const void* residual;   /* dev [n_out, ld_res] or NULL */
   int32_t ld_res;
-  int32_t n_in;           /* rows of `in`, or 0 if not stated (only the pre-split tensor-core kernel needs it) */
+  int32_t n_in;           /* rows of `in`, or 0 if not stated (informational) */
   SgnnEpilogue a, b;
   int32_t flags;          /* SGNN_CONV_* bits */
   int32_t reserved;
@@ -157,9 +157,6 @@ int sgnn_conv_forward(const SgnnConvArgs* args, void* stream);
  * offset).  `workspace`: dev scratch of sgnn_conv_tc32_workspace_bytes(K, cin, child_mode) bytes for the prepared
  * filter bank (written by the call, on `stream`).  SGNN_E_UNSUPPORTED for shapes outside the above. */
 size_t sgnn_conv_tc32_workspace_bytes(int32_t K, int32_t cin, int32_t child_mode);
-/* Same plus room for the input rows pre-split into bf16 planes (96 B per row and 16-channel slice): with a workspace
- * of this size and args->n_in set, the call may split the rows once per layer instead of once per (row, filter offset). */
-size_t sgnn_conv_tc32_workspace_bytes_rows(int32_t K, int32_t cin, int32_t child_mode, int64_t n_in);
 int sgnn_conv_forward_tc32(const SgnnConvArgs* args, void* workspace, size_t workspace_bytes, void* stream);
 /* The filter-bank preparation of the two tensor-core calls on its own (fp32 [K][cin][cout] -> split bf16 planes in the
  * tensor core's operand layout; child mode: pre-summed per child and parent offset).  Weights do not change between
@@ -313,6 +310,9 @@ typedef struct SgnnGeneratorW {
   SgnnSurfaceW surf;
   void* prepared;                   /* dev, sgnn_generator_prepared_bytes() bytes, filled by sgnn_generator_prepare; or NULL */
   size_t prepared_bytes;
+  /* SGNN_GEN_TC32 row thresholds, 0 = default: site sets with >= ur_min_rows rows (1000) get a unique-row tile plan; other
+   * Cout = 16 convolutions with >= tc32_min_rows output rows (60000) use sgnn_conv_forward_tc32, the rest sgnn_conv_forward */
+  int64_t tc32_min_rows, ur_min_rows;
 } SgnnGeneratorW;
 typedef struct SgnnGeneratorOut {
   int64_t n_out;        int32_t* out_locs;  float* out_sdf;        /* [n_out,4], [n_out,1] */
@@ -371,22 +371,6 @@ int sgnn_coords_to_i64(const int32_t* in, int64_t n, int64_t* out, void* stream)
 
 /* Number of CUDA kernels this library has launched in the calling process (monotonic). */
 int64_t sgnn_launch_count(void);
-
-/* Test / A-B hook: choose among kernel generations that compute the same thing.
- *   FFMA convolution (all bit-identical): 0 default row-owner kernel, 1 tile kernels, 2 runtime-shape kernel, 3-7, 10, 11
- *   variants of the row-owner policy.
- *   Tensor-core fp32 convolution (sgnn_conv_forward_tc32; all within the same tolerance): 0 default (single-role regular
- *   kernel + warp-specialised child kernel), 21 one filter offset per work item, 23 warp-specialised regular kernel,
- *   24 A operand through tensor memory, 27 input rows pre-split into bf16 planes once per layer, 25 single-role child
- *   kernel, 26 one offset per item for 32-channel inputs, 28 EXPERIMENTAL (never run on a GPU yet): distinct rows of a
- *   tile staged once in shared memory.   30: one-thread-per-output transposed dense convolution. */
-void sgnn_debug_set_conv_impl(int impl);
-
-/* Tuning hook: under SGNN_GEN_TC32 only convolutions with at least n output rows use the tensor-core path (default 60000). */
-void sgnn_debug_set_tc32_min_rows(int64_t n);
-/* Tuning hook: under SGNN_GEN_TC32 site sets with at least n rows get a tile plan and run their K = 27, Cout = 16
- * convolutions through sgnn_conv_forward_tc32_ur (default 1000). */
-void sgnn_debug_set_ur_min_rows(int64_t n);
 
 /* Watchdog record of sgnn_conv_forward_tc32_ur: a barrier wait that exceeds ~2 s traps the kernel (the call chain then
  * reports SGNN_E_CUDA) after writing where it stood; out128[0] != 0 when a record exists (128 words, see csrc/conv_ur.cu). */

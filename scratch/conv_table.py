@@ -13,14 +13,13 @@ import sgnn_b200                                        # noqa: E402
 from sgnn_b200._lib import lib                          # noqa: E402
 from sgnn_b200.synth import fill_parameters, synthetic_batch   # noqa: E402
 
-ur_min = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
-tc_min = int(sys.argv[2]) if len(sys.argv) > 2 else 60000
-lib.sgnn_debug_set_ur_min_rows(ur_min)
-lib.sgnn_debug_set_tc32_min_rows(tc_min)
+ur_min = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+tc_min = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 m = sgnn_b200.GenModel(8, 64, 1, 16, 16, 4, True, True, 1, 1)
 fill_parameters(m, 0)
 m = m.cuda().eval()
 m.conv_mode = 'tc32'
+m.ur_min_rows, m.tc32_min_rows = ur_min, tc_min
 locs, feats = synthetic_batch(32, 64, 0.05)
 locs, feats = locs.cuda(), feats.cuda()
 ones = np.ones(5, dtype=np.float32)

@@ -17,8 +17,6 @@ m = sgnn_b200.GenModel(8, 64, 1, 16, 16, 4, True, True, 1, 1)
 fill_parameters(m, 0)
 m = m.cuda().eval()
 m.conv_mode = mode
-from sgnn_b200._lib import lib                          # noqa: E402
-lib.sgnn_debug_set_conv_impl(int(os.environ.get('SGNN_CONV_IMPL', '0')))
 locs, feats = synthetic_batch(32, 64, 0.05)
 locs, feats = locs.cuda(), feats.cuda()
 ones = np.ones(5, dtype=np.float32)

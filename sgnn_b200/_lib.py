@@ -72,7 +72,8 @@ class SgnnSurfaceW(C.Structure):
 class SgnnGeneratorW(C.Structure):
     _fields_ = [('enc', SgnnEncLevelW * 3), ('dense', SgnnDenseLayerW * 6), ('w_heads', C.c_void_p),
                 ('nf_coarse', C.c_int32), ('reserved', C.c_int32), ('ref', SgnnRefineW * 3), ('surf', SgnnSurfaceW),
-                ('prepared', C.c_void_p), ('prepared_bytes', C.c_size_t)]
+                ('prepared', C.c_void_p), ('prepared_bytes', C.c_size_t), ('tc32_min_rows', C.c_int64),
+                ('ur_min_rows', C.c_int64)]
 
 
 class SgnnGeneratorOut(C.Structure):
@@ -101,7 +102,6 @@ SIGNATURES = {
     'sgnn_rulebook_strided': (_I, [_G, _P, _L, _P, _P, _L, _P]),
     'sgnn_conv_forward': (_I, [C.POINTER(SgnnConvArgs), _P]),
     'sgnn_conv_tc32_workspace_bytes': (_Z, [_I, _I, _I]),
-    'sgnn_conv_tc32_workspace_bytes_rows': (_Z, [_I, _I, _I, _L]),
     'sgnn_conv_forward_tc32': (_I, [C.POINTER(SgnnConvArgs), _P, _Z, _P]),
     'sgnn_conv_tc32_prepare': (_I, [_P, _I, _I, _I, _I, _P, _Z, _P]),
     'sgnn_generator_prepared_bytes': (_Z, [C.POINTER(SgnnGeneratorW)]),
@@ -137,9 +137,6 @@ SIGNATURES = {
     'sgnn_children_coords': (_I, [_P, _L, _P, _P]),
     'sgnn_concat_skip': (_I, [_G, _P, _I, _I, _P, _L, _P, _I, _I, _P]),
     'sgnn_coords_to_i64': (_I, [_P, _L, _P, _P]),
-    'sgnn_debug_set_conv_impl': (None, [_I]),
-    'sgnn_debug_set_tc32_min_rows': (None, [_L]),
-    'sgnn_debug_set_ur_min_rows': (None, [_L]),
     'sgnn_debug_ur_diag': (_I, [_P]),
     'sgnn_debug_ffma_peak': (_I, [_I, C.POINTER(C.c_double), _P]),
     'sgnn_launch_count': (_L, []),

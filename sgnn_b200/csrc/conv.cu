@@ -17,7 +17,6 @@
 #define CHUNK 16       // input channels per stage
 #define XS (CHUNK + 4) // X tile row stride (floats)
 
-int g_sgnn_conv_impl = 0;  // tuning hook, see sgnn_debug_set_conv_impl
 
 struct ConvParams {
   const float* in;
@@ -243,142 +242,6 @@ conv_gather_f32_kernel(ConvParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// v2 tile kernel: channel counts are compile-time (every loop unrolls, every LDS has an immediate
-// offset), the 27 x 128 neighbour indices of the tile are fetched ONCE into shared memory (coalesced;
-// the child-mode offset arithmetic is paid once per entry, not once per copied chunk), the filter bank
-// is streamed one offset per stage next to the gathered rows (3 KB instead of 83 KB resident -> 2-4 CTAs
-// per SM), dead offsets (no live neighbour in the tile) are skipped without a barrier, and the
-// cp.async ring is NS deep with a single __syncthreads per stage.
-// Same arithmetic as the v1 kernel: k ascending, ci ascending, one fmaf chain per output element.
-template <int CINP>
-struct TileCfg {
-  static constexpr int XS2 = (CINP % 8 == 4) ? CINP : CINP + 4;  // row stride == 4 (mod 8) words: conflict-free LDS.128
-  static constexpr int NS = CINP >= 28 ? 2 : 3;
-  static constexpr int CPR = CINP / 4;
-};
-
-template <int COUT, int CINP>
-__global__ void __launch_bounds__(NSG * (COUT / 4), (CINP >= 28 ? 2 : 4))
-conv_tile_f32_kernel(ConvParams p) {
-  constexpr int NCG = COUT / 4;
-  constexpr int NT = NSG * NCG;
-  constexpr int XS2 = TileCfg<CINP>::XS2;
-  constexpr int NS = TileCfg<CINP>::NS;
-  constexpr int CPR = TileCfg<CINP>::CPR;
-  constexpr int XT = TM * XS2;
-  constexpr int WT = CINP * COUT;
-  constexpr int PAIRS = TM * CPR;
-  extern __shared__ __align__(16) float smem[];
-  int* idx_s = reinterpret_cast<int*>(smem);  // [27][TM]
-  float* stage0 = smem + 27 * TM;              // NS x (X tile [TM][XS2] + W slice [CINP][COUT])
-  __shared__ unsigned live_mask_s;
-
-  const int tid = threadIdx.x;
-  const int sg = tid / NCG, cg = tid % NCG;
-  const long long tile_base = (long long)blockIdx.x * TM;
-
-  if (tid == 0) live_mask_s = 0u;
-  // zero the weight rows of the channel padding once (cp.async only ever writes rows < cin)
-  for (int b = 0; b < NS; ++b) {
-    float* Wd = stage0 + b * (XT + WT) + XT;
-    for (int q = p.cin * COUT + tid; q < WT; q += NT) Wd[q] = 0.f;
-  }
-  __syncthreads();
-  unsigned my_live = 0u;
-  for (int e = tid; e < p.K * TM; e += NT) {
-    const int k = e / TM, site = e % TM;
-    const long long j = tile_base + site;
-    const int r = (j < p.n_out) ? conv_src_row(p, j, k) : -1;
-    idx_s[e] = r;
-    if (r >= 0) my_live |= 1u << k;
-  }
-  my_live = __reduce_or_sync(0xffffffffu, my_live);
-  if ((tid & 31) == 0 && my_live) atomicOr(&live_mask_s, my_live);
-  __syncthreads();
-  unsigned issue_mask = live_mask_s;
-  const int S = __popc(issue_mask);
-
-  float acc[TS][4];
-#pragma unroll
-  for (int t = 0; t < TS; ++t)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[t][c] = 0.f;
-
-  auto issue = [&](int k, int buf) {
-    float* X = stage0 + buf * (XT + WT);
-    float* Wd = X + XT;
-    const int* idk = idx_s + k * TM;
-#pragma unroll
-    for (int it = 0; it < (PAIRS + NT - 1) / NT; ++it) {
-      const int pi = tid + it * NT;
-      if (PAIRS % NT != 0 && pi >= PAIRS) break;
-      const int site = pi / CPR, ch = pi % CPR;
-      const int r = idk[site];
-      float* dst = X + site * XS2 + ch * 4;
-      if (r >= 0) {
-        const float* src = p.in + (long long)r * p.ld_in + ch * 4;
-        if (ch * 4 + 4 <= p.cin) {
-          cp_async16(dst, src);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (ch * 4 + e < p.cin) cp_async4(dst + e, src + e);
-            else dst[e] = 0.f;
-          }
-        }
-      } else {
-        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    const float* Wk = p.weight + (size_t)k * p.cin * COUT;
-    for (int q = tid; q < p.cin * NCG; q += NT) cp_async16(Wd + q * 4, Wk + q * 4);
-  };
-
-#pragma unroll
-  for (int i = 0; i < NS - 1; ++i) {
-    if (issue_mask) {
-      const int k = __ffs(issue_mask) - 1;
-      issue_mask &= issue_mask - 1;
-      issue(k, i);
-    }
-    cp_async_commit();
-  }
-  for (int s = 0; s < S; ++s) {
-    cp_async_wait<NS - 2>();
-    __syncthreads();
-    if (issue_mask) {
-      const int k = __ffs(issue_mask) - 1;
-      issue_mask &= issue_mask - 1;
-      issue(k, (s + NS - 1) % NS);
-    }
-    cp_async_commit();
-    const float* X = stage0 + (s % NS) * (XT + WT);
-    const float* Wd = X + XT + cg * 4;
-    const float* Xr = X + sg * XS2;
-#pragma unroll
-    for (int c4 = 0; c4 < CINP; c4 += 4) {
-      float4 xv[TS];
-#pragma unroll
-      for (int t = 0; t < TS; ++t) xv[t] = *reinterpret_cast<const float4*>(Xr + NSG * t * XS2 + c4);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float4 w = *reinterpret_cast<const float4*>(Wd + (c4 + e) * COUT);
-#pragma unroll
-        for (int t = 0; t < TS; ++t) {
-          const float x = e == 0 ? xv[t].x : e == 1 ? xv[t].y : e == 2 ? xv[t].z : xv[t].w;
-          acc[t][0] = fmaf(x, w.x, acc[t][0]);
-          acc[t][1] = fmaf(x, w.y, acc[t][1]);
-          acc[t][2] = fmaf(x, w.z, acc[t][2]);
-          acc[t][3] = fmaf(x, w.w, acc[t][3]);
-        }
-      }
-    }
-  }
-  cp_async_wait<0>();
-  conv_epilogue<COUT>(p, acc, tile_base, sg, cg);
-}
-
-// ------------------------------------------------------------------------------------------------
 // Child-mode kernel (generative upsampling, model.py:192-207,224-225): the n1 convolution over
 // the 8 children of every site.  A tile is 16 parents = 128 outputs.  The 27 parent-neighbour rows of each
 // parent are staged in shared memory ONCE (16 x 27 rows) and serve all 8 children x 27 offsets -- 8x less
@@ -386,6 +249,11 @@ conv_tile_f32_kernel(ConvParams p) {
 // current offset streams (double buffered).  Thread (g, w, cg): parents {g, g+8}, children {w, w+4},
 // channels [4cg, 4cg+4): the 8 lane groups of a warp read 8 different parents of the same (child, offset),
 // i.e. 8 rows at stride 27*XS -- conflict free.  Arithmetic order identical to the generic kernels.
+template <int CINP>
+struct TileCfg {
+  static constexpr int XS2 = (CINP % 8 == 4) ? CINP : CINP + 4;  // row stride == 4 (mod 8) words: conflict-free LDS.128
+};
+
 template <int COUT, int CINP>
 __global__ void __launch_bounds__(NSG * (COUT / 4), 2)
 conv_child_f32_kernel(ConvParams p) {
@@ -539,45 +407,6 @@ static int launch_child(const ConvParams& p, cudaStream_t st) {
   }
   conv_child_f32_kernel<COUT, CINP><<<(int)tiles, NT, smem, st>>>(p);
   SGNN_CHECK_LAUNCH();
-  return SGNN_OK;
-}
-
-template <int COUT, int CINP>
-static int launch_tile(const ConvParams& p, cudaStream_t st) {
-  constexpr int NT = NSG * (COUT / 4);
-  const size_t smem = ((size_t)27 * TM + (size_t)TileCfg<CINP>::NS * (TM * TileCfg<CINP>::XS2 + CINP * COUT)) *
-                      sizeof(float);
-  const long long tiles = (p.n_out + TM - 1) / TM;
-  if (tiles > 0x7fffffff) return SGNN_E_TOO_LARGE;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SGNN_CUDA(cudaFuncSetAttribute(conv_tile_f32_kernel<COUT, CINP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
-    attr_set = true;
-  }
-  conv_tile_f32_kernel<COUT, CINP><<<(int)tiles, NT, smem, st>>>(p);
-  SGNN_CHECK_LAUNCH();
-  return SGNN_OK;
-}
-
-// (cin padded to 4, cout) pairs of the SG-NN channel plan get the v2 kernel
-static int dispatch_tile(const ConvParams& p, cudaStream_t st, bool* handled) {
-  const int cinp = (p.cin + 3) & ~3;
-  *handled = true;
-#define SGNN_TILE_CASE(CO, CI) \
-  if (p.cout == CO && cinp == CI) return launch_tile<CO, CI>(p, st);
-  SGNN_TILE_CASE(8, 4)
-  SGNN_TILE_CASE(8, 8)
-  SGNN_TILE_CASE(12, 8)
-  SGNN_TILE_CASE(12, 12)
-  SGNN_TILE_CASE(16, 12)
-  SGNN_TILE_CASE(16, 16)
-  SGNN_TILE_CASE(16, 28)
-  SGNN_TILE_CASE(16, 32)
-  SGNN_TILE_CASE(16, 36)
-  SGNN_TILE_CASE(16, 48)
-#undef SGNN_TILE_CASE
-  *handled = false;
   return SGNN_OK;
 }
 
@@ -818,18 +647,14 @@ static int launch_ro(const ConvParams& p, bool vec, cudaStream_t st) {
 }
 
 // exact (cin, cout) pairs of the SG-NN channel plan
-static int dispatch_ro(const ConvParams& p, bool vec, cudaStream_t st, bool* handled, int alt) {
+static int dispatch_ro(const ConvParams& p, bool vec, cudaStream_t st, bool* handled) {
   *handled = true;
   // Rows per thread by launch size: S=4 amortises the weight reads best but makes 512-row CTAs; a launch that cannot
   // fill the chip (148 SMs x 3 CTAs) with those is latency bound (ncu: 45-80 us floors on the coarse levels), so
   // mid-size launches use S=2 and small ones S=1 (4x more, 4x shorter CTAs).
   if (p.child_mode && !vec) { *handled = false; return SGNN_OK; }
-  long long t4 = 300000, t2 = 90000;
-  if (g_sgnn_conv_impl == 10) { t4 = 150000; t2 = 40000; }     // A/B: thresholds of the rows-per-thread policy
-  if (g_sgnn_conv_impl == 11) { t4 = 600000; t2 = 200000; }
-  int sz = p.n_out >= t4 ? 4 : (p.n_out >= t2 ? 2 : 1);
-  if (g_sgnn_conv_impl == 6 && sz == 4) sz = 2;   // A/B: never 4 rows per thread
-  if (g_sgnn_conv_impl == 7 && sz == 1) sz = 2;   // A/B: never 1 row per thread
+  const long long t4 = 300000, t2 = 90000;
+  const int sz = p.n_out >= t4 ? 4 : (p.n_out >= t2 ? 2 : 1);
 #define SGNN_RO_CASE(CO, CI, SS, CHH) \
   if (p.cout == CO && p.cin == CI) return launch_ro<CO, CI, SS, CHH>(p, vec, st);
 #define SGNN_RO_SIZED(CO, CI, CHH)              \
@@ -844,7 +669,7 @@ static int dispatch_ro(const ConvParams& p, bool vec, cudaStream_t st, bool* han
   SGNN_RO_SIZED(12, 12, 12)
   SGNN_RO_SIZED(16, 12, 12)
   SGNN_RO_SIZED(16, 16, 16)
-  if (alt) {   // wide inputs: one stage per offset (whole padded row)
+  {   // wide inputs: one stage per offset (whole padded row)
     if (sz >= 2) {
       SGNN_RO_CASE(16, 26, 2, 28)
       SGNN_RO_CASE(16, 30, 2, 32)
@@ -857,10 +682,6 @@ static int dispatch_ro(const ConvParams& p, bool vec, cudaStream_t st, bool* han
       SGNN_RO_CASE(16, 48, 1, 24)
     }
   }
-  SGNN_RO_CASE(16, 26, 4, 16)
-  SGNN_RO_CASE(16, 30, 4, 16)
-  SGNN_RO_CASE(16, 34, 4, 16)
-  SGNN_RO_CASE(16, 48, 4, 16)
 #undef SGNN_RO_SIZED
 #undef SGNN_RO_CASE
   *handled = false;
@@ -897,15 +718,6 @@ __global__ void conv_gather_f32_generic_kernel(ConvParams p) {
       p.out_b[j * p.ld_b + co] = y;
     }
   }
-}
-
-// (declared near the top of the file) 0 (default): v4 row-owner kernel, whole-row stages for wide inputs, parent-staged kernel for child mode;
-// 1: v2 tile kernels; 2: v1 runtime-shape kernel; 3: v4 only (whole-row stages for wide inputs); 4: v4 with
-// 16-channel sub-stages + child kernel; 5: v4 with 16-channel sub-stages only.  Tuning hook, all bit-identical.
-extern int g_sgnn_dense_impl;   // dense.cu
-extern "C" void sgnn_debug_set_conv_impl(int v) {
-  g_sgnn_dense_impl = v == 30 ? 1 : 0;
-  g_sgnn_conv_impl = v == 30 ? 0 : v;
 }
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -974,17 +786,9 @@ extern "C" int sgnn_conv_forward(const SgnnConvArgs* a, void* stream) {
     const bool vec = aligned16(a->in) && (a->ld_in & 3) == 0;
     {
       bool handled = false;
-      if (vec && p.child_mode && p.cout == 16 && p.cin == 48 && (p.n_out & 7) == 0 &&
-          (g_sgnn_conv_impl == 0 || g_sgnn_conv_impl == 4 || g_sgnn_conv_impl >= 6))
-        return launch_child<16, 48>(p, st);
-      if (g_sgnn_conv_impl == 0 || g_sgnn_conv_impl >= 3) {
-        rc = dispatch_ro(p, vec, st, &handled, g_sgnn_conv_impl == 0 || g_sgnn_conv_impl == 3 || g_sgnn_conv_impl >= 6);
-        if (handled) return rc;
-      }
-      if (vec && g_sgnn_conv_impl <= 1) {
-        rc = dispatch_tile(p, st, &handled);
-        if (handled) return rc;
-      }
+      if (vec && p.child_mode && p.cout == 16 && p.cin == 48 && (p.n_out & 7) == 0) return launch_child<16, 48>(p, st);
+      rc = dispatch_ro(p, vec, st, &handled);
+      if (handled) return rc;
     }
     switch (a->cout) {
       case 4: return launch_conv<4>(p, vec, st);

@@ -9,7 +9,6 @@
 // and relu.  The input may be the channel concatenation of two tensors (torch.cat of model.py:156,160).
 #include "common.cuh"
 
-int g_sgnn_dense_impl = 0;   // A/B hook (sgnn_debug_set_conv_impl 30): 1 = one-thread-per-output transposed convolution
 
 struct DenseArgs {
   const float* in0; int c0;
@@ -292,7 +291,7 @@ static int dense_launch(bool transposed, const float* in0, int c0, const float* 
     if (ks == 4) dense_conv3d_fast_kernel<4><<<fb, 64, 0, (cudaStream_t)stream>>>(a);
     else dense_conv3d_fast_kernel<1><<<fb, 64, 0, (cudaStream_t)stream>>>(a);
   } else if (transposed && ks == 4 && stride == 2 && pad == 1 && cout % DCT_CO == 0 && (c0 + c1) * 8 * DCT_CO * 4 <= 48 * 1024 &&
-             g_sgnn_dense_impl == 0) {
+             true) {
     // outputs = 8 parity classes x (nb x input cells): the extents are exactly twice the input's
     const long long cells = (long long)nb * d0 * d1 * d2;
     dim3 grid((unsigned)sgnn_blocks(cells, 128, 4096), (unsigned)(8 * (cout / DCT_CO)));

@@ -8,14 +8,13 @@
 #include <string.h>
 #include "common.cuh"
 
-// SGNN_GEN_TC32: convolutions with fewer output rows stay on the FFMA kernels (a launch that cannot fill the chip with
-// 128-row tiles is latency bound either way, and the FFMA kernel's per-tile latency is shorter)
-extern int g_sgnn_conv_impl;   // conv.cu
-long long g_sgnn_tc32_min_rows = 60000;
-extern "C" void sgnn_debug_set_tc32_min_rows(int64_t n) { g_sgnn_tc32_min_rows = n; }
-// site sets with at least this many rows get a unique-row tile plan (conv_ur.cu) for their Cout = 16 submanifold convolutions
-long long g_sgnn_ur_min_rows = 1000;
-extern "C" void sgnn_debug_set_ur_min_rows(int64_t n) { g_sgnn_ur_min_rows = n; }
+// Row thresholds of the tensor-core paths under SGNN_GEN_TC32 (SgnnGeneratorW::tc32_min_rows / ur_min_rows override them):
+//  * site sets with at least UR rows get a unique-row tile plan (conv_ur.cu / conv_urc.cu) for their K = 27, Cout = 16
+//    convolutions and their child-mode convolution;
+//  * other Cout = 16 convolutions (stride-2, or no plan) with at least TC32 output rows run on the round-1 tcgen05 kernels; below
+//    that a launch cannot fill the chip with 128-row tiles and the FFMA kernel's shorter per-tile latency wins.
+#define SGNN_DEFAULT_TC32_MIN_ROWS 60000
+#define SGNN_DEFAULT_UR_MIN_ROWS 1000
 
 namespace {
 
@@ -41,6 +40,7 @@ struct Ctx {
   bool tc32;
   int n_ev;
   const SgnnGeneratorW* w;
+  long long tc32_min_rows, ur_min_rows;
 };
 
 // event pool for SGNN_GEN_PROFILE (pairs around every sgnn_conv_forward of the pass)
@@ -109,7 +109,7 @@ static int build_plan(Ctx& c, Level* L, int cout) {
   L->plan = nullptr;
   // (the kernel also takes Cout 8 / 12, but on the 5 %-occupancy encoder levels its per-tile overhead loses to the FFMA kernel:
   // 87-95 us against 68-72 us for 420 k rows, measured)
-  if (!c.tc32 || cout != 16 || !L->nbr || L->n < g_sgnn_ur_min_rows) return SGNN_OK;
+  if (!c.tc32 || cout != 16 || !L->nbr || L->n < c.ur_min_rows) return SGNN_OK;
   const size_t pb = sgnn_tile_plan_bytes(L->n);
   void* plan = c.ar.get(pb);
   if (!plan) return SGNN_E_NOMEM;
@@ -265,11 +265,9 @@ static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr,
     if (!ws) return SGNN_E_NOMEM;
     rc = sgnn_conv_forward_tc32_ur(&x, plan, ws, wb, c.stream);
     used_tc = rc == SGNN_OK;
-  } else if (c.tc32 && cout == 16 && cin >= 12 && cin <= 48 && (!child || cin == 48) && n_out >= g_sgnn_tc32_min_rows) {
-    // room for the pre-split input planes only when that kernel generation is selected (hook 27)
-    const size_t wb = g_sgnn_conv_impl == 27 ? sgnn_conv_tc32_workspace_bytes_rows(K, cin, child, x.n_in)
-                                             : sgnn_conv_tc32_workspace_bytes(K, cin, child);
-    void* ws = g_sgnn_conv_impl == 27 ? nullptr : prepared_bank(c.w, w, K, child);
+  } else if (c.tc32 && cout == 16 && cin >= 12 && cin <= 48 && (!child || cin == 48) && n_out >= c.tc32_min_rows) {
+    const size_t wb = sgnn_conv_tc32_workspace_bytes(K, cin, child);
+    void* ws = prepared_bank(c.w, w, K, child);
     if (ws) x.flags |= SGNN_CONV_PREPARED;
     else ws = c.ar.get(wb);
     if (!ws) return SGNN_E_NOMEM;
@@ -388,6 +386,8 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
   c.profile = (flags & SGNN_GEN_PROFILE) != 0; c.n_ev = 0;
   c.tc32 = (flags & SGNN_GEN_TC32) != 0;
   c.w = w;
+  c.tc32_min_rows = w->tc32_min_rows > 0 ? w->tc32_min_rows : SGNN_DEFAULT_TC32_MIN_ROWS;
+  c.ur_min_rows = w->ur_min_rows > 0 ? w->ur_min_rows : SGNN_DEFAULT_UR_MIN_ROWS;
   int rc = SGNN_OK;
   do {
 #define GEN(call)                 \

@@ -10,7 +10,6 @@
 #define T32_COLS 128   // TMEM columns of the regular kernel: 7 main accumulators (16 each) + the correction accumulator
 #define T32_CORR 112u
 
-extern int g_sgnn_conv_impl;
 
 struct Tc32Params {
   const float* in; int ld_in; int cin; int cout;   // cout: 16, or 8 / 12 (unique-row kernel: accumulator columns >= cout are zero)

@@ -192,7 +192,7 @@ def conv(x, nbr, weight, n_out, out_a, child_mode=False, residual=None, scale_a=
         check(lib.sgnn_conv_forward_tc32_ur(C.byref(a), _ptr(plan), C.c_void_p(ws.data_ptr()), wb, _stream()),
               'sgnn_conv_forward_tc32_ur')
     elif tc32:
-        wb = lib.sgnn_conv_tc32_workspace_bytes_rows(K, cin, a.child_mode, a.n_in)
+        wb = lib.sgnn_conv_tc32_workspace_bytes(K, cin, a.child_mode)
         ws = _scratch(wb, x.device)
         check(lib.sgnn_conv_forward_tc32(C.byref(a), C.c_void_p(ws.data_ptr()), wb, _stream()), 'sgnn_conv_forward_tc32')
     else:

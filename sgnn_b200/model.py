@@ -224,6 +224,8 @@ class GenModel(nn.Module):
         # fmaf order of the FFMA kernels);  'exact': every convolution on the fixed-order FFMA kernels -- bit-reproducible,
         # == oracle/o3.c, and bit-identical to forward_fused / forward_modules.
         self.conv_mode = 'tc32'
+        self.tc32_min_rows = 0       # row thresholds of the tensor-core paths (0 = library defaults, SgnnGeneratorW)
+        self.ur_min_rows = 0
 
     # model.py:357-369.  The sizes are upper bounds of mode-0 InputLayers; the reference doubles
     # refine_max_dim inside the k loop -- mirrored, not "fixed": bounds only grow.

@@ -139,6 +139,8 @@ class NativeGenerator(object):
         if nb is None:
             nb = int(locs[:, 3].max().item()) + 1 if locs.shape[0] else 1
         out = _lib.SgnnGeneratorOut()
+        self.weights.w.tc32_min_rows = int(getattr(m, 'tc32_min_rows', 0))
+        self.weights.w.ur_min_rows = int(getattr(m, 'ur_min_rows', 0))
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         for _ in range(8):
             rc = lib.sgnn_generator_forward(C.byref(self.weights.w), C.c_void_p(locs.data_ptr()),

@@ -22,27 +22,6 @@ def _E():
     return E
 
 
-_EXPERIMENTAL = pytest.mark.skipif(not os.environ.get('SGNN_EXPERIMENTAL'),
-                                   reason='kernel generation written without GPU access; set SGNN_EXPERIMENTAL=1 to run it')
-
-
-@pytest.fixture(autouse=True, params=[0, 23, 24, 25, 27, pytest.param(28, marks=_EXPERIMENTAL)],
-                ids=['default', 'warp-specialised', 'tmem-operand', 'child-single-role', 'presplit-planes',
-                     'unique-rows-experimental'])
-def tc_impl(request):
-    """Every generation of the regular tensor-core kernel: 0 = every warp gathers, thread 0 issues the MMAs;
-    23 = producer warps + MMA-issuer warp with a two-stage shared-memory ring and double-buffered TMEM accumulators;
-    24 = as 23 but the A operand is written to tensor memory (tcgen05.st) and the MMAs read it from there;
-    25 = regular kernel as 0, child-mode convolution on the single-role kernel instead of the warp-specialised one;
-    27 = as 24 but the input rows are split into bf16 planes once per layer (pre-pass) and gathered straight into TMEM;
-    28 = (experimental, opt-in) every distinct input row of a tile staged once in shared memory, taps expanded from there."""
-    from sgnn_b200._lib import lib
-    lib.sgnn_debug_set_conv_impl(request.param)
-    yield request.param
-    lib.sgnn_debug_set_conv_impl(0)
-    lib.sgnn_debug_set_tc32_min_rows(60000)     # _model() lowers it to 0 so that every eligible layer is covered
-
-
 def _bound(x, nbr, w, n_out, child_mode=False):
     """sum over the rules of |x| @ |w|: the magnitude the rounding errors scale with."""
     return o3.conv(x.abs(), nbr, w.abs(), n_out, child_mode=child_mode)
@@ -177,8 +156,7 @@ def _model(dims, seed, mode):
     m = sgnn_b200.GenModel(8, list(dims), 1, 16, 16, 4, True, True, 1, 1)
     fill_parameters(m, seed)
     m.conv_mode = mode
-    from sgnn_b200._lib import lib
-    lib.sgnn_debug_set_tc32_min_rows(0 if mode == 'tc32' else 60000)   # tests: every eligible layer on the tensor cores
+    m.tc32_min_rows = m.ur_min_rows = 1          # tests: every eligible layer on the tensor cores, every site set planned
     return m.cuda().eval()
 
 
