@@ -34,18 +34,32 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--blocks', type=int, default=32, help='64^3 blocks per GPU per step')
+    ap.add_argument('--blocks', type=int, default=0, help='64^3 blocks per GPU per step (0: 32, or 512 for --config 3)')
     ap.add_argument('--sets', type=int, default=4, help='distinct input batches rotated across steps')
     ap.add_argument('--param-seed', type=int, default=0)
-    ap.add_argument('--cpu-blocks', type=int, default=1, help='blocks per CPU-baseline forward')
+    ap.add_argument('--cpu-blocks', type=int, default=0, help='blocks per CPU forward: 0 = 8 for the cpu_baseline sample of the '
+                    'B200 arm, --blocks (the same workload) for --impl reference')
     ap.add_argument('--cpu-reps', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ledger', default='', help='write the per-layer ledger JSON here')
+    ap.add_argument('--config', type=int, default=1, choices=[1, 2, 3, 4],
+                    help='BASELINE.json configs[i]: 1 = 32 blocks per GPU (default), 3 = 512 blocks per GPU (4096 over 8 GPUs), '
+                         '2 = one 128^3 block bf16 Convolution+Deconvolution, 4 = 10 M-site rulebook build')
     ap.add_argument('--conv-mode', default='tc32', choices=['exact', 'tc32'],
                     help="exact: fixed-order FFMA convolutions; tc32: Cout=16 convolutions on tcgen05 (3-way bf16 split)")
     ap.add_argument('--tc32-min-rows', type=int, default=0, help='GenModel.tc32_min_rows (A/B runs; 0 = default)')
     ap.add_argument('--ur-min-rows', type=int, default=0, help='GenModel.ur_min_rows (A/B runs; 0 = default)')
     return ap.parse_args()
+
+
+def load_synth():
+    """sgnn_b200/synth.py by FILE PATH: importing it as part of the package would run sgnn_b200/__init__.py and map the product
+    libsgnn_b200.so into the reference arm's process (numpy / torch only, no package-relative imports)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('sgnn_synth', os.path.join(ROOT, 'sgnn_b200', 'synth.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -60,7 +74,8 @@ def cpu_forward_rate(n_blocks, reps, seed, first_block=0):
     This is the ONE place bench.py executes oracle code: as the thing the B200 arm is compared with."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     from genmodel import OracleGenModel
-    from sgnn_b200.synth import fill_parameters, synthetic_batch
+    synth = load_synth()
+    fill_parameters, synthetic_batch = synth.fill_parameters, synth.synthetic_batch
     cores = cpu_threads()
     torch.set_num_threads(cores)
     m = OracleGenModel()
@@ -82,40 +97,51 @@ def cpu_forward_rate(n_blocks, reps, seed, first_block=0):
 
 
 def run_reference(args):
+    """Reference arm: the CPU path (oracle port of model.py on the restated SparseConvNet-CPU ops) on the SAME workload as the
+    B200 arm -- `--blocks` 64^3 blocks per step, exactly --steps timed steps after --warmup warm-ups (3
+    warm-ups, median of >= 10 also reported), all usable host threads.  A 9-minute budget bounds a slow box: steps not run
+    are reported as such.  This process never loads the product library."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    # each "step" = one forward over a bounded sample (cpu_blocks blocks) of the same workload
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     from genmodel import OracleGenModel
-    from sgnn_b200.synth import fill_parameters, synthetic_batch
+    synth = load_synth()
     cores = cpu_threads()
     torch.set_num_threads(cores)
     m = OracleGenModel()
-    fill_parameters(m, args.param_seed)
+    synth.fill_parameters(m, args.param_seed)
     m.eval()
-    steps = min(args.steps, 8)
-    warm = min(args.warmup, 1)
-    vox, t_total = 0, 0.0
+    steps, warm = max(args.steps, 1), max(args.warmup, 0)
+    blocks = args.cpu_blocks if args.cpu_blocks > 0 else args.blocks
+    batches = [synth.synthetic_batch(blocks, 64, 0.05, first=s * blocks) for s in range(args.sets)]
+    times, vox = [], []
+    t_begin = time.perf_counter()
     with torch.no_grad():
         for s in range(warm + steps):
-            locs, feats = synthetic_batch(args.cpu_blocks, 64, 0.05, first=s * args.cpu_blocks)
+            locs, feats = batches[s % args.sets]
             t0 = time.perf_counter()
             m(locs, feats)
             dt = time.perf_counter() - t0
             if s >= warm:
-                vox += locs.shape[0]
-                t_total += dt
-    value = vox / t_total
+                times.append(dt)
+                vox.append(locs.shape[0])
+            if time.perf_counter() - t_begin > 540 and len(times) >= 3:
+                break
+    t_total = float(sum(times))
+    value = sum(vox) / t_total
+    done = len(times)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * t_total / steps, 'higher_is_better': True,
+        'steps': done, 'warmup': warm, 'ms_per_step': 1e3 * t_total / done, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'configs[1] sampled: %d x 64^3 block(s) @5%% per step, full 3-level generator'
-                               % args.cpu_blocks, 'host': 'cpu'},
+        'config': {'workload': 'BASELINE configs[1]: %d synthetic 64^3 TSDF blocks @5%% per step, full 3-level coarse-to-fine '
+                               'generator, fp32' % blocks, 'blocks_per_step': blocks, 'host': 'cpu',
+                   'steps_requested': steps, 'median_ms_per_step': 1e3 * float(np.median(times)),
+                   'product_library_loaded': any('libsgnn_b200' in l for l in open('/proc/self/maps'))},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': '%d forward(s) of %d block(s); restated SparseConvNet-CPU path (oracle O2) '
-                                   'under the oracle port of model.py' % (steps, args.cpu_blocks)},
+                         'sample': '%d timed forward(s) of %d block(s) after %d warm-up(s); restated SparseConvNet-CPU path '
+                                   '(oracle O2) under the oracle port of model.py' % (done, blocks, warm)},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -180,6 +206,16 @@ class ConvProfiler(object):
         return ConvProfiler._Ctx(self, rec)
 
 
+def kernel_source_hash():
+    """sha256 over the CUDA sources: profiles/conv_dram_traffic.json (an ncu capture) is only quoted for the kernels it measured."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, 'sgnn_b200', 'csrc', '*.cu*'))):
+        h.update(open(f, 'rb').read())
+    return h.hexdigest()
+
+
 def child_rule_count(nbr):
     """Rules of the child-mode convolution = for each parent/child/offset with an existing parent neighbour."""
     present = (nbr >= 0).view(3, 3, 3, -1).float()           # [pz,py,px, n]
@@ -204,6 +240,20 @@ def run_b200(args):
         raise SystemExit('bench.py: the B200 arm needs a CUDA device (no CPU fallback)')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    # one slice of the host cores per rank: the host side of the e2e path (pinned copies, launches) otherwise migrates
+    # between cores shared by all ranks (round 1: e2e scaling 0.917 at N = 8 with every GPU reporting the same CPU affinity)
+    bound = None
+    try:
+        cores_all = sorted(os.sched_getaffinity(0))
+        lw = int(os.environ.get('LOCAL_WORLD_SIZE', str(world)))
+        if lw > 1 and len(cores_all) >= 2 * lw:
+            per = len(cores_all) // lw
+            mine = cores_all[local * per:(local + 1) * per]
+            os.sched_setaffinity(0, mine)
+            torch.set_num_threads(max(1, min(per, 8)))
+            bound = '%d-%d' % (mine[0], mine[-1])
+    except Exception:
+        pass
     if world > 1:
         if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
             os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: ONE JSON line
@@ -219,11 +269,13 @@ def run_b200(args):
     model.conv_mode = args.conv_mode
     model.tc32_min_rows, model.ur_min_rows = args.tc32_min_rows, args.ur_min_rows
 
+    if args.blocks <= 0:
+        args.blocks = 512 if args.config == 3 else 32
     # inputs: `sets` distinct batches per rank (global block id = (set*world + rank)*blocks + i), resident in HBM
     host, resident = [], []
     for s in range(args.sets):
         locs, feats = synthetic_batch(args.blocks, 64, 0.05, first=(s * world + rank) * args.blocks)
-        host.append((locs.pin_memory(), feats.pin_memory()))
+        host.append((locs.to(torch.int16).pin_memory(), feats.pin_memory()))   # coordinates cross PCIe as int16 x 4
         resident.append((locs.to(dev), feats.to(dev)))
     vox = [int(h[0].shape[0]) for h in host]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -320,11 +372,11 @@ def run_b200(args):
             if prev is not None:
                 hl, hs = runner.result(prev)                   # host-side result of step i-1 is complete
                 if count:
-                    d2h += hl.numel() * 8 + hs.numel() * 4
+                    d2h += hl.numel() * hl.element_size() + hs.numel() * 4
             prev = t
         hl, hs = runner.result(prev)
         if count:
-            d2h += hl.numel() * 8 + hs.numel() * 4
+            d2h += hl.numel() * hl.element_size() + hs.numel() * 4
         return d2h
 
     e2e_run(4, False)
@@ -335,7 +387,15 @@ def run_b200(args):
     barrier()
     e2e_ms = shard.max_over_ranks(e0.elapsed_time(e1), dev)
     e2e_value = total_vox / (e2e_ms * 1e-3)
-    h2d = sum(host[i % args.sets][0].numel() * 8 + host[i % args.sets][1].numel() * 4 for i in range(args.steps))
+    h2d = sum(host[i % args.sets][0].numel() * host[i % args.sets][0].element_size() + host[i % args.sets][1].numel() * 4
+              for i in range(args.steps))
+    my_e2e_ms = e0.elapsed_time(e1)
+    pcie = {'rank': rank, 'h2d_GBps': h2d / (my_e2e_ms * 1e-3) / 1e9, 'd2h_GBps': d2h / (my_e2e_ms * 1e-3) / 1e9, 'cores': bound}
+    per_rank = [pcie]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, pcie)
+        per_rank = gathered
 
     if rank != 0:
         if world > 1:
@@ -371,16 +431,21 @@ def run_b200(args):
     traffic, traffic_src = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, 'profiles', 'conv_dram_traffic.json')))
-        if args.conv_mode == 'tc32' and args.blocks == 32:
+        stamp = kernel_source_hash()
+        if args.conv_mode == 'tc32' and args.blocks == 32 and tj.get('kernel_source_sha256') == stamp:
             traffic, traffic_src = tj['dram_bytes_per_launch'], 'profiles/conv_dram_traffic.json: ' + tj['source']
+        else:
+            traffic_src = ('not reported: profiles/conv_dram_traffic.json was captured for other kernel sources / another '
+                           'workload (stamp %s, now %s)' % (str(tj.get('kernel_source_sha256'))[:12], stamp[:12]))
     except Exception:
         pass
     # ledger is of set 0; all sets are statistically alike (same generator) -> scale by launches
     alg_bytes_total = per_set_bytes * args.steps
     achieved = alg_bytes_total / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0
     roofline = {
-        'kernel': ('sgnn_conv_forward_tc32 = conv_tc32_kernel<Q,KG> + conv_tc32_child_kernel (tcgen05) for Cout=16, '
-                   'conv_ro_kernel (FFMA) for the rest (all %d convolutions per step)' if args.conv_mode == 'tc32' else
+        'kernel': ('all %d convolutions per step: conv_ur_kernel<Q> + conv_urc_kernel (tcgen05, distinct rows of a tile staged once by '
+                   'TMA) for the Cout=16 layers of site sets >= 1000 rows, conv_tc32_kernel for large stride-2 layers, '
+                   'conv_ro_kernel (FFMA) for the rest' if args.conv_mode == 'tc32' else
                    'sgnn_conv_forward = conv_ro_kernel<COUT,CIN,..> + conv_child_f32_kernel (all %d launches per step)')
                   % round(convs_per_step),
         'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
@@ -396,27 +461,27 @@ def run_b200(args):
         'achieved_tflops_fp32': per_set_flops * args.steps / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0,
         'fp32_ffma_peak_tflops': 148 * 128 * 2 * 1.965e9 / 1e12,
         'fp32_ffma_peak_tflops_measured': ffma_meas,
-        'note': ('tc32: fp32 features on tcgen05 via an exact 3-way bf16 split for the wide layers with >= 60000 rows (child-mode '
-                 'upsampling + FCN/head convolutions), FFMA kernels for the rest; activations are L2 resident, the tensor-core '
-                 'kernels are bound by the L1/shared data pipe (row gathers + st.shared of the split planes, ncu: 79 %) and by '
-                 'latency at 8-16 warps per SM, not by HBM or the tensor pipe (8-14 % busy)' if args.conv_mode == 'tc32' else
+        'note': ('tc32: fp32 features on tcgen05 via an exact 3-way bf16 split; activations are L2 resident (DRAM traffic below the '
+                 'algorithmic bytes); the unique-row kernels are bound by per-work-item synchronisation latency (~870 cycles per 3 '
+                 'filter offsets on both the MMA-issue and the producer side, profiles/r02_ur_pipeline_analysis.txt), shared-memory '
+                 'data pipe 65 %, tensor pipe 17 %' if args.conv_mode == 'tc32' else
                  'fp32 FFMA path: activations are L2 resident and the kernel is FFMA / L2-gather bound, so the HBM '
                  'fraction (SURVEY 8(d) definition) is small by construction; achieved_tflops_fp32 vs the FFMA peak '
                  'is the meaningful ceiling for this dtype'),
     }
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, t, cores, nvox = cpu_forward_rate(args.cpu_blocks, args.cpu_reps, args.param_seed)
+        v, t, cores, nvox = cpu_forward_rate(args.cpu_blocks if args.cpu_blocks > 0 else 8, args.cpu_reps, args.param_seed)
         cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-               'sample': 'median of %d forwards of %d x 64^3 block(s) (%d voxels, %.2f s each); restated '
-                         'SparseConvNet-CPU path (oracle O2) under the oracle port of model.py' %
-                         (args.cpu_reps, args.cpu_blocks, nvox, t)}
+               'sample': 'median of %d forwards of %d x 64^3 block(s) of the same workload (%d voxels, %.2f s each, 1 warm-up); '
+                         'restated SparseConvNet-CPU path (oracle O2) under the oracle port of model.py' %
+                         (args.cpu_reps, args.cpu_blocks if args.cpu_blocks > 0 else 8, nvox, t)}
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'BASELINE configs[1]: %d synthetic 64^3 TSDF blocks @5%% per GPU per step, full '
-                               '3-level coarse-to-fine generator, fp32' % args.blocks,
+        'config': {'workload': 'BASELINE configs[%d]: %d synthetic 64^3 TSDF blocks @5%% per GPU per step, full '
+                               '3-level coarse-to-fine generator, fp32' % (args.config, args.blocks),
                    'blocks_per_gpu': args.blocks, 'input_voxels_per_step_per_gpu': vox[0],
                    'level_candidates_set0': level_rows, 'output_voxels_set0': final_rows,
                    'parallelism': 'independent blocks, rank = block mod %d, one NCCL weight broadcast' % world,
@@ -426,7 +491,8 @@ def run_b200(args):
                    'conv_mode': args.conv_mode},
         'roofline': roofline, 'cpu_baseline': cpu,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d // args.steps,
-                'd2h_bytes_per_step': d2h // max(args.steps, 1), 'ms_per_step': e2e_ms / args.steps},
+                'd2h_bytes_per_step': d2h // max(args.steps, 1), 'ms_per_step': e2e_ms / args.steps,
+                'coordinates': 'int16 x 4 over PCIe both ways (StreamingRunner compact mode)', 'per_rank': per_rank},
         'gpu_launches': launches, 'clocks': sampler.summary(), 'wall_s': wall,
     }
     if args.ledger:
@@ -446,7 +512,13 @@ def main():
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     sys.stdout = os.fdopen(real_stdout, 'w', buffering=1)
-    if args.impl == 'reference':
+    if args.config in (2, 4):
+        if int(os.environ.get('RANK', '0')) == 0:
+            import bench_ops
+            bench_ops.contract_line(args)
+    elif args.impl == 'reference':
+        if args.blocks <= 0:
+            args.blocks = 32          # the CPU arm samples configs[3] with the configs[1] step (same per-voxel work)
         run_reference(args)
     else:
         run_b200(args)

@@ -20,6 +20,7 @@ import json
 import os
 import sys
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -130,6 +131,149 @@ def main():
                               'deconv_frac_of_hbm': b_dec / (t_dec * 1e-3) / 1e9 / hbm,
                               'conv_tflops': 2.0 * n * 256 / (t_conv * 1e-3) / 1e12,
                               'ms_conv_fp32_ffma_same_geometry': t_f32, 'hbm_peak_GBps': hbm}))
+
+
+def _cpu_sample(config):
+    """CPU arm of configs[2] / configs[4]: the restated SparseConvNet-CPU ops (oracle O2) on a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import sparseconvnet as o2
+    import time
+    torch.set_num_threads(max(1, min(os.cpu_count() or 1, 16)))
+    rng = np.random.default_rng(1234)
+    if config == 2:
+        mask = rng.random((128, 128, 128)) < 0.03
+        c = np.argwhere(mask)
+        c = torch.from_numpy(np.concatenate([c, np.zeros((c.shape[0], 1), dtype=np.int64)], 1))
+        f = torch.from_numpy(rng.standard_normal((c.shape[0], 16)).astype(np.float32))
+        net = o2.Sequential().add(o2.Convolution(3, 16, 16, 2, 2, False)).add(o2.Deconvolution(3, 16, 16, 2, 2, False)).eval()
+        inp = o2.InputLayer(3, [128, 128, 128], mode=0)
+        def run():
+            with torch.no_grad():
+                net(inp([c, f]))
+        what = 'one 128^3 block @3%% (%d sites), fp32 Convolution+Deconvolution k2 s2 on oracle O2' % c.shape[0]
+    else:
+        cs = []
+        for b in range(8):
+            m = rng.random((64, 64, 64)) < 0.05
+            a = np.argwhere(m)
+            cs.append(np.concatenate([a, np.full((a.shape[0], 1), b)], 1))
+        c = torch.from_numpy(np.concatenate(cs).astype(np.int64))
+        f = torch.zeros((c.shape[0], 1))
+        conv = o2.SubmanifoldConvolution(3, 1, 1, 3, False).eval()
+        inp = o2.InputLayer(3, [64, 64, 64], mode=0)
+        def run():
+            t = inp([c, f])
+            t.metadata.getSubmanifoldRuleBook(t.spatial_size, 3) if hasattr(t.metadata, 'getSubmanifoldRuleBook') else conv(t)
+        what = '8 x 64^3 blocks @5%% (%d sites): site index + 3^3 submanifold rulebook on oracle O2' % c.shape[0]
+    run()
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter(); run(); ts.append(time.perf_counter() - t0)
+    t = float(np.median(ts))
+    return c.shape[0] / t, t, what
+
+
+def contract_line(args):
+    """bench.py --config 2 / 4: the bench contract's JSON line for BASELINE configs[2] (one 128^3 block @3 %, bf16, stride-2
+    Convolution + Deconvolution) and configs[4] (rulebook build, 10 M active voxels)."""
+    metric = {2: 'fine_active_sites_per_s_conv_k2s2_plus_deconv_bf16', 4: 'active_sites_per_s_rulebook_build'}[args.config]
+    if args.impl == 'reference':
+        v, t, what = _cpu_sample(args.config)
+        print(json.dumps({'impl': 'reference', 'metric': metric, 'value': v, 'unit': 'sites/s', 'n_gpus': 1, 'steps': 3, 'warmup': 1,
+                          'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                          'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': 'BASELINE configs[%d] on the CPU: %s' % (args.config, what)},
+                          'cpu_baseline': {'value': v, 'unit': 'sites/s', 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': what},
+                          'e2e': {'value': v, 'unit': 'sites/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}))
+        return
+    import sgnn_b200.engine as E
+    from sgnn_b200._lib import lib
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm = float(peaks.get('hbm_gbs', 6650.0))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    K, W = max(args.steps, 1), max(args.warmup, 3)
+    state = {}
+    if args.config == 2:
+        mask = torch.rand((1, 128, 128, 128), device=dev, generator=g) < 0.03
+        coords = torch.nonzero(mask)[:, [1, 2, 3, 0]].contiguous().int()
+        n = coords.shape[0]
+        x = torch.randn((n, 16), device=dev, generator=g).bfloat16()
+        wc = (torch.randn((8, 16, 16), device=dev, generator=g) * 0.2).bfloat16()
+        wd = (torch.randn((8, 16, 16), device=dev, generator=g) * 0.2).bfloat16()
+        grid = E.build_grid(coords, 1, (128, 128, 128))
+        cg = E.coarsen(grid)
+        parent, children = E.rulebook_strided(grid, cg)
+        y = torch.empty((cg.n, 16), dtype=torch.bfloat16, device=dev)
+        z = torch.empty((n, 16), dtype=torch.bfloat16, device=dev)
+        def step():
+            E.conv(x, children, wc, cg.n, y)
+            E.deconv(y, parent, wd, z)
+        hc, hx = coords.cpu().pin_memory(), x.cpu().pin_memory()
+        hz = torch.empty((n, 16), dtype=torch.bfloat16).pin_memory()
+        def e2e_step():
+            c_d, x_d = hc.to(dev, non_blocking=True), hx.to(dev, non_blocking=True)
+            gr = E.build_grid(c_d, 1, (128, 128, 128)); cgr = E.coarsen(gr); par, chi = E.rulebook_strided(gr, cgr)
+            yy = torch.empty((cgr.n, 16), dtype=torch.bfloat16, device=dev)
+            E.conv(x_d, chi, wc, cgr.n, yy); E.deconv(yy, par, wd, z)
+            hz.copy_(z, non_blocking=True)
+        alg = 2 * ((n * 16 + cg.n * 16) * 2 + 8 * n + 8 * 16 * 16 * 2)
+        h2d, d2h, launches, units = hc.numel() * 4 + hx.numel() * 2, hz.numel() * 2, 2, n
+        workload = 'BASELINE configs[2]: one 128^3 block @3%% (%d fine / %d coarse sites), bf16 features, Convolution k2 s2 + Deconvolution k2 s2 on tcgen05' % (n, cg.n)
+        dtype, kernel = 'bf16', 'conv_tc_bf16_kernel (tcgen05, bf16 -> fp32 in TMEM), convolution + deconvolution'
+    else:
+        nb = 763
+        mask = torch.rand((nb, 64, 64, 64), device=dev, generator=g) < 0.05
+        coords = torch.nonzero(mask)[:, [1, 2, 3, 0]].contiguous().int()
+        del mask
+        n = coords.shape[0]
+        def step():
+            state['g'] = E.build_grid(coords, nb, (64, 64, 64))
+            state['nbr'] = E.rulebook_submanifold(state['g'])
+        hc = coords.cpu().pin_memory()
+        hcnt = torch.empty(27, dtype=torch.int64).pin_memory()
+        def e2e_step():
+            c_d = hc.to(dev, non_blocking=True)
+            gr = E.build_grid(c_d, nb, (64, 64, 64)); nbr = E.rulebook_submanifold(gr)
+            hcnt.copy_((nbr >= 0).sum(1), non_blocking=True)        # rules per filter offset: the host-side summary of the rulebook
+        step(); torch.cuda.synchronize()
+        r = int((state['nbr'] >= 0).sum().item())
+        alg = 16 * n + 12 * n + 208 * n + 8 * r
+        h2d, d2h, launches, units = hc.numel() * 4, 27 * 8, 7, n
+        workload = 'BASELINE configs[4]: rulebook build, %d active voxels (763 x 64^3 @5%%), %d rules, 3^3 submanifold' % (n, r)
+        dtype, kernel = 'int32', 'grid_set_bits + popcount scan + grid_fill_rank + rulebook_submanifold_kernel'
+
+    def run(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for i in range(k):
+            flush.fill_(i & 0xff)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot
+    run(step, W)
+    l0 = lib.sgnn_launch_count()
+    ms = run(step, K) / K
+    launches = (lib.sgnn_launch_count() - l0) / K
+    run(e2e_step, 3)
+    ms_e2e = run(e2e_step, K) / K
+    cpu_v, cpu_t, what = _cpu_sample(args.config)
+    ach = alg / (ms * 1e-3) / 1e9
+    print(json.dumps({
+        'metric': metric, 'value': units / (ms * 1e-3), 'unit': 'sites/s', 'n_gpus': 1, 'steps': K, 'warmup': W, 'ms_per_step': ms,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': dtype, 'data': 'synthetic',
+        'config': {'workload': workload, 'l2': '256 MiB flush before every step (outside the per-step event pair)'},
+        'roofline': {'kernel': kernel, 'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm, 'traffic': None,
+                     'algorithmic_bytes_per_step': alg, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'},
+        'cpu_baseline': {'value': cpu_v, 'unit': 'sites/s', 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': what},
+        'e2e': {'value': units / (ms_e2e * 1e-3), 'unit': 'sites/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': ms_e2e, 'includes': 'pinned H2D of coordinates (+ features), site index + rulebooks, the kernels, D2H of the result'},
+        'gpu_launches': launches}))
 
 
 def bench_mesh(args, dev, flush):

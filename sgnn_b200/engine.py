@@ -23,9 +23,20 @@ def _ptr(t):
 
 
 def _need_cuda(*ts):
+    """Every tensor on a CUDA device, and on the CURRENT one: the C ABI launches on the current device / its current stream,
+    so a tensor of another device would hand foreign pointers to kernels of this one.  (GenModel.forward switches the device
+    itself; direct users of this layer wrap their calls in `with torch.cuda.device(t.device)`.)"""
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError('sgnn_b200: tensors must be CUDA tensors (no CPU fallback in the product path)')
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError('sgnn_b200: tensor on cuda:%d but the current device is cuda:%d -- wrap the call in '
+                               '`with torch.cuda.device(tensor.device)`' % (t.device.index, cur))
 
 
 # Optional profiler hook (bench.py): an object with .conv(tag, x, nbr, weight, n_out, child_mode) -> ctx or None,
@@ -371,9 +382,6 @@ def dense_conv(x0, x1, weight, cout, ksize, stride, pad, scale=None, shift=None,
     return out
 
 
-_BN_CACHE = {}
-
-
 def fold_bn(bn):
     """Eval-mode BatchNormReLU folded to (scale, shift): y = max(fma(x, scale, shift), 0).
     scale = gamma * (running_var + eps)^-1/2, shift = beta - running_mean * scale  (SURVEY App. A.8).
@@ -381,8 +389,8 @@ def fold_bn(bn):
     module until a parameter or buffer changes."""
     ts = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
     key = tuple((t._version, t.data_ptr()) for t in ts)
-    hit = _BN_CACHE.get(id(bn))
-    if hit is not None and hit[0] == key and hit[3] is bn:
+    hit = getattr(bn, '_sgnn_fold', None)        # cached ON the module: dies with it (no global table of strong references)
+    if hit is not None and hit[0] == key:
         return hit[1], hit[2]
     w, b, rm, rv = [t.detach().cpu().float() for t in ts]
     inv = (rv + bn.eps).pow(-0.5)
@@ -390,5 +398,5 @@ def fold_bn(bn):
     shift = (b - rm * scale).contiguous()
     dev = bn.running_var.device
     scale, shift = scale.to(dev), shift.to(dev)
-    _BN_CACHE[id(bn)] = (key, scale, shift, bn)
+    object.__setattr__(bn, '_sgnn_fold', (key, scale, shift))
     return scale, shift

@@ -12,9 +12,14 @@ from ._lib import lib, check
 
 
 def supported(model):
+    """Default SG-NN structure, every parameter on one CUDA device, channel widths inside the kernels' limits (Cin <= 64)."""
     try:
-        return (len(model.refinement) == 3 and len(model.encoder.process_sparse) == 3 and model.pass_occ and
-                model.pass_feats and model.use_skip_sparse and model.encoder.use_skip_dense and model.PRED_SURF)
+        ok = (len(model.refinement) == 3 and len(model.encoder.process_sparse) == 3 and model.pass_occ and
+              model.pass_feats and model.use_skip_sparse and model.encoder.use_skip_dense and model.PRED_SURF)
+        devs = set(p.device for p in model.parameters())
+        ok = ok and len(devs) == 1 and next(iter(devs)).type == 'cuda'
+        widths = [model.surfacepred.p1.nIn] + [r.nf_in for r in model.refinement] + [3 * r.nf for r in model.refinement]
+        return bool(ok and max(widths) <= 64)
     except Exception:
         return False
 
@@ -133,6 +138,18 @@ class NativeGenerator(object):
     def forward(self, locs, feats, want_cand_locs=True, nb=None):
         """locs int64/int32 [n,4] CUDA, feats fp32 [n,cin] CUDA -> raw SgnnGeneratorOut-backed tensors (clones)."""
         dev = feats.device
+        m = self.model
+        cin = m.encoder.process_sparse[0].nf_in
+        if locs.dim() != 2 or locs.shape[1] != 4 or feats.dim() != 2 or feats.shape[0] != locs.shape[0]:
+            raise ValueError('sgnn_b200: expected locs [n,4] and feats [n,%d], got %s and %s' % (cin, tuple(locs.shape), tuple(feats.shape)))
+        if feats.shape[1] != cin:
+            raise ValueError('sgnn_b200: the model takes %d input feature channel(s), got %d' % (cin, feats.shape[1]))
+        if next(m.parameters()).device != dev:
+            raise RuntimeError('sgnn_b200: model parameters on %s, features on %s' % (next(m.parameters()).device, dev))
+        with torch.cuda.device(dev):
+            return self._forward(locs, feats, want_cand_locs, nb, dev)
+
+    def _forward(self, locs, feats, want_cand_locs, nb, dev):
         self._prepare(dev)
         m = self.model
         dims = (C.c_int32 * 3)(*[int(v) for v in m.encoder.process_sparse[0].p0.spatial_size])
@@ -141,7 +158,7 @@ class NativeGenerator(object):
         out = _lib.SgnnGeneratorOut()
         self.weights.w.tc32_min_rows = int(getattr(m, 'tc32_min_rows', 0))
         self.weights.w.ur_min_rows = int(getattr(m, 'ur_min_rows', 0))
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         for _ in range(8):
             rc = lib.sgnn_generator_forward(C.byref(self.weights.w), C.c_void_p(locs.data_ptr()),
                                             1 if locs.dtype == torch.int64 else 0, C.c_void_p(feats.data_ptr()),
@@ -181,12 +198,14 @@ def forward_native(model, x, loss_weights):
     if model._native is None:
         model._native = NativeGenerator(model)
     g = model._native
+    if locs.shape[0] == 0:
+        raise RuntimeError('sgnn_b200.GenModel: empty input (scn raises on an empty InputLayer batch too)')
     locs = locs.to(dev).contiguous()
     if locs.dtype not in (torch.int64, torch.int32):
         locs = locs.long()
     feats = feats.float().contiguous()
     ssz = [int(v) for v in model.encoder.process_sparse[0].p0.spatial_size]
-    with torch.no_grad():
+    with torch.no_grad(), torch.cuda.device(dev):
         out, nb = g.forward(locs, feats, want_cand_locs=True, nb=int(x[2]) if len(x) > 2 else None)
         def to64(v):
             return E.coords_to_i64(v) if model.return_long else v.clone()

@@ -57,8 +57,9 @@ class Metadata(object):
             raise RuntimeError('no active-site set at spatial size %s in this metadata' % (_key(spatial_size),))
 
     def getSpatialLocations(self, spatial_size):
-        """LongTensor [N,4] (z,y,x,batch) in row order (model.py:380), on the feature device."""
-        return E.coords_to_i64(self.grid(spatial_size).coords)
+        """CPU LongTensor [N,4] (z,y,x,batch) in row order (model.py:380), as scn returns it: the reference's concat_skip
+        (model.py:344-353) indexes CPU tensors with it.  The device copy stays internal (self.grid(...).coords)."""
+        return E.coords_to_i64(self.grid(spatial_size).coords).cpu()
 
     def nActive(self, spatial_size):
         return self.grid(spatial_size).n

@@ -58,3 +58,54 @@ def sorted_rows(locs, *vals):
     keys = [locs[:, i] for i in range(locs.shape[1])]
     order = np.lexsort(tuple(keys[:3][::-1]) + ((keys[3],) if len(keys) > 3 else ()))
     return (locs[order],) + tuple(np.asarray(v)[order] for v in vals)
+
+
+def compare_generator_outputs(want, got, margin=1e-5, tol_logit=1e-4, tol_sdf=1e-3, max_flips_per_level=2, tag=''):
+    """Margin-aware comparison of two generator results  ((out_locs, out_sdf), levels), block by block.
+
+    Blocks (batch indices) are independent.  At every level the candidate coordinates of the blocks that have not diverged
+    must be EQUAL, in order, and the (occ, sdf) values within tol_logit.  A mask flip is legal only where the reference
+    logit is within `margin` of the threshold; it is COUNTED (bounded by max_flips_per_level, printed) and only the block
+    it happened in is excluded from the later levels -- every other block keeps being compared to the end, including the
+    final coordinates and the TSDF head (tol_sdf).  Returns (flips per level, diverged blocks)."""
+    (wl, ws), wlv = want
+    (gl, gs), glv = got
+    cpu = lambda t: t.detach().cpu() if isinstance(t, torch.Tensor) else t
+    diverged = set()
+    flips_per_level = []
+
+    def live(locs):
+        locs = cpu(locs)
+        if not diverged:
+            return torch.ones(locs.shape[0], dtype=torch.bool)
+        return ~torch.isin(locs[:, 3], torch.tensor(sorted(diverged), dtype=locs.dtype))
+    assert len(wlv) == len(glv)
+    for i, (w, g) in enumerate(zip(wlv, glv)):
+        if isinstance(w[0], list) or isinstance(g[0], list):          # empty level (model.py:211)
+            assert isinstance(w[0], list) and isinstance(g[0], list), 'level %d: one side empty' % i
+            flips_per_level.append(0)
+            continue
+        w0, w1, g0, g1 = cpu(w[0]), cpu(w[1]), cpu(g[0]), cpu(g[1])
+        kw, kg = live(w0), live(g0)
+        assert torch.equal(w0[kw], g0[kg]), '%s candidate coordinates at level %d (blocks %s excluded)' % (tag, i, sorted(diverged))
+        lw, lg = w1[kw], g1[kg]
+        err = float((lw - lg).abs().max()) if lw.numel() else 0.0
+        assert err <= tol_logit, '%s level %d logits differ by %.3e' % (tag, i, err)
+        fl = (torch.sigmoid(lw[:, 0]) > 0.5) != (torch.sigmoid(lg[:, 0]) > 0.5)
+        n = int(fl.sum())
+        flips_per_level.append(n)
+        if n:
+            assert bool((lw[:, 0][fl].abs() < margin).all()), '%s illegal mask flip at level %d (|logit| >= %g)' % (tag, i, margin)
+            assert n <= max_flips_per_level, '%s %d legal flips at level %d' % (tag, n, i)
+            diverged |= set(int(b) for b in w0[kw][fl][:, 3].tolist())
+    if isinstance(wl, list) or isinstance(gl, list):
+        assert isinstance(wl, list) and isinstance(gl, list)
+    else:
+        wl, ws, gl, gs = cpu(wl), cpu(ws), cpu(gl), cpu(gs)
+        kw, kg = live(wl), live(gl)
+        assert torch.equal(wl[kw], gl[kg]), '%s final coordinates' % tag
+        err = float((ws[kw] - gs[kg]).abs().max()) if int(kw.sum()) else 0.0
+        assert err <= tol_sdf, '%s TSDF differs by %.3e' % (tag, err)
+        print('%s parity: flips per level %s, diverged blocks %s, TSDF max err %.2e over %d voxels' % (
+            tag, flips_per_level, sorted(diverged), err, int(kw.sum())))
+    return flips_per_level, diverged
