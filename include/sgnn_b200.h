@@ -347,7 +347,13 @@ int sgnn_generator_profile_entry(int32_t i, int64_t* rec6, float* ms);
  *                   raster, table order) and with its bits (every float operation rounds once, in its operand order).
  *   sgnn_mc_merge_host  HOST function on host arrays: merge_close_vertices(1e-5, approx) in first-come order, then
  *                   remove_degenerate_faces / remove_duplicate_faces (:266-455).  verts [3*n_tri,3] and faces [n_tri,3]
- *                   are caller-allocated upper bounds; the used counts are returned. */
+ *                   are caller-allocated upper bounds; the used counts are returned.
+ *   sgnn_mc_merge_host_src  the same, and vert_src[v] (host [3*n_tri], may be NULL) = index into the soup's 3*n_tri
+ *                   vertices of the first-come vertex that became merged vertex v -- the reference gives v that vertex's
+ *                   colour (:399-431).
+ *   sgnn_mc_tri_cells   tri_cell dev [n_tri] = linear (z,y,x) cell index each triangle of the soup was emitted for; the
+ *                   reference paints a triangle with the colour of that cell's voxel (:228-231,255-257), so per-voxel
+ *                   colours need no kernel of their own: colour[v] = colors[tri_cell[vert_src[v] / 3]]. */
 size_t sgnn_mc_scratch_bytes(int32_t n0, int32_t n1, int32_t n2);
 int sgnn_mc_count(const float* tsdf, int32_t n0, int32_t n1, int32_t n2, float isovalue, float truncation, float thresh,
                   int32_t* offs, void* scratch, size_t scratch_bytes, void* stream);
@@ -355,6 +361,9 @@ int sgnn_mc_emit(const float* tsdf, int32_t n0, int32_t n1, int32_t n2, float is
                  const int32_t* offs, float* tris, void* stream);
 int sgnn_mc_merge_host(const float* tris, int64_t n_tri, float* verts, int32_t* faces, int64_t* n_verts,
                        int64_t* n_faces);
+int sgnn_mc_merge_host_src(const float* tris, int64_t n_tri, float* verts, int32_t* faces, int32_t* vert_src,
+                           int64_t* n_verts, int64_t* n_faces);
+int sgnn_mc_tri_cells(const int32_t* offs, int64_t n_cells, int32_t* tri_cell, void* stream);
 /* The packed triangulation table the kernels use: 256 words, 4 bits per triangle-vertex edge id, 0xF terminates. */
 int sgnn_mc_table(uint64_t* out256);
 

@@ -133,6 +133,8 @@ SIGNATURES = {
     'sgnn_mc_count': (_I, [_P, _I, _I, _I, C.c_float, C.c_float, C.c_float, _P, _P, _Z, _P]),
     'sgnn_mc_emit': (_I, [_P, _I, _I, _I, C.c_float, C.c_float, C.c_float, _P, _P, _P]),
     'sgnn_mc_merge_host': (_I, [_P, _L, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    'sgnn_mc_merge_host_src': (_I, [_P, _L, _P, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    'sgnn_mc_tri_cells': (_I, [_P, _L, _P, _P]),
     'sgnn_mc_table': (_I, [_P]),
     'sgnn_children_coords': (_I, [_P, _L, _P, _P]),
     'sgnn_concat_skip': (_I, [_G, _P, _I, _I, _P, _L, _P, _I, _I, _P]),

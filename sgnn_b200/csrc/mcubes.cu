@@ -43,6 +43,15 @@ __global__ void mc_emit_kernel(McArgs a, const int* __restrict__ offs, float* __
   }
 }
 
+// the cell (linear z,y,x index) every emitted triangle came from: the reference colours a triangle's three vertices with
+// the colour of that cell's voxel (marching_cubes.cpp:228-231,255-257)
+__global__ void mc_tri_cells_kernel(const int* __restrict__ offs, long long total, int* __restrict__ tri_cell) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int first = offs[i], last = offs[i + 1];
+    for (int t = first; t < last; ++t) tri_cell[t] = (int)i;
+  }
+}
+
 McArgs mc_args(const float* tsdf, int n0, int n1, int n2, float iso, float trunc, float thresh) {
   McArgs a;
   a.tsdf = tsdf; a.n0 = n0; a.n1 = n1; a.n2 = n2; a.iso = iso; a.trunc = trunc; a.thresh = thresh;
@@ -93,8 +102,20 @@ extern "C" int sgnn_mc_emit(const float* tsdf, int32_t n0, int32_t n1, int32_t n
   return SGNN_OK;
 }
 
+extern "C" int sgnn_mc_tri_cells(const int32_t* offs, int64_t n_cells, int32_t* tri_cell, void* stream) {
+  if (!offs || !tri_cell || n_cells <= 0) return SGNN_E_INVALID;
+  mc_tri_cells_kernel<<<sgnn_blocks(n_cells, 256), 256, 0, (cudaStream_t)stream>>>(offs, n_cells, tri_cell);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
 extern "C" int sgnn_mc_merge_host(const float* tris, int64_t n_tri, float* verts, int32_t* faces, int64_t* n_verts,
                                   int64_t* n_faces) {
+  return sgnn_mc_merge_host_src(tris, n_tri, verts, faces, nullptr, n_verts, n_faces);
+}
+
+extern "C" int sgnn_mc_merge_host_src(const float* tris, int64_t n_tri, float* verts, int32_t* faces, int32_t* vert_src,
+                                      int64_t* n_verts, int64_t* n_faces) {
   if (n_tri < 0 || (n_tri > 0 && (!tris || !verts || !faces)) || !n_verts || !n_faces) return SGNN_E_INVALID;
   if (n_tri * 3 >= 0x7fffffffLL) return SGNN_E_TOO_LARGE;
   const size_t nv = (size_t)n_tri * 3;
@@ -127,6 +148,7 @@ extern "C" int sgnn_mc_merge_host(const float* tris, int64_t n_tri, float* verts
       while (table[h].used) h = (h + 1) & (cap - 1);
       table[h].x = cx; table[h].y = cy; table[h].z = cz; table[h].id = cnt; table[h].used = true;
       verts[3 * (size_t)cnt] = px; verts[3 * (size_t)cnt + 1] = py; verts[3 * (size_t)cnt + 2] = pz;
+      if (vert_src) vert_src[cnt] = (int32_t)v;
       look[v] = cnt++;
     }
   }

@@ -7,6 +7,7 @@
 #include "../sgnn_b200/csrc/mc_core.h"
 
 static std::vector<float> g_tris;
+static std::vector<int> g_cells;   // == mc_tri_cells_kernel: the cell of every triangle
 
 extern "C" int mch_run(const float* tsdf, int n0, int n1, int n2, float iso, float trunc, float thresh) {
   McArgs a;
@@ -18,15 +19,21 @@ extern "C" int mch_run(const float* tsdf, int n0, int n1, int n2, float iso, flo
     offs[i + 1] = offs[i] + mc_cell_count(a, x, y, z);
   }
   g_tris.assign((size_t)offs[total] * 9, 0.f);
+  g_cells.assign((size_t)offs[total], 0);
   for (long long i = 0; i < total; ++i) {                      // == mc_emit_kernel
     const int n_tri = offs[i + 1] - offs[i];
     if (!n_tri) continue;
     const int x = (int)(i % n2), y = (int)((i / n2) % n1), z = (int)(i / ((long long)n1 * n2));
     mc_cell_emit(a, x, y, z, n_tri, g_tris.data() + (size_t)offs[i] * 9);
+    for (int t = offs[i]; t < offs[i + 1]; ++t) g_cells[t] = (int)i;
   }
   return offs[total];
 }
 
 extern "C" void mch_copy(float* tris) {
   for (size_t i = 0; i < g_tris.size(); ++i) tris[i] = g_tris[i];
+}
+
+extern "C" void mch_cells(int* cells) {
+  for (size_t i = 0; i < g_cells.size(); ++i) cells[i] = g_cells[i];
 }

@@ -57,19 +57,61 @@ def test_host_merge_empty_and_degenerate():
     assert v.shape == (3, 3) and f.tolist() == [[0, 1, 2]]
 
 
-def test_mesh_writers_round_trip(tmp_path):
-    """.obj with vertex colours as marching_cubes.py:9-18 writes it, .ply with the same elements plyfile would write."""
+def _ref_mc():
+    """The REAL reference extension (oracle/_ref/marching_cubes_cpp.so, compiled from its source in place) or skip."""
+    import build_ref
+    ref = build_ref.load_marching_cubes()
+    if ref is None:
+        pytest.skip('oracle/_ref/marching_cubes_cpp.so not built (reference sources absent)')
+    return ref
+
+
+def test_mesh_writers_obj_and_binary_ply_layout(tmp_path):
+    """.obj with vertex colours as marching_cubes.py:9-18 writes it; .ply in save_to_ply's binary layout
+    (marching_cubes.cpp:519-560): 15-byte vertices, 13-byte faces."""
     from sgnn_b200 import mesh
     v = np.array([[0, 0, 0], [1.5, 0, 0.25], [0, 2, 0]], dtype=np.float32)
-    c = np.full((3, 3), 220, dtype=np.uint8)
+    c = np.array([[220, 220, 220], [1, 2, 3], [255, 0, 7]], dtype=np.uint8)
     f = np.array([[0, 1, 2]], dtype=np.int32)
     obj, ply = str(tmp_path / 'm.obj'), str(tmp_path / 'm.ply')
     mesh.save_mesh(v, c, f, obj)
     mesh.save_mesh(v, c, f, ply)
     lines = open(obj).read().split('\n')
-    assert lines[1] == 'v 1.500000 0.000000 0.250000 220 220 220' and 'f 1 2 3' in lines
-    body = open(ply).read().split('end_header\n')[1].split('\n')
-    assert body[1].split()[:3] == ['1.500000', '0.000000', '0.250000'] and body[3] == '3 0 1 2'
+    assert lines[1] == 'v 1.500000 0.000000 0.250000 1 2 3' and 'f 1 2 3' in lines
+    raw = open(ply, 'rb').read()
+    head, body = raw.split(b'end_header\n')
+    assert head.startswith(b'ply\nformat binary_little_endian 1.0\nelement vertex 3\n') and b'element face 1\n' in head
+    assert len(body) == 3 * 15 + 13
+    assert np.frombuffer(body[15:27], dtype='<f4').tolist() == [1.5, 0.0, 0.25] and list(body[27:30]) == [1, 2, 3]
+    assert body[45] == 3 and np.frombuffer(body[46:58], dtype='<i4').tolist() == [0, 1, 2]
+
+
+@pytest.mark.parametrize('name', ['sphere', 'noise'])
+def test_ply_bytes_and_vertex_colours_equal_the_reference(name, tmp_path):
+    """Host side of the colour / file path against the REAL reference: the kernels' per-cell code (host harness) gives
+    the soup and the cell of every triangle, the product's merge + colour lookup + writer give the file;
+    export_marching_cubes of the compiled reference gives the bytes to match (both with per-voxel colours and with the
+    grey volume marching_cubes.py:29-30 substitutes for colors=None)."""
+    from sgnn_b200 import mesh
+    ref = _ref_mc()
+    g = np.load(os.path.join(GOLDEN, 'mc_ref.npz'))
+    tsdf = g['case_%s_tsdf' % name]
+    rng = np.random.default_rng(3)
+    colors = rng.integers(0, 256, tsdf.shape + (3,), dtype=np.uint8)
+    soup, cells = _harness_soup(tsdf, cells=True)
+    v, f, src = mesh.merge_triangles(soup, return_source=True)
+    vc = mesh.vertex_colors(colors, cells, src)
+    rv, rc, rf = ref.run_marching_cubes(torch.from_numpy(tsdf), torch.from_numpy(colors), 0.0, 3.0, 10.0)
+    assert np.array_equal(v.view(np.uint32), rv.numpy().view(np.uint32)) and np.array_equal(f, rf.numpy())
+    assert np.array_equal(vc, rc.numpy())
+    mine, theirs = str(tmp_path / 'mine.ply'), str(tmp_path / 'ref.ply')
+    mesh.save_mesh(v, vc, f, mine)
+    ref.export_marching_cubes(torch.from_numpy(tsdf), torch.from_numpy(colors), 0.0, 3.0, 10.0, theirs)
+    assert open(mine, 'rb').read() == open(theirs, 'rb').read()
+    grey = torch.ones(tsdf.shape + (3,), dtype=torch.uint8) * 220
+    ref.export_marching_cubes(torch.from_numpy(tsdf), grey, 0.0, 3.0, 10.0, theirs)
+    mesh.save_mesh(v, np.full((v.shape[0], 3), 220, dtype=np.uint8), f, mine)
+    assert open(mine, 'rb').read() == open(theirs, 'rb').read()
 
 
 def _host_harness():
@@ -85,13 +127,17 @@ def _host_harness():
     return C.CDLL(so)
 
 
-def _harness_soup(tsdf):
+def _harness_soup(tsdf, cells=False):
     h = _host_harness()
     t = np.ascontiguousarray(tsdf, dtype=np.float32)
     n = h.mch_run(t.ctypes.data_as(C.c_void_p), t.shape[0], t.shape[1], t.shape[2], C.c_float(0.0), C.c_float(3.0),
                   C.c_float(10.0))
     tris = np.empty((n, 3, 3), dtype=np.float32)
     h.mch_copy(tris.ctypes.data_as(C.c_void_p))
+    if cells:
+        cl = np.empty(n, dtype=np.int32)
+        h.mch_cells(cl.ctypes.data_as(C.c_void_p))
+        return tris, cl
     return tris
 
 
@@ -172,5 +218,26 @@ def test_gpu_sparse_prediction_to_mesh_like_save_predictions(tmp_path):
     dense[locs[:, 0], locs[:, 1], locs[:, 2]] = vals
     V, F = mcubes.marching_cubes(dense, 0.0, 2.9, 10.0)
     assert np.array_equal(v.numpy().view(np.uint32), V.view(np.uint32)) and np.array_equal(f.numpy(), F)
-    head = open(out).read(200)
-    assert head.startswith('ply') and 'element vertex %d' % V.shape[0] in head
+    head = open(out, 'rb').read(200)
+    assert head.startswith(b'ply\nformat binary_little_endian 1.0\n') and b'element vertex %d\n' % V.shape[0] in head
+    assert os.path.getsize(out) == open(out, 'rb').read().index(b'end_header\n') + 11 + 15 * V.shape[0] + 13 * F.shape[0]
+
+
+@pytest.mark.gpu
+def test_gpu_vertex_colours_and_ply_file_equal_the_reference(tmp_path):
+    """marching_cubes(tsdf, colors, ..., 'x.ply') end to end on the GPU against the compiled reference's
+    export_marching_cubes: same file, byte for byte, with per-voxel colours and with colors=None."""
+    from sgnn_b200 import mesh
+    ref = _ref_mc()
+    g = np.load(os.path.join(GOLDEN, 'mc_ref.npz'))
+    tsdf = g['case_blobs_tsdf']
+    colors = np.random.default_rng(4).integers(0, 256, tsdf.shape + (3,), dtype=np.uint8)
+    v, c, f = mesh.run_marching_cubes(torch.from_numpy(tsdf).cuda(), torch.from_numpy(colors).cuda())
+    rv, rc, rf = ref.run_marching_cubes(torch.from_numpy(tsdf), torch.from_numpy(colors), 0.0, 3.0, 10.0)
+    assert torch.equal(v.view(torch.int32), rv.view(torch.int32)) and torch.equal(c, rc) and torch.equal(f, rf)
+    mine, theirs = str(tmp_path / 'mine.ply'), str(tmp_path / 'ref.ply')
+    for col in (colors, None):
+        mesh.marching_cubes(torch.from_numpy(tsdf), None if col is None else torch.from_numpy(col), 0.0, 3.0, 10.0, mine)
+        rcol = torch.from_numpy(col) if col is not None else torch.ones(tsdf.shape + (3,), dtype=torch.uint8) * 220
+        ref.export_marching_cubes(torch.from_numpy(tsdf), rcol, 0.0, 3.0, 10.0, theirs)
+        assert open(mine, 'rb').read() == open(theirs, 'rb').read()
