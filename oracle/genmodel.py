@@ -149,8 +149,12 @@ class OracleGenModel(nn.Module):
         add[hit] = skip_feats[order[pos[hit]]]
         return torch.cat([feats, add], 1)
 
-    def forward(self, locs, feats):
-        """locs LongTensor [N,4] (z,y,x,b), feats [N,1] -> ([locs, sdf], [[cand_locs, cand(occ,sdf)] x 4])."""
+    def forward(self, locs, feats, forced_keep=None):
+        """locs LongTensor [N,4] (z,y,x,b), feats [N,1] -> ([locs, sdf], [[cand_locs, cand(occ,sdf)] x 4]).
+        forced_keep (tests only, "teacher forcing"): one bool mask per level that REPLACES this oracle's own
+        sigmoid(occ) > 0.5 decision for what continues to the next level (the reported logits stay the oracle's own), so
+        that a device pass can be checked level by level over the whole input even when a logit within rounding distance
+        of the threshold falls on the other side there."""
         enc = self.encoder
         x = [locs, feats]
         skips = []
@@ -176,6 +180,8 @@ class OracleGenModel(nn.Module):
         cand_locs = torch.cat([cell.repeat(B, 1), torch.arange(B).repeat_interleave(cell.shape[0]).view(-1, 1)], 1)
         cand = torch.stack([occ[:, 0].reshape(-1), sdf[:, 0].reshape(-1)], 1)
         keep = torch.sigmoid(cand[:, 0]) > 0.5
+        if forced_keep is not None:
+            keep = forced_keep[0].reshape(-1).bool()
         f = torch.cat([cand, xd.permute(0, 2, 3, 4, 1).reshape(-1, C)], 1)[keep]
         cur = cand_locs[keep]
         outputs = [[cand_locs, cand]]
@@ -190,6 +196,8 @@ class OracleGenModel(nn.Module):
             y = r.n3(r.n2(r.n1(r.n0([kids, y.repeat_interleave(8, 0)]))))
             cand = torch.cat([r.linear(y), r.linearsdf(y)], 1)                           # model.py:230-240
             keep = torch.sigmoid(cand[:, 0]) > 0.5
+            if forced_keep is not None:
+                keep = forced_keep[h + 1].reshape(-1).bool()
             outputs.append([kids, cand])
             cur, f = kids[keep], torch.cat([y[keep], cand[keep]], 1)
         if cur.shape[0] == 0:

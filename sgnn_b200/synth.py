@@ -61,3 +61,29 @@ def synthetic_batch(blocks, size=64, occ=0.05, seed0=1234, first=0):
         fs.append(f)
     return (torch.from_numpy(np.ascontiguousarray(np.concatenate(cs))),
             torch.from_numpy(np.ascontiguousarray(np.concatenate(fs))))
+
+
+def synthetic_scene(dims_zyx=(128, 320, 256), seed=0, truncation=3.0):
+    """A room-like whole scene: floor, four walls with a doorway, a table slab and a few spheres; the
+    signed distance to the nearest surface in voxels (+ a little measurement noise), kept where |sdf| < truncation.
+    -> (locs int32 [n,3] (z,y,x) raster order, sdf float32 [n]).  128 x 320 x 256 gives ~1.3 M sites."""
+    d0, d1, d2 = (int(v) for v in dims_zyx)
+    rng = np.random.default_rng(seed)
+    z, y, x = np.meshgrid(np.arange(d0, dtype=np.float32), np.arange(d1, dtype=np.float32),
+                          np.arange(d2, dtype=np.float32), indexing='ij', sparse=True)
+    big = np.float32(1e3)
+    sd = np.broadcast_to(z - np.float32(4.3), (d0, d1, d2)).copy()                             # floor
+    sd = np.minimum(sd, np.where((y > d1 * 0.4) & (y < d1 * 0.5) & (z < d0 * 0.6), big, x - np.float32(5.6)))   # wall + door
+    sd = np.minimum(sd, np.float32(d2 - 6.2) - x)
+    sd = np.minimum(sd, y - np.float32(4.9))
+    sd = np.minimum(sd, np.float32(d1 - 5.4) - y)
+    slab = np.maximum(np.maximum(np.abs(z - d0 * 0.35) - 2.2, np.abs(y - d1 * 0.55) - d1 * 0.12), np.abs(x - d2 * 0.5) - d2 * 0.2)
+    sd = np.minimum(sd, slab.astype(np.float32))
+    for _ in range(6):
+        c = rng.uniform([10, 30, 30], [d0 * 0.5, d1 - 30, d2 - 30]).astype(np.float32)
+        r = np.float32(rng.uniform(6, 14))
+        sd = np.minimum(sd, np.sqrt((z - c[0]) ** 2 + (y - c[1]) ** 2 + (x - c[2]) ** 2) - r)
+    keep = np.abs(sd) < truncation
+    locs = np.argwhere(keep).astype(np.int32)
+    vals = sd[keep].astype(np.float32) + rng.normal(0, 0.02, int(keep.sum())).astype(np.float32)
+    return locs, np.clip(vals, -truncation + 1e-3, truncation - 1e-3).astype(np.float32)

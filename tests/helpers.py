@@ -109,3 +109,44 @@ def compare_generator_outputs(want, got, margin=1e-5, tol_logit=1e-4, tol_sdf=1e
         print('%s parity: flips per level %s, diverged blocks %s, TSDF max err %.2e over %d voxels' % (
             tag, flips_per_level, sorted(diverged), err, int(kw.sum())))
     return flips_per_level, diverged
+
+
+def compare_teacher_forced(oracle, locs, feats, got, margin=1e-5, tol_logit=1e-4, tol_sdf=1e-3, max_flips=8, tag=''):
+    """Whole-input parity with NOTHING excluded (for batch-1 scenes, where one flipped mask bit would otherwise take the
+    only block out of the comparison): the oracle generator is run with the device pass's keep decisions forced on it
+    (OracleGenModel.forward(..., forced_keep=...)), so both sides refine the same sites at every level.  Checked at every
+    level over all candidates: coordinates EQUAL in order, (occ, sdf) within tol_logit, and the oracle's OWN decision
+    sigmoid(occ) > 0.5 equal to the device's except where the oracle logit is within `margin` of the threshold -- those
+    legal flips are counted, bounded (max_flips in total) and printed.  Then the final coordinates (equal) and the TSDF
+    head (tol_sdf).  Returns the flips per level."""
+    (gl, gs), glv = got
+    cpu = lambda t: t.detach().cpu() if isinstance(t, torch.Tensor) else t
+    forced = []
+    for g in glv:
+        forced.append(torch.zeros(0, dtype=torch.bool) if isinstance(g[0], list) else torch.sigmoid(cpu(g[1])[:, 0]) > 0.5)
+    with torch.no_grad():
+        (wl, ws), wlv = oracle(locs, feats, forced_keep=forced)
+    flips = []
+    for i, (w, g) in enumerate(zip(wlv, glv)):
+        if isinstance(w[0], list) or isinstance(g[0], list):
+            assert isinstance(w[0], list) and isinstance(g[0], list), 'level %d: one side empty' % i
+            flips.append(0)
+            continue
+        w0, w1, g0, g1 = cpu(w[0]), cpu(w[1]), cpu(g[0]), cpu(g[1])
+        assert torch.equal(w0, g0), '%s candidate coordinates at level %d' % (tag, i)
+        err = float((w1 - g1).abs().max())
+        assert err <= tol_logit, '%s level %d logits differ by %.3e' % (tag, i, err)
+        fl = (torch.sigmoid(w1[:, 0]) > 0.5) != forced[i]
+        flips.append(int(fl.sum()))
+        assert bool((w1[:, 0][fl].abs() < margin).all()), '%s illegal mask flip at level %d (|logit| >= %g)' % (tag, i, margin)
+    assert sum(flips) <= max_flips, '%s %s legal flips' % (tag, flips)
+    if isinstance(wl, list) or isinstance(gl, list) or len(wl) == 0:
+        assert len(wl) == 0 and len(gl) == 0
+        err, n = 0.0, 0
+    else:
+        wl, ws, gl, gs = cpu(wl), cpu(ws), cpu(gl), cpu(gs)
+        assert torch.equal(wl, gl), '%s final coordinates' % tag
+        err, n = float((ws - gs).abs().max()), int(wl.shape[0])
+        assert err <= tol_sdf, '%s TSDF differs by %.3e' % (tag, err)
+    print('%s teacher-forced parity: legal flips per level %s, TSDF max err %.2e over %d voxels' % (tag, flips, err, n))
+    return flips

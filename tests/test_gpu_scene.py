@@ -1,0 +1,90 @@
+"""-m gpu, SURVEY 8(f1): the whole-scene path at scene scale -- the call chain of the reference's test_scene.py:66-104
+(data set -> collate -> update_sizes -> forward -> pad removal -> save_predictions) on a batch-1, non-cubic,
+1.38 M-site scene (128 x 320 x 256 after padding), against the CPU oracle generator over the WHOLE scene (teacher-forced,
+helpers.compare_teacher_forced: no region is excluded, legal threshold flips are counted) and the oracle marching cubes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import mcubes
+from helpers import compare_teacher_forced
+
+pytestmark = pytest.mark.gpu
+DIMS = (120, 310, 250)          # true extent; padded to (128, 320, 256) by the data set (multiples of 32)
+
+
+def _scene_sample(tmp_path, dims=DIMS, seed=0):
+    from sgnn_b200 import scene_io
+    from sgnn_b200.synth import synthetic_scene
+    locs, sdf = synthetic_scene(dims, seed)
+    os.makedirs(str(tmp_path / 'in'), exist_ok=True), os.makedirs(str(tmp_path / 'tgt'), exist_ok=True)
+    for sub in ('in', 'tgt'):
+        scene_io.save_scene(str(tmp_path / sub / 'room.sdf'), locs, sdf, list(dims))
+    with open(str(tmp_path / 'tgt' / 'room.knw'), 'wb') as f:
+        f.write(open(str(tmp_path / 'tgt' / 'room.sdf'), 'rb').read()[:8 * 3 + 4 + 64])
+        f.write(np.zeros(dims[0] * dims[1] * dims[2], dtype=np.uint8).tobytes())
+    ds = scene_io.SceneDataset([str(tmp_path / 'in' / 'room.sdf')], [128, 64, 64], 3.0, 4, 128, 0, str(tmp_path / 'tgt'))
+    assert len(ds) == 1
+    return scene_io.collate([ds[0]])
+
+
+@pytest.mark.parametrize('mode', ['tc32', 'exact'])
+def test_scene_scale_batch1_against_oracle_whole_scene(tmp_path, mode):
+    import sgnn_b200
+    from genmodel import OracleGenModel
+    from sgnn_b200 import scene
+    from sgnn_b200.synth import fill_parameters
+    sample = _scene_sample(tmp_path)
+    pdims = tuple(int(v) for v in sample['sdf'].shape[2:])
+    assert pdims == (128, 320, 256) and sample['input'][0].shape[0] >= 1_000_000
+    ora = OracleGenModel(input_dim=64)
+    fill_parameters(ora, 4)
+    ora.eval()
+    ora.set_sizes(pdims)
+    m = sgnn_b200.GenModel(8, 64, 1, 16, 16, 4, True, True, 1, 1)
+    m.load_state_dict(ora.state_dict())
+    m = m.cuda().eval()
+    m.conv_mode = mode
+    # the raw forward (what run_scene calls), compared over the whole scene
+    m.update_sizes(np.array(pdims), np.array(pdims) // 8)
+    got = m([sample['input'][0], sample['input'][1].cuda()], np.ones(5, dtype=np.float32))
+    compare_teacher_forced(ora, sample['input'][0], sample['input'][1], got, margin=1e-5, tol_logit=1e-4, tol_sdf=1e-3,
+                           max_flips=8, tag='scene %s %s' % (pdims, mode))
+    # the driver: same numbers after pad removal, nothing at or beyond the true extent
+    timings = {}
+    inputs, out = scene.run_scene(m, sample, output_path=None, timings=timings)
+    (gl, gs), _ = got
+    keep = (gl[:, 0] < DIMS[0]) & (gl[:, 1] < DIMS[1]) & (gl[:, 2] < DIMS[2])
+    assert torch.equal(out[0], gl[keep]) and torch.equal(out[1], gs[keep])
+    assert inputs[0].shape[0] == sample['input'][0].shape[0] and int(out[0][:, 1].max()) < DIMS[1]
+    print('run_scene %s: %d input sites -> %d output voxels, forward %.1f ms' % (mode, inputs[0].shape[0], out[0].shape[0],
+                                                                               timings['forward_ms']))
+
+
+def test_run_scene_writes_the_reference_meshes(tmp_path):
+    """save_predictions step on a smaller scene: both .ply files equal, byte for byte, what the reference's writer gives
+    for the oracle marching cubes of the same dense grids (data_util.py:262-281)."""
+    import sgnn_b200
+    from sgnn_b200 import mesh, scene
+    from sgnn_b200.synth import fill_parameters
+    dims = (40, 90, 70)
+    sample = _scene_sample(tmp_path, dims, seed=3)
+    m = sgnn_b200.GenModel(8, 64, 1, 16, 16, 4, True, True, 1, 1)
+    fill_parameters(m, 4)
+    m = m.cuda().eval()
+    out_dir = str(tmp_path / 'vis')
+    timings = {}
+    inputs, out = scene.run_scene(m, sample, output_path=out_dir, timings=timings)
+    assert sorted(os.listdir(out_dir)) == ['roominput-mesh.ply', 'roompred-mesh.ply']
+    hi = np.maximum(inputs[0].numpy().max(0)[:3], out[0].cpu().numpy().max(0)[:3]) + 1
+    for fname, locs, vals in (('roominput-mesh.ply', inputs[0].numpy(), inputs[1].cpu().numpy()[:, 0]),
+                              ('roompred-mesh.ply', out[0].cpu().numpy(), out[1].cpu().numpy()[:, 0])):
+        dense = np.full(tuple(hi), -np.inf, dtype=np.float32)
+        dense[locs[:, 0], locs[:, 1], locs[:, 2]] = vals
+        V, F = mcubes.marching_cubes(dense, 0.0, 2.9, 10.0)
+        want = str(tmp_path / ('want-' + fname))
+        mesh.save_to_ply(want, V, np.full((V.shape[0], 3), 220, dtype=np.uint8), F)
+        assert V.shape[0] > 1000 and open(os.path.join(out_dir, fname), 'rb').read() == open(want, 'rb').read()
+    assert set(timings) == {'forward_ms', 'pad_removal_ms', 'meshes_ms'}
