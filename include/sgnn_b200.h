@@ -98,6 +98,14 @@ int sgnn_grid_lookup(const SgnnGrid* g, const int32_t* coords, int64_t n, int sh
  * upstream Metadata::getSubmanifoldRuleBook).  nbr: dev [27][n] int32. */
 int sgnn_rulebook_submanifold(const SgnnGrid* g, const int32_t* coords, int64_t n, int32_t* nbr,
                               void* stream);
+/* The same rulebook in COMPACT form, for site sets whose rows have few neighbours (the 5 %-occupancy encoder input,
+ * model.py:32,38,40: 2.3 of 27 offsets present -- the dense table is 108 B/site of which 9 B are rules): per site only the
+ * PRESENT offsets, in ascending k (centre included), packed k << 27 | input_row:
+ *   cnt   dev [n] uint8      number of present offsets of the site (1..27)
+ *   slots dev [27][n] int32  slots[s][i], s < cnt[i]; entries at s >= cnt[i] are NOT written (allocate 27 * n, touch few)
+ * upstream: the same Metadata::getSubmanifoldRuleBook, regrouped per output row.  n < 2^27. */
+int sgnn_rulebook_submanifold_compact(const SgnnGrid* g, const int32_t* coords, int64_t n, int32_t* slots, uint8_t* cnt,
+                                      void* stream);
 
 /* ---- a4 (rules): filter 2 stride 2 rulebook (upstream Metadata::getRuleBook).
  *   parent   dev [n_fine]        coarse_row * 8 + k, or -1 if the fine site has no coarse parent
@@ -146,7 +154,16 @@ typedef struct SgnnConvArgs {
 } SgnnConvArgs;
 /* tensor-core calls: `workspace` already holds this weight's prepared filter bank (sgnn_conv_tc32_prepare): skip the preparation */
 #define SGNN_CONV_PREPARED 1
+/* sgnn_conv_forward kernel selection (A/B; the result bits do not depend on it): force / forbid the lane = (row, channel
+ * group) kernel of csrc/conv_sp.cu (K = 27 only), by default used for K = 27 launches of <= 4096 rows */
+#define SGNN_CONV_ROWLANE 2
+#define SGNN_CONV_NO_ROWLANE 4
 int sgnn_conv_forward(const SgnnConvArgs* args, void* stream);
+/* sgnn_conv_forward (fp32, K = 27, not child mode) over a compact rulebook (sgnn_rulebook_submanifold_compact): args->nbr is
+ * ignored, args->nbr_stride is the slot stride (n).  Visits only the present offsets of a row; the same fmaf chain (k ascending,
+ * ci ascending, absent offsets skipped as oracle/o3.c skips them) => bit-identical to sgnn_conv_forward.  (Cout, Cin) in
+ * {(8,1), (8,8), (12,8), (12,12), (16,12), (16,16)}, else SGNN_E_UNSUPPORTED.  csrc/conv_sp.cu. */
+int sgnn_conv_forward_compact(const SgnnConvArgs* args, const int32_t* slots, const uint8_t* cnt, void* stream);
 
 /* ---- a3 / a4 / a9 on the tensor cores: the same operation as sgnn_conv_forward for fp32 features with Cout = 16
  * and Cin <= 48 (every wide layer of the generator: model.py:179,186,254 and the FullyConvolutionalNet blocks),
@@ -325,6 +342,8 @@ typedef struct SgnnGeneratorOut {
 #define SGNN_GEN_CAND_LOCS 1        /* materialise the candidate coordinates of every level (model.py:247,336) */
 #define SGNN_GEN_PROFILE 2          /* time every convolution launch with CUDA events (adds one sync at the end) */
 #define SGNN_GEN_TC32 4             /* run the Cout = 16 convolutions through sgnn_conv_forward_tc32 (tensor cores) */
+#define SGNN_GEN_DENSE_RULES 8      /* A/B: dense neighbour table + sgnn_conv_forward on the encoder's input level instead of the
+                                     * compact rulebook + sgnn_conv_forward_compact (same bits either way) */
 /* Prepared tensor-core filter banks of every Cout = 16 convolution of the generator, built once per weight set: with
  * w->prepared set, SGNN_GEN_TC32 passes launch no preparation kernels (~30 launches per pass otherwise). */
 size_t sgnn_generator_prepared_bytes(const SgnnGeneratorW* w);

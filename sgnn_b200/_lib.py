@@ -86,6 +86,7 @@ class SgnnGeneratorOut(C.Structure):
 GEN_CAND_LOCS = 1
 GEN_PROFILE = 2
 GEN_TC32 = 4
+GEN_DENSE_RULES = 8
 
 _P, _I, _L, _Z = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
 _G, _E = C.POINTER(SgnnGrid), C.POINTER(SgnnEpilogue)
@@ -101,6 +102,8 @@ SIGNATURES = {
     'sgnn_rulebook_submanifold': (_I, [_G, _P, _L, _P, _P]),
     'sgnn_rulebook_strided': (_I, [_G, _P, _L, _P, _P, _L, _P]),
     'sgnn_conv_forward': (_I, [C.POINTER(SgnnConvArgs), _P]),
+    'sgnn_conv_forward_compact': (_I, [C.POINTER(SgnnConvArgs), _P, _P, _P]),
+    'sgnn_rulebook_submanifold_compact': (_I, [_G, _P, _L, _P, _P, _P]),
     'sgnn_conv_tc32_workspace_bytes': (_Z, [_I, _I, _I]),
     'sgnn_conv_forward_tc32': (_I, [C.POINTER(SgnnConvArgs), _P, _Z, _P]),
     'sgnn_conv_tc32_prepare': (_I, [_P, _I, _I, _I, _I, _P, _Z, _P]),

@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=../libsgnn_b200.so
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v"
-SRCS="scan.cu grid.cu conv.cu pointwise.cu generate.cu dense.cu generator.cu conv_tc.cu conv_tc32.cu conv_ur.cu conv_urc.cu mcubes.cu"
+SRCS="scan.cu grid.cu conv.cu pointwise.cu generate.cu dense.cu generator.cu conv_tc.cu conv_tc32.cu conv_ur.cu conv_urc.cu conv_sp.cu mcubes.cu"
 OBJ=$(mktemp -d)
 trap 'rm -rf "$OBJ"' EXIT
 : > build.log

@@ -754,6 +754,15 @@ static int check_epilogue(const SgnnEpilogue& e, bool need_vec) {
 int sgnn_conv_tc_bf16(const void* in, int ld_in, const int* tbl, long long tbl_stride, int K, int mode, const void* w,
                       int cin, int cout, long long n_out, const SgnnEpilogue* ep, cudaStream_t st);  // conv_tc.cu
 
+int sgnn_conv_forward_rowlane(const SgnnConvArgs* a, cudaStream_t st);   // conv_sp.cu
+
+// K = 27 launches up to this many rows are latency bound on the staged row-owner pipeline (27 stages of cp.async -> wait ->
+// compute: a flat 25-27 us even at 256 rows); the lane = (row, channel group) kernel of conv_sp.cu takes them (G taps of
+// loads in flight per thread).  Same fmaf chain, same bits.  Measured (scratch/sp_bench.py, B200): 2048 rows 16->16: 18.4 vs
+// 23.5 us through ctypes; at 16 k rows and beyond, and for K = 8 at every size, the row-owner kernel wins (its weights are
+// warp-uniform broadcasts, the row-lane kernel re-reads them per row: 25.5 vs 23.6 us at 16 k rows, 142 vs 80 us at 126 k).
+#define SGNN_ROWLANE_MAX_ROWS 4096
+
 extern "C" int sgnn_conv_forward(const SgnnConvArgs* a, void* stream) {
   if (!a || a->n_out < 0 || a->cin <= 0 || a->cout <= 0 || !a->weight) return SGNN_E_INVALID;
   if (a->dtype == SGNN_BF16) {   // tcgen05 path (conv_tc.cu): bf16 features/weights/outputs, fp32 accumulation in TMEM
@@ -784,6 +793,11 @@ extern "C" int sgnn_conv_forward(const SgnnConvArgs* a, void* stream) {
     if (!aligned16(a->weight)) return SGNN_E_ALIGN;
     if (a->residual && (!aligned16(a->residual) || (a->ld_res & 3))) return SGNN_E_ALIGN;
     const bool vec = aligned16(a->in) && (a->ld_in & 3) == 0;
+    if (!p.child_mode && !(a->flags & SGNN_CONV_NO_ROWLANE) &&
+        a->K == 27 && (a->n_out <= SGNN_ROWLANE_MAX_ROWS || (a->flags & SGNN_CONV_ROWLANE))) {
+      rc = sgnn_conv_forward_rowlane(a, st);
+      if (rc != SGNN_E_UNSUPPORTED) return rc;
+    }
     {
       bool handled = false;
       if (vec && p.child_mode && p.cout == 16 && p.cin == 48 && (p.n_out & 7) == 0) return launch_child<16, 48>(p, st);

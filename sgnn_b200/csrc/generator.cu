@@ -38,6 +38,7 @@ struct Ctx {
   void* stream;
   bool profile;
   bool tc32;
+  bool compact;    // compact rulebook + conv_sp.cu on the encoder's input level
   int n_ev;
   const SgnnGeneratorW* w;
   long long tc32_min_rows, ur_min_rows;
@@ -67,6 +68,8 @@ struct Level {
   int32_t* coords;
   int32_t* nbr;
   void* plan;      // unique-row tile plan of nbr (conv_ur.cu) or nullptr
+  int32_t* slots;  // compact rulebook (grid.cu COMPACT / conv_sp.cu) instead of nbr, or nullptr
+  uint8_t* cnt;
   int64_t n;
   int dims[3];
 };
@@ -119,7 +122,7 @@ static int build_plan(Ctx& c, Level* L, int cout) {
 
 // a1 + a2: site set from explicit coordinates, with its 27-neighbour table
 static int build_level(Ctx& c, const void* coords, int is64, int64_t n, int nb, const int dims[3], int32_t* status,
-                       Level* L) {
+                       Level* L, bool compact = false) {
   grid_shape(&L->g, nb, dims);
   for (int i = 0; i < 3; ++i) L->dims[i] = dims[i];
   L->n = n;
@@ -134,8 +137,13 @@ static int build_level(Ctx& c, const void* coords, int is64, int64_t n, int nb, 
   RC(sgnn_grid_build(&L->g, coords, is64, n, ci32, status, scr, sb, c.stream));
   c.ar.off = mark;
   ALLOC(nbr, int32_t, 27 * n);
+  L->plan = nullptr; L->slots = nullptr; L->cnt = nullptr;
+  if (compact && n < (1LL << 27)) {
+    ALLOC(cnt, uint8_t, n);
+    L->nbr = nullptr; L->slots = nbr; L->cnt = cnt;
+    return sgnn_rulebook_submanifold_compact(&L->g, ci32, n, nbr, cnt, c.stream);
+  }
   L->nbr = nbr;
-  L->plan = nullptr;
   return sgnn_rulebook_submanifold(&L->g, ci32, n, nbr, c.stream);
 }
 
@@ -151,7 +159,7 @@ static int coarsen_begin(Ctx& c, const Level& f, Level* L) {
   ALLOC(mask, uint64_t, L->g.n_words);
   ALLOC(prefix, int32_t, L->g.n_words + 1);
   L->g.mask = mask; L->g.prefix = prefix; L->g.row_of_rank = nullptr;
-  L->n = -1; L->coords = nullptr; L->nbr = nullptr; L->plan = nullptr;
+  L->n = -1; L->coords = nullptr; L->nbr = nullptr; L->plan = nullptr; L->slots = nullptr; L->cnt = nullptr;
   const size_t mark = c.ar.off;
   const size_t sb = sgnn_scan_scratch_bytes(L->g.n_words);
   ALLOC(scr, char, sb);
@@ -160,13 +168,23 @@ static int coarsen_begin(Ctx& c, const Level& f, Level* L) {
   return SGNN_OK;
 }
 
-// one synchronisation for up to 4 pending levels
-static int read_counts(Ctx& c, Level** lv, int n) {
+// one host read for up to 4 pending levels, in two halves: post() enqueues the 4-byte copies and records an event,
+// wait() blocks on THAT EVENT only -- kernels enqueued in between (convolutions that do not depend on the counts) keep the
+// GPU busy while the host reads the counts and enqueues the dependent work behind them, so the read costs no GPU idle time.
+static thread_local cudaEvent_t g_count_ev = nullptr;
+static int counts_post(Ctx& c, Level** lv, int n) {
   int32_t* pin;
   RC(pinned_slots(&pin));
+  if (!g_count_ev) SGNN_CUDA(cudaEventCreateWithFlags(&g_count_ev, cudaEventDisableTiming));
   for (int i = 0; i < n; ++i)
     SGNN_CUDA(cudaMemcpyAsync(pin + 1 + i, lv[i]->g.prefix + lv[i]->g.n_words, 4, cudaMemcpyDeviceToHost, c.st));
-  SGNN_CUDA(cudaStreamSynchronize(c.st));
+  SGNN_CUDA(cudaEventRecord(g_count_ev, c.st));
+  return SGNN_OK;
+}
+static int counts_wait(Ctx& c, Level** lv, int n) {
+  int32_t* pin;
+  RC(pinned_slots(&pin));
+  SGNN_CUDA(cudaEventSynchronize(g_count_ev));
   for (int i = 0; i < n; ++i) lv[i]->n = pin[1 + i];
   return SGNN_OK;
 }
@@ -233,7 +251,8 @@ static void* prepared_bank(const SgnnGeneratorW* w, const float* p, int K, int c
 
 static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr, int64_t nbr_stride, int K,
                 int child, const float* w, int cout, int64_t n_out, const float* res, int ld_res, const Epi& a,
-                const Epi& b, int64_t n_in = 0, const void* plan = nullptr) {
+                const Epi& b, int64_t n_in = 0, const void* plan = nullptr, const int32_t* slots = nullptr,
+                const uint8_t* cnt = nullptr) {
   SgnnConvArgs x;
   memset(&x, 0, sizeof(x));
   x.in = in; x.ld_in = ld_in; x.dtype = SGNN_F32; x.nbr = nbr; x.nbr_stride = nbr_stride; x.K = K;
@@ -249,7 +268,9 @@ static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr,
   }
   int rc = SGNN_E_UNSUPPORTED;
   bool used_tc = false;
-  if (c.tc32 && plan && K == 27 && child && cout == 16 && cin == 48) {
+  if (slots && cnt) {
+    rc = sgnn_conv_forward_compact(&x, slots, cnt, c.stream);
+  } else if (c.tc32 && plan && K == 27 && child && cout == 16 && cin == 48) {
     const size_t wb = (size_t)64 * 4608;
     char* bank = (char*)prepared_bank(c.w, w, K, 1);
     void* ws = bank ? bank + ((sgnn_conv_tc32_workspace_bytes(K, cin, 1) + 255) & ~(size_t)255) : c.ar.get(wb);
@@ -288,8 +309,9 @@ static int conv(Ctx& c, const float* in, int ld_in, int cin, const int32_t* nbr,
 static int res_block(Ctx& c, const Level& lv, const SgnnResBlockW& rb, int ch, const float* x_raw, const float* x_bn,
                      const Epi& a, const Epi& b) {
   ALLOC(mid, float, lv.n * ch);
-  RC(conv(c, x_bn, ch, ch, lv.nbr, lv.n, 27, 0, rb.w0, ch, lv.n, nullptr, 0, epi_bn(mid, ch, rb.bn1), kNoEpi, 0, lv.plan));
-  return conv(c, mid, ch, ch, lv.nbr, lv.n, 27, 0, rb.w1, ch, lv.n, x_raw, ch, a, b, 0, lv.plan);
+  RC(conv(c, x_bn, ch, ch, lv.nbr, lv.n, 27, 0, rb.w0, ch, lv.n, nullptr, 0, epi_bn(mid, ch, rb.bn1), kNoEpi, 0, lv.plan,
+          lv.slots, lv.cnt));
+  return conv(c, mid, ch, ch, lv.nbr, lv.n, 27, 0, rb.w1, ch, lv.n, x_raw, ch, a, b, 0, lv.plan, lv.slots, lv.cnt);
 }
 
 // FullyConvolutionalNet(reps 1, [c,c,c], residual) + BatchNormReLU(3c): J0 [n, 3c]   (model.py:180-181,255-256)
@@ -305,18 +327,18 @@ static int fcn(Ctx& c, const Level& lv0, const SgnnFcnW& f, const float* x_raw, 
   int32_t *par01, *chi01, *par12 = nullptr, *chi12 = nullptr;
   RC(coarsen_begin(c, lv0, &lv1));
   RC(coarsen_begin(c, lv1, &lv2));
-  {
-    Level* pend[2] = {&lv1, &lv2};
-    RC(read_counts(c, pend, 2));
-  }
+  Level* pend[2] = {&lv1, &lv2};
+  RC(counts_post(c, pend, 2));
+  // the finest residual block does not depend on the coarse counts: it runs while the host reads them
+  ALLOC(y0_bn, float, lv0.n * ch);
+  RC(res_block(c, lv0, f.blk[0], ch, x_raw, x_bn, epi_bn(J0, 3 * ch, f.bn_join), epi_bn(y0_bn, ch, f.bn_down[0])));
+  RC(counts_wait(c, pend, 2));
   RC(coarsen_finish(c, lv0, &lv1, &par01, &chi01, true));
   RC(coarsen_finish(c, lv1, &lv2, &par12, &chi12, true));
   RC(build_plan(c, &lv1, ch));
   RC(build_plan(c, &lv2, ch));
   rows[1] = lv1.n;
   rows[2] = lv2.n;
-  ALLOC(y0_bn, float, lv0.n * ch);
-  RC(res_block(c, lv0, f.blk[0], ch, x_raw, x_bn, epi_bn(J0, 3 * ch, f.bn_join), epi_bn(y0_bn, ch, f.bn_down[0])));
   ALLOC(J1, float, lv1.n * 2 * ch);
   if (lv1.n) {
     ALLOC(z1_raw, float, lv1.n * ch);
@@ -385,6 +407,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
   c.st = (cudaStream_t)stream; c.stream = stream;
   c.profile = (flags & SGNN_GEN_PROFILE) != 0; c.n_ev = 0;
   c.tc32 = (flags & SGNN_GEN_TC32) != 0;
+  c.compact = (flags & SGNN_GEN_DENSE_RULES) == 0;
   c.w = w;
   c.tc32_min_rows = w->tc32_min_rows > 0 ? w->tc32_min_rows : SGNN_DEFAULT_TC32_MIN_ROWS;
   c.ur_min_rows = w->ur_min_rows > 0 ? w->ur_min_rows : SGNN_DEFAULT_UR_MIN_ROWS;
@@ -400,7 +423,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
     Level lv;
     GALLOC(status, int32_t, 1);
     if ((rc = (cudaMemsetAsync(status, 0, 4, c.st) == cudaSuccess ? SGNN_OK : SGNN_E_CUDA)) != SGNN_OK) break;
-    GEN(build_level(c, coords, coords_i64, n, nb, dims, status, &lv));
+    GEN(build_level(c, coords, coords_i64, n, nb, dims, status, &lv, c.compact));
     out->rows[0] = n;
     Skip skips[4];
     const float* x = feats;
@@ -417,17 +440,8 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
     if ((rc = (cudaMemcpyAsync(pinb + 8, status, 4, cudaMemcpyDeviceToHost, c.st) == cudaSuccess ? SGNN_OK : SGNN_E_CUDA)) !=
         SGNN_OK)
       break;
-    {
-      Level* pend[3] = {&enc_lv[1], &enc_lv[2], &enc_lv[3]};
-      GEN(read_counts(c, pend, 3));
-    }
-    if (pinb[8]) { rc = SGNN_E_INVALID; break; }   // a coordinate outside [0, dims) x [0, nb): scn raises here too
-    GEN(coarsen_finish(c, enc_lv[0], &enc_lv[1], &enc_par[0], &enc_chi[0], true));
-    GEN(coarsen_finish(c, enc_lv[1], &enc_lv[2], &enc_par[1], &enc_chi[1], true));
-    GEN(coarsen_finish(c, enc_lv[2], &enc_lv[3], &enc_par[2], &enc_chi[2], false));
-    GEN(build_plan(c, &lv, w->enc[0].c));
-    GEN(build_plan(c, &enc_lv[1], w->enc[1].c));
-    GEN(build_plan(c, &enc_lv[2], w->enc[2].c));
+    Level* enc_pend[3] = {&enc_lv[1], &enc_lv[2], &enc_lv[3]};
+    GEN(counts_post(c, enc_pend, 3));
     bool enc_ok = true;
     for (int l = 0; l < 3 && enc_ok; ++l) {
       const SgnnEncLevelW& e = w->enc[l];
@@ -436,10 +450,21 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       GALLOC(a_raw, float, lv.n * ch);
       GALLOC(a_bn, float, lv.n * ch);
       GEN(conv(c, x, ld_x, e.cin, lv.nbr, lv.n, 27, 0, e.w_in, ch, lv.n, nullptr, 0, epi(a_raw, ch),
-               epi_bn(a_bn, ch, e.res.bn0), 0, lv.plan));
+               epi_bn(a_bn, ch, e.res.bn0), 0, lv.plan, lv.slots, lv.cnt));
       GALLOC(skip, float, lv.n * ch);
       GEN(res_block(c, lv, e.res, ch, a_raw, a_bn, epi_bn(skip, ch, e.bn_out), kNoEpi));
       skips[l].g = lv.g; skips[l].f = skip; skips[l].c = ch; skips[l].n = lv.n;
+      if (l == 0) {
+        // the three convolutions above ran on the input level while the host waited for the pyramid's counts (out-of-range
+        // coordinates were masked out of the site set by sgnn_grid_build, so that work was safe; it is discarded here)
+        GEN(counts_wait(c, enc_pend, 3));
+        if (pinb[8]) { rc = SGNN_E_INVALID; break; }   // a coordinate outside [0, dims) x [0, nb): scn raises here too
+        GEN(coarsen_finish(c, enc_lv[0], &enc_lv[1], &enc_par[0], &enc_chi[0], true));
+        GEN(coarsen_finish(c, enc_lv[1], &enc_lv[2], &enc_par[1], &enc_chi[1], true));
+        GEN(coarsen_finish(c, enc_lv[2], &enc_lv[3], &enc_par[2], &enc_chi[2], false));
+        GEN(build_plan(c, &enc_lv[1], w->enc[1].c));
+        GEN(build_plan(c, &enc_lv[2], w->enc[2].c));
+      }
       Level cl = enc_lv[l + 1];
       int32_t* chi = enc_chi[l];
       out->rows[l + 1] = cl.n;

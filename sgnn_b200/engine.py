@@ -134,6 +134,15 @@ def rulebook_submanifold(grid):
     return nbr
 
 
+def rulebook_submanifold_compact(grid):
+    """a2, compact form: (slots int32 [27, n] -- only slots[s][i], s < cnt[i], are defined: k << 27 | row --, cnt uint8 [n])."""
+    slots = torch.zeros((27, grid.n), dtype=torch.int32, device=grid.device)
+    cnt = torch.empty(grid.n, dtype=torch.uint8, device=grid.device)
+    check(lib.sgnn_rulebook_submanifold_compact(grid.ref(), _ptr(grid.coords), grid.n, _ptr(slots), _ptr(cnt), _stream()),
+          'sgnn_rulebook_submanifold_compact')
+    return slots, cnt
+
+
 def rulebook_strided(fine, coarse):
     """a4: parent int32 [n_fine] (row*8+k) and children int32 [8, n_coarse]."""
     parent = torch.empty(fine.n, dtype=torch.int32, device=fine.device)
@@ -159,15 +168,19 @@ def _epilogue(out, scale=None, shift=None, relu=False):
 
 
 def conv(x, nbr, weight, n_out, out_a, child_mode=False, residual=None, scale_a=None, shift_a=None,
-         relu_a=False, out_b=None, scale_b=None, shift_b=None, relu_b=False, tc32=False, plan=None):
+         relu_a=False, out_b=None, scale_b=None, shift_b=None, relu_b=False, tc32=False, plan=None, compact=None, flags=0):
     """a3/a4/a9: out[j] = sum_k x[nbr[k][j]] @ W[k]  (+residual, affine, relu; two output slots).
     x / out_* may be column views of wider row-major buffers (stride(1) == 1).
     tc32=True: the tensor-core path for fp32 features (sgnn_conv_forward_tc32: Cout = 16, Cin <= 48; fp32 accuracy,
-    not the fixed fmaf order); raises for unsupported shapes."""
+    not the fixed fmaf order); raises for unsupported shapes.
+    compact=(slots, cnt) of rulebook_submanifold_compact: sgnn_conv_forward_compact (nbr may be None)."""
     _need_cuda(x, nbr, weight, out_a, residual, out_b)
     K, cin, cout = weight.shape
     assert weight.is_contiguous() and weight.dtype in (torch.float32, torch.bfloat16)
     assert x.dtype == weight.dtype == out_a.dtype and x.stride(1) == 1 and x.shape[1] == cin
+    if compact is not None:
+        _need_cuda(*compact)
+        nbr = compact[0]
     assert nbr.dtype == torch.int32 and nbr.shape[0] == K and nbr.stride(1) == 1
     a = SgnnConvArgs()
     a.in_ = x.data_ptr()
@@ -190,9 +203,13 @@ def conv(x, nbr, weight, n_out, out_a, child_mode=False, residual=None, scale_a=
         a.ld_res = 0
     a.a = _epilogue(out_a, scale_a, shift_a, relu_a)
     a.b = _epilogue(out_b, scale_b, shift_b, relu_b)
+    a.flags = int(flags)          # SGNN_CONV_ROWLANE (2) / SGNN_CONV_NO_ROWLANE (4): kernel selection A/B, same bits
     ctx = PROFILER.conv(x, nbr, weight, int(n_out), child_mode, residual is not None,
                         out_b is not None) if PROFILER is not None else None
-    if plan is not None and child_mode:
+    if compact is not None:
+        check(lib.sgnn_conv_forward_compact(C.byref(a), _ptr(compact[0]), _ptr(compact[1]), _stream()),
+              'sgnn_conv_forward_compact')
+    elif plan is not None and child_mode:
         wb = 64 * 4608
         ws = _scratch(wb, x.device)
         check(lib.sgnn_conv_forward_tc32_urc(C.byref(a), _ptr(plan), C.c_void_p(ws.data_ptr()), wb, _stream()),

@@ -226,6 +226,7 @@ class GenModel(nn.Module):
         self.conv_mode = 'tc32'
         self.tc32_min_rows = 0       # row thresholds of the tensor-core paths (0 = library defaults, SgnnGeneratorW)
         self.ur_min_rows = 0
+        self.dense_rules = False     # A/B: dense neighbour table on the encoder's input level (default: compact rulebook; same bits)
 
     # model.py:357-369.  The sizes are upper bounds of mode-0 InputLayers; the reference doubles
     # refine_max_dim inside the k loop -- mirrored, not "fixed": bounds only grow.

@@ -165,7 +165,8 @@ class NativeGenerator(object):
                                             locs.shape[0], nb, dims, C.c_void_p(self.arena.data_ptr()),
                                             self.arena.numel(), (_lib.GEN_CAND_LOCS if want_cand_locs else 0) |
                                             (_lib.GEN_PROFILE if self.profile else 0) |
-                                            (_lib.GEN_TC32 if getattr(m, 'conv_mode', 'tc32') == 'tc32' else 0),
+                                            (_lib.GEN_TC32 if getattr(m, 'conv_mode', 'tc32') == 'tc32' else 0) |
+                                            (_lib.GEN_DENSE_RULES if getattr(m, 'dense_rules', False) else 0),
                                             C.byref(out), stream)
             if rc != -6:
                 break

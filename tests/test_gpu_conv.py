@@ -262,3 +262,141 @@ def test_dispatched_conv_kernels_bit_identical_to_o3():
             E.conv(xb.cuda()[:, :cin], nbr.cuda(), w.cuda(), no, out, child_mode=child, residual=r.cuda(),
                    scale_a=s_.cuda(), shift_a=t_.cuda(), relu_a=True)
             assert torch.equal(out.cpu(), want), (cin, cout, child)
+
+
+# ------------------------------------------------------------------ compact rulebook + conv_sp.cu (encoder input level)
+def _decode_compact(slots, cnt):
+    """(slots [27,n], cnt [n]) -> dense [27,n] table with -1 for absent; asserts ascending k within a row."""
+    slots, cnt = slots.cpu().numpy().astype(np.uint32), cnt.cpu().numpy()
+    n = cnt.shape[0]
+    dense = np.full((27, n), -1, dtype=np.int32)
+    last_k = np.full(n, -1, dtype=np.int64)
+    for s in range(int(cnt.max()) if n else 0):
+        live = np.nonzero(cnt > s)[0]
+        e = slots[s, live]
+        k, r = (e >> 27).astype(np.int64), (e & 0x7ffffff).astype(np.int32)
+        assert (k > last_k[live]).all(), 'offsets of a row must ascend'
+        last_k[live] = k
+        dense[k, live] = r
+    return dense
+
+
+@pytest.mark.parametrize('nb,dims,occ', [(2, (12, 10, 14), 0.35), (3, (20, 70, 130), 0.05), (1, (9, 9, 64), 0.9)])
+def test_compact_rulebook_equals_dense_table(nb, dims, occ):
+    E = _E()
+    rng = np.random.default_rng(nb * 7 + dims[2])
+    c = random_coords(rng, nb, dims, occ)
+    c = c[rng.permutation(c.shape[0])]                        # caller order (row_of_rank in play), x on word edges for 130
+    g = E.build_grid(torch.from_numpy(c).cuda(), nb, dims)
+    nbr = E.rulebook_submanifold(g)
+    slots, cnt = E.rulebook_submanifold_compact(g)
+    assert np.array_equal(nbr.cpu().numpy(), nbr_table(c))
+    assert np.array_equal(_decode_compact(slots, cnt), nbr.cpu().numpy())
+    assert np.array_equal(cnt.cpu().numpy(), (nbr.cpu().numpy() >= 0).sum(0).astype(np.uint8))
+
+
+@pytest.mark.parametrize('cin,cout', [(1, 8), (8, 8), (8, 12), (12, 12), (12, 16), (16, 16)])
+@pytest.mark.parametrize('occ', [0.05, 0.5])
+def test_compact_conv_bit_identical_to_dense_table_conv_and_oracle(cin, cout, occ):
+    E = _E()
+    rng = np.random.default_rng(cin * 17 + cout)
+    nb, dims = 2, (14, 12, 70)
+    c = random_coords(rng, nb, dims, occ)
+    c = c[rng.permutation(c.shape[0])]
+    n = c.shape[0]
+    ld = (cin + 3) // 4 * 4
+    xbuf = torch.full((n, ld), float('nan'))
+    xbuf[:, :cin] = torch.from_numpy(rng.standard_normal((n, cin)).astype(np.float32))
+    w = torch.from_numpy((rng.standard_normal((27, cin, cout)) * 0.1).astype(np.float32))
+    r = torch.from_numpy(rng.standard_normal((n, cout)).astype(np.float32))
+    sa, ta = torch.rand(cout) + 0.5, torch.rand(cout) - 0.5
+    g = E.build_grid(torch.from_numpy(c).cuda(), nb, dims)
+    nbr = E.rulebook_submanifold(g)
+    comp = E.rulebook_submanifold_compact(g)
+    xd = xbuf.cuda()
+    # plain
+    a = torch.empty((n, cout), device='cuda')
+    b = torch.empty((n, cout), device='cuda')
+    E.conv(xd[:, :cin], nbr, w.cuda(), n, a)
+    E.conv(xd[:, :cin], None, w.cuda(), n, b, compact=comp)
+    assert torch.equal(a, b) and torch.equal(b.cpu(), o3.conv(xbuf[:, :cin], nbr.cpu(), w, n))
+    # residual + two epilogue slots, one of them a column view of a wider buffer
+    wide = torch.full((n, 48), -7.0, device='cuda')
+    raw = torch.empty((n, cout), device='cuda')
+    E.conv(xd[:, :cin], None, w.cuda(), n, wide[:, 16:16 + cout], residual=r.cuda(), scale_a=sa.cuda(), shift_a=ta.cuda(),
+           relu_a=True, out_b=raw, compact=comp)
+    assert torch.equal(wide[:, 16:16 + cout].cpu(), o3.conv(xbuf[:, :cin], nbr.cpu(), w, n, residual=r, scale=sa, shift=ta, relu=True))
+    assert torch.equal(raw.cpu(), o3.conv(xbuf[:, :cin], nbr.cpu(), w, n, residual=r))
+    assert (wide[:, :16] == -7).all() and (wide[:, 16 + cout:] == -7).all()
+
+
+def test_generator_same_bits_with_compact_and_dense_rules():
+    """The native generator with the compact rulebook on the encoder input level (default) and with the dense table (A/B flag):
+    identical outputs, both convolution modes."""
+    import sgnn_b200
+    from sgnn_b200.synth import fill_parameters, synthetic_batch
+    m = sgnn_b200.GenModel(8, [32, 32, 32], 1, 16, 16, 4, True, True, 1, 1)
+    fill_parameters(m, 0)
+    m = m.cuda().eval()
+    locs, feats = synthetic_batch(3, [32, 32, 32], 0.08)
+    ones = np.ones(5, dtype=np.float32)
+    for mode in ('exact', 'tc32'):
+        m.conv_mode = mode
+        m.dense_rules = False
+        (la, sa), lva = m([locs.cuda(), feats.cuda()], ones)
+        m.dense_rules = True
+        (lb, sb), lvb = m([locs.cuda(), feats.cuda()], ones)
+        assert torch.equal(la, lb) and torch.equal(sa, sb)
+        for x, y in zip(lva, lvb):
+            assert torch.equal(x[0], y[0]) and torch.equal(x[1], y[1])
+
+
+@pytest.mark.parametrize('cin,cout,K', [(1, 8, 27), (8, 8, 27), (8, 12, 27), (12, 12, 27),
+                                        (12, 16, 27), (16, 16, 27), (26, 16, 27), (30, 16, 27), (34, 16, 27)])
+def test_rowlane_kernel_same_bits_as_row_owner_kernel(cin, cout, K):
+    """sgnn_conv_forward's two kernels for dense tables (conv.cu row-owner, conv_sp.cu lane = (row, channel group)) forced
+    one after the other on a launch larger than the automatic threshold: identical bits, equal to oracle O3."""
+    E = _E()
+    rng = np.random.default_rng(cin * 13 + cout + K)
+    nb, dims = 2, (16, 14, 40)
+    c = random_coords(rng, nb, dims, 0.6)
+    n_in = c.shape[0]
+    ld = (cin + 7) // 8 * 8
+    xbuf = torch.full((n_in, ld), float('nan'))
+    xbuf[:, :cin] = torch.from_numpy(rng.standard_normal((n_in, cin)).astype(np.float32))
+    w = torch.from_numpy((rng.standard_normal((K, cin, cout)) * 0.1).astype(np.float32))
+    if K == 27:
+        tbl = torch.from_numpy(nbr_table(c))
+        n_out = n_in
+    else:
+        cc, parent, children, cd = coarse_sets(c, dims)
+        tbl = torch.from_numpy(children)
+        n_out = cc.shape[0]
+    assert n_out > 4096
+    r = torch.from_numpy(rng.standard_normal((n_out, cout)).astype(np.float32))
+    sa, ta = torch.rand(cout) + 0.5, torch.rand(cout) - 0.5
+    want = o3.conv(xbuf[:, :cin], tbl, w, n_out, residual=r, scale=sa, shift=ta, relu=True)
+    outs = []
+    for flags in (2, 4):                                     # SGNN_CONV_ROWLANE, SGNN_CONV_NO_ROWLANE
+        o = torch.empty((n_out, cout), device='cuda')
+        raw = torch.empty((n_out, cout), device='cuda')
+        E.conv(xbuf.cuda()[:, :cin], tbl.cuda(), w.cuda(), n_out, o, residual=r.cuda(), scale_a=sa.cuda(), shift_a=ta.cuda(),
+               relu_a=True, out_b=raw, flags=flags)
+        outs.append((o.cpu(), raw.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][0], want)
+
+
+def test_rowlane_small_and_ragged_launches():
+    """The automatic route (K = 27, <= 4096 rows): 1 row, 63/64/65 rows (tile edges), absent-only rows."""
+    E = _E()
+    rng = np.random.default_rng(3)
+    for n in (1, 63, 64, 65, 700):
+        x = torch.from_numpy(rng.standard_normal((n, 16)).astype(np.float32))
+        w = torch.from_numpy((rng.standard_normal((27, 16, 16)) * 0.1).astype(np.float32))
+        nbr = torch.from_numpy(rng.integers(-1, n, (27, n)).astype(np.int32))
+        nbr[:, 0] = -1                                        # a row with no neighbour at all -> zeros (+ epilogue)
+        out = torch.empty((n, 16), device='cuda')
+        E.conv(x.cuda(), nbr.cuda(), w.cuda(), n, out)
+        assert torch.equal(out.cpu(), o3.conv(x, nbr, w, n))
+        assert (out[0] == 0).all()
