@@ -190,6 +190,10 @@ int sgnn_conv_tc32_prepare(const void* weight, int32_t K, int32_t cin, int32_t c
 size_t sgnn_tile_plan_bytes(int64_t n_rows);
 int sgnn_tile_plan_build(const int32_t* nbr, int64_t nbr_stride, int64_t n_rows, void* plan, size_t plan_bytes,
                          void* stream);
+/* sgnn_rulebook_submanifold + sgnn_tile_plan_build in one kernel (the table is written once and not read back): nbr dev
+ * [27][n] and the plan of that table.  Same outputs as the two calls. */
+int sgnn_rulebook_submanifold_plan(const SgnnGrid* g, const int32_t* coords, int64_t n, int32_t* nbr, void* plan,
+                                   size_t plan_bytes, void* stream);
 /* sgnn_conv_forward_tc32 for K = 27, Cin <= 32 (ld_in % 4 == 0), Cout in {8, 12, 16} with a tile plan of args->nbr: the distinct rows of a tile are
  * fetched by TMA (cp.async.bulk, one per row) into shared memory, split into the bf16 planes once, and expanded filter
  * offset by filter offset from shared memory into tensor memory for tcgen05.mma.  Same arithmetic and tolerance as
@@ -281,6 +285,13 @@ int sgnn_heads_flags(const float* x, int32_t ld_x, int32_t c, const float* w_occ
 int sgnn_heads_write(const float* x, int32_t ld_x, int32_t c, const float* cand_out,
                      const int32_t* parent_coords, int64_t n_cand, const uint8_t* flags, const int32_t* offs,
                      int32_t* locs, float* feats, int32_t ld_feats, void* stream);
+/* sgnn_heads_write + the skip join of the NEXT level in one pass (sgnn_concat_skip, model.py:338-355,391,401): columns
+ * [c+2, c+2+c_skip) of a kept row receive the features of the skip site at the row's own (child) coordinates, zeros where the
+ * skip set has none; ld_feats >= c + 2 + c_skip.  Same values as the two calls. */
+int sgnn_heads_write_join(const float* x, int32_t ld_x, int32_t c, const float* cand_out, const int32_t* parent_coords,
+                          int64_t n_cand, const uint8_t* flags, const int32_t* offs, int32_t* locs, float* feats,
+                          int32_t ld_feats, const SgnnGrid* skip_grid, const float* skip_feats, int32_t ld_skip,
+                          int32_t c_skip, void* stream);
 int sgnn_dense_flags(const float* dense_out, int32_t nb, int64_t vol, float* cand_out, uint8_t* flags,
                      int32_t* offs, void* scratch, size_t scratch_bytes, void* stream);
 int sgnn_dense_write(const float* dense_feats, const float* dense_out, int32_t nb, int32_t c, int32_t d0,

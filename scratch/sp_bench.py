@@ -63,5 +63,18 @@ def main():
         run('L%d->L%d stride-2 %d->%d K=8' % (l, l + 1, c, c), x, children, w8, cg.n)
 
 
+def wide():
+    """first convolution of a refinement level (Cin = 34 / 30 / 26 joined rows, ld = 40 / 32): row-lane vs row-owner"""
+    for size, occ, cin in ((16, 0.11, 34), (32, 0.035, 34), (32, 0.15, 30)):
+        locs, _ = synthetic_batch(32, size, occ)
+        g = E.build_grid(locs.to(dev), 32, (size, size, size))
+        nbr = E.rulebook_submanifold(g)
+        ld = (cin + 7) // 8 * 8
+        x = torch.randn((g.n, ld), device=dev)[:, :cin]
+        w = torch.randn((27, cin, 16), device=dev) * 0.1
+        run('%d^3 @%.3f  %d->16 K=27' % (size, occ, cin), x, nbr, w, g.n)
+
+
 if __name__ == '__main__':
+    wide()
     main()

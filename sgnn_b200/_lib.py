@@ -103,6 +103,7 @@ SIGNATURES = {
     'sgnn_rulebook_strided': (_I, [_G, _P, _L, _P, _P, _L, _P]),
     'sgnn_conv_forward': (_I, [C.POINTER(SgnnConvArgs), _P]),
     'sgnn_conv_forward_compact': (_I, [C.POINTER(SgnnConvArgs), _P, _P, _P]),
+    'sgnn_rulebook_submanifold_plan': (_I, [_G, _P, _L, _P, _P, _Z, _P]),
     'sgnn_rulebook_submanifold_compact': (_I, [_G, _P, _L, _P, _P, _P]),
     'sgnn_conv_tc32_workspace_bytes': (_Z, [_I, _I, _I]),
     'sgnn_conv_forward_tc32': (_I, [C.POINTER(SgnnConvArgs), _P, _Z, _P]),
@@ -127,6 +128,7 @@ SIGNATURES = {
     'sgnn_heads_compact': (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _P, _P, _Z, _P]),
     'sgnn_heads_flags': (_I, [_P, _I, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P, _Z, _P]),
     'sgnn_heads_write': (_I, [_P, _I, _I, _P, _P, _L, _P, _P, _P, _P, _I, _P]),
+    'sgnn_heads_write_join': (_I, [_P, _I, _I, _P, _P, _L, _P, _P, _P, _P, _I, _G, _P, _I, _I, _P]),
     'sgnn_dense_flags': (_I, [_P, _I, _L, _P, _P, _P, _P, _Z, _P]),
     'sgnn_dense_write': (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     'sgnn_generator_forward': (_I, [C.POINTER(SgnnGeneratorW), _P, _I, _P, _L, _I, C.POINTER(C.c_int32), _P, _Z, _I,

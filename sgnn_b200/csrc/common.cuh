@@ -74,6 +74,52 @@ __device__ __forceinline__ int grid_row_checked(const GridView& g, int b, int z,
   return grid_row(g, b, z, y, x);
 }
 
+// The 27 submanifold neighbours of site c = (z,y,x,b) (offset id k = (dz+1)*9 + (dy+1)*3 + (dx+1), -1 = absent or outside the
+// extent): shared by the rulebook kernels (grid.cu) and the fused rulebook + tile-plan kernel (conv_ur.cu).  The three
+// x-neighbours of a (z+dz, y+dy) row live in one mask word (two when x sits on a word edge): one word + one prefix load and the
+// three bits are tested in registers.
+__device__ __forceinline__ void rulebook_probe27(const GridView& g, int4 c, int (&idx)[27]) {
+  const int z = c.x, y = c.y, x = c.z, b = c.w;
+  const bool inb = (unsigned)z < (unsigned)g.d0 && (unsigned)y < (unsigned)g.d1 &&
+                   (unsigned)x < (unsigned)g.d2 && (unsigned)b < (unsigned)g.nb;
+  const bool edge = ((x & 63) == 0) || ((x & 63) == 63);
+#pragma unroll
+  for (int dz = -1; dz <= 1; ++dz) {
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int zz = z + dz, yy = y + dy;
+      const int k0 = (dz + 1) * 9 + (dy + 1) * 3;
+      int r0 = -1, r1 = -1, r2 = -1;
+      if (inb && (unsigned)zz < (unsigned)g.d0 && (unsigned)yy < (unsigned)g.d1) {
+        if (!edge) {
+          long long w = grid_word(g, b, zz, yy, x);
+          unsigned long long m = __ldg(g.mask + w);
+          unsigned sh = (x & 63) - 1;
+          unsigned bits = (unsigned)(m >> sh) & 7u;
+          if (bits) {
+            int base = __ldg(g.prefix + w) + __popcll(m & ((1ull << sh) - 1));
+            int rk0 = base, rk1 = base + (bits & 1), rk2 = rk1 + ((bits >> 1) & 1);
+            if (g.row_of_rank) {
+              if (bits & 1) r0 = __ldg(g.row_of_rank + rk0);
+              if (bits & 2) r1 = __ldg(g.row_of_rank + rk1);
+              if (bits & 4) r2 = __ldg(g.row_of_rank + rk2);
+            } else {
+              if (bits & 1) r0 = rk0;
+              if (bits & 2) r1 = rk1;
+              if (bits & 4) r2 = rk2;
+            }
+          }
+        } else {
+          if (x - 1 >= 0) r0 = grid_row(g, b, zz, yy, x - 1);
+          r1 = grid_row(g, b, zz, yy, x);
+          if (x + 1 < g.d2) r2 = grid_row(g, b, zz, yy, x + 1);
+        }
+      }
+      idx[k0] = r0; idx[k0 + 1] = r1; idx[k0 + 2] = r2;
+    }
+  }
+}
+
 // literal fp32 restatement of `nn.Sigmoid()(x) > 0.5` (model.py:233,322)
 __device__ __forceinline__ bool sigmoid_gt_half(float x) {
   float s = 1.0f / (1.0f + expf(-x));

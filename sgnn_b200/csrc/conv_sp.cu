@@ -254,7 +254,6 @@ int sgnn_conv_forward_rowlane(const SgnnConvArgs* a, cudaStream_t st) {
   p.slots = a->nbr; p.cnt = nullptr;
 #define SP_CASE(CO, CI, KK) if (a->cout == CO && a->cin == CI && a->K == KK) return launch_sp<CO, CI, KK>(p, vec, st);
   SP_CASE(8, 1, 27) SP_CASE(8, 8, 27) SP_CASE(12, 8, 27) SP_CASE(12, 12, 27) SP_CASE(16, 12, 27) SP_CASE(16, 16, 27)
-  SP_CASE(16, 26, 27) SP_CASE(16, 30, 27) SP_CASE(16, 34, 27)
 #undef SP_CASE
   return SGNN_E_UNSUPPORTED;
 }

@@ -35,9 +35,15 @@ unsigned long long* g_ur_diag_host = nullptr;   // mapped pinned host memory, 12
 namespace {
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 8)
+// PROBE = false: the neighbour table exists, read it.  PROBE = true (sgnn_rulebook_submanifold_plan): rulebook and plan in ONE
+// kernel -- thread = row probes its 27 neighbours in the site grid (rulebook_probe27), stores them k-major into `nbr_out`
+// (the table the direct mode, the child-mode kernel and the FFMA fallbacks read) and goes straight on to the plan: the table
+// is written once and not read back (27 x 4 B per row less traffic and one launch less per site set).
+template <bool PROBE>
+__global__ void __launch_bounds__(128, PROBE ? 6 : 8)
 tile_plan_kernel(const int* __restrict__ nbr, long long nbr_stride, long long n_rows, long long n_tiles,
-                 int* __restrict__ ucount, int* __restrict__ urows, unsigned short* __restrict__ lidx) {
+                 int* __restrict__ ucount, int* __restrict__ urows, unsigned short* __restrict__ lidx,
+                 GridView g, const int* __restrict__ coords, int* __restrict__ nbr_out) {
   __shared__ unsigned bm[UR_BM_WORDS];
   __shared__ unsigned short pre[UR_BM_WORDS];    // ranks <= 27 * 128
   __shared__ int red_min[4], red_max[4], warp_sum[4];
@@ -47,11 +53,22 @@ tile_plan_kernel(const int* __restrict__ nbr, long long nbr_stride, long long n_
     const long long j = tile * 128 + tid;
     int idx[27];
     int mn = 0x7fffffff, mx = -1;
+    if (PROBE) {
+      if (j < n_rows) {
+        rulebook_probe27(g, __ldg(reinterpret_cast<const int4*>(coords) + j), idx);
 #pragma unroll
-    for (int k = 0; k < 27; ++k) {
-      idx[k] = j < n_rows ? __ldg(nbr + (long long)k * nbr_stride + j) : -1;
-      if (idx[k] >= 0) { mn = min(mn, idx[k]); mx = max(mx, idx[k]); }
+        for (int k = 0; k < 27; ++k) nbr_out[(long long)k * nbr_stride + j] = idx[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 27; ++k) idx[k] = -1;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 27; ++k) idx[k] = j < n_rows ? __ldg(nbr + (long long)k * nbr_stride + j) : -1;
     }
+#pragma unroll
+    for (int k = 0; k < 27; ++k)
+      if (idx[k] >= 0) { mn = min(mn, idx[k]); mx = max(mx, idx[k]); }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
       mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
@@ -539,8 +556,24 @@ extern "C" int sgnn_tile_plan_build(const int32_t* nbr, int64_t nbr_stride, int6
   const long long tiles = (n_rows + 127) / 128;
   PlanView v = plan_view(plan, tiles);
   long long grid = tiles < 148 * 9 ? tiles : 148 * 9;
-  tile_plan_kernel<<<(int)grid, 128, 0, (cudaStream_t)stream>>>(nbr, nbr_stride, n_rows, tiles, (int*)v.ucount, (int*)v.urows,
-                                                                 (unsigned short*)v.lidx);
+  tile_plan_kernel<false><<<(int)grid, 128, 0, (cudaStream_t)stream>>>(nbr, nbr_stride, n_rows, tiles, (int*)v.ucount, (int*)v.urows,
+                                                                        (unsigned short*)v.lidx, GridView(), nullptr, nullptr);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+extern "C" int sgnn_rulebook_submanifold_plan(const SgnnGrid* g, const int32_t* coords, int64_t n, int32_t* nbr, void* plan,
+                                              size_t plan_bytes, void* stream) {
+  if (!g || !g->mask || !g->prefix || n < 0 || (n > 0 && (!coords || !nbr || !plan))) return SGNN_E_INVALID;
+  if (n == 0) return SGNN_OK;
+  if (n * 27 > 0x7fffffff00LL) return SGNN_E_TOO_LARGE;
+  if (plan_bytes < sgnn_tile_plan_bytes(n)) return SGNN_E_NOMEM;
+  if (!al(plan, 256)) return SGNN_E_ALIGN;
+  const long long tiles = (n + 127) / 128;
+  PlanView v = plan_view(plan, tiles);
+  long long grid = tiles < 148 * 6 ? tiles : 148 * 6;
+  tile_plan_kernel<true><<<(int)grid, 128, 0, (cudaStream_t)stream>>>(nullptr, n, n, tiles, (int*)v.ucount, (int*)v.urows,
+                                                                       (unsigned short*)v.lidx, make_view(g), coords, nbr);
   SGNN_CHECK_LAUNCH();
   return SGNN_OK;
 }

@@ -115,30 +115,39 @@ __global__ void heads_flag_kernel(const float* __restrict__ x, int ld_x, int c, 
 
 // 8 lanes per candidate row: the kept row (c features + occ + sdf + zeroed spare columns) is written as 16-byte /
 // 4-byte pieces by neighbouring lanes instead of one thread striding through a 112-byte row.
+// JOIN: the skip join of the next level (concat_skip, model.py:338-355: the features of the encoder site at the kept
+// child's coordinates, zeros where there is none) is written with the row -- columns [c+2, c+2+c_skip) -- instead of by a
+// second kernel that re-reads every coordinate and re-walks every row (sgnn_concat_skip).
+struct SkipJoin { GridView g; const float* f; int ld, c; };
+template <bool JOIN>
 __global__ void heads_write_kernel(const float* __restrict__ x, int ld_x, int c, const float* __restrict__ cand_out,
                                    const int* __restrict__ parent_coords, long long n_cand,
                                    const unsigned char* __restrict__ flags, const int* __restrict__ offs,
                                    int* __restrict__ locs, float* __restrict__ feats, int ld,
-                                   int* __restrict__ count) {
+                                   int* __restrict__ count, SkipJoin sk) {
   if (count && blockIdx.x == 0 && threadIdx.x == 0) *count = offs[n_cand];
   const int sub = threadIdx.x & 7;
   for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3; i < n_cand;
        i += ((long long)gridDim.x * blockDim.x) >> 3) {
     if (!flags[i]) continue;
     const int pos = offs[i];
-    if (sub == 0) {
-      const int4 p = __ldg(reinterpret_cast<const int4*>(parent_coords) + (i >> 3));
-      const int ch8 = (int)(i & 7);
-      reinterpret_cast<int4*>(locs)[pos] =
-          make_int4(2 * p.x + ((ch8 >> 2) & 1), 2 * p.y + ((ch8 >> 1) & 1), 2 * p.z + (ch8 & 1), p.w);
+    const int4 p = __ldg(reinterpret_cast<const int4*>(parent_coords) + (i >> 3));
+    const int ch8 = (int)(i & 7);
+    const int4 q = make_int4(2 * p.x + ((ch8 >> 2) & 1), 2 * p.y + ((ch8 >> 1) & 1), 2 * p.z + (ch8 & 1), p.w);
+    if (sub == 0) reinterpret_cast<int4*>(locs)[pos] = q;
+    const float* srow = nullptr;
+    if (JOIN) {
+      const int r = grid_row_checked(sk.g, q.w, q.x, q.y, q.z);      // 8 lanes, one address: a broadcast
+      if (r >= 0) srow = sk.f + (long long)r * sk.ld;
     }
     float* f = feats + (long long)pos * ld;
     const float* xr = x + i * ld_x;
     for (int ch = sub; ch < ld; ch += 8) {
-      float v = 0.f;                                         // spare columns for the skip join
+      float v = 0.f;                                         // spare columns (skip join of the next level / padding)
       if (ch < c) v = xr[ch];
       else if (ch == c) v = cand_out[2 * i];
       else if (ch == c + 1) v = cand_out[2 * i + 1];
+      else if (JOIN && srow && ch < c + 2 + sk.c) v = __ldg(srow + (ch - c - 2));
       f[ch] = v;
     }
   }
@@ -167,8 +176,8 @@ extern "C" int sgnn_heads_compact(const float* x, int32_t ld_x, int32_t c, const
   SGNN_CHECK_LAUNCH();
   rc = sgnn_scan_exclusive(cs.flags, SCAN_U8, cs.offs, n_cand, cs.scan, cs.scan_bytes, st);
   if (rc) return rc;
-  heads_write_kernel<<<sgnn_blocks(n_cand * 8, 256), 256, 0, st>>>(x, ld_x, c, cand_out, parent_coords, n_cand,
-                                                               cs.flags, cs.offs, locs, feats, ld_feats, count);
+  heads_write_kernel<false><<<sgnn_blocks(n_cand * 8, 256), 256, 0, st>>>(x, ld_x, c, cand_out, parent_coords, n_cand,
+                                                                      cs.flags, cs.offs, locs, feats, ld_feats, count, SkipJoin());
   SGNN_CHECK_LAUNCH();
   return SGNN_OK;
 }
@@ -198,8 +207,25 @@ extern "C" int sgnn_heads_write(const float* x, int32_t ld_x, int32_t c, const f
   if (n_cand < 0 || c <= 0 || ld_feats < c + 2) return SGNN_E_INVALID;
   if (n_cand == 0) return SGNN_OK;
   if (!x || !cand_out || !parent_coords || !flags || !offs || !locs || !feats) return SGNN_E_INVALID;
-  heads_write_kernel<<<sgnn_blocks(n_cand * 8, 256), 256, 0, (cudaStream_t)stream>>>(
-      x, ld_x, c, cand_out, parent_coords, n_cand, flags, offs, locs, feats, ld_feats, nullptr);
+  heads_write_kernel<false><<<sgnn_blocks(n_cand * 8, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, ld_x, c, cand_out, parent_coords, n_cand, flags, offs, locs, feats, ld_feats, nullptr, SkipJoin());
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}
+
+extern "C" int sgnn_heads_write_join(const float* x, int32_t ld_x, int32_t c, const float* cand_out,
+                                     const int32_t* parent_coords, int64_t n_cand, const uint8_t* flags,
+                                     const int32_t* offs, int32_t* locs, float* feats, int32_t ld_feats,
+                                     const SgnnGrid* skip_grid, const float* skip_feats, int32_t ld_skip, int32_t c_skip,
+                                     void* stream) {
+  if (n_cand < 0 || c <= 0 || c_skip <= 0 || ld_feats < c + 2 + c_skip) return SGNN_E_INVALID;
+  if (n_cand == 0) return SGNN_OK;
+  if (!x || !cand_out || !parent_coords || !flags || !offs || !locs || !feats) return SGNN_E_INVALID;
+  if (!skip_grid || !skip_grid->mask || !skip_grid->prefix || !skip_feats) return SGNN_E_INVALID;
+  SkipJoin sk;
+  sk.g = make_view(skip_grid); sk.f = skip_feats; sk.ld = ld_skip; sk.c = c_skip;
+  heads_write_kernel<true><<<sgnn_blocks(n_cand * 8, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, ld_x, c, cand_out, parent_coords, n_cand, flags, offs, locs, feats, ld_feats, nullptr, sk);
   SGNN_CHECK_LAUNCH();
   return SGNN_OK;
 }

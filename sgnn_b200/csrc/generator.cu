@@ -107,22 +107,27 @@ static void grid_shape(SgnnGrid* g, int nb, const int dims[3]) {
   g->n_words = (int64_t)nb * dims[0] * dims[1] * g->wx;
 }
 
-// unique-row tile plan of a level's neighbour table, when the level is large enough for the tensor-core path
-static int build_plan(Ctx& c, Level* L, int cout) {
+// does a site set of n rows feeding Cout = cout convolutions get a unique-row tile plan?  (The kernel also takes Cout 8 / 12,
+// but on the sparse encoder levels its per-tile overhead loses to the FFMA kernels: 87-95 us against 68-72 us for 420 k rows.)
+static bool wants_plan(const Ctx& c, int64_t n, int cout) { return c.tc32 && cout == 16 && n >= c.ur_min_rows; }
+
+// neighbour table of a site set and, when it qualifies, its tile plan -- in one kernel (sgnn_rulebook_submanifold_plan)
+static int rulebook_and_plan(Ctx& c, Level* L, int32_t* nbr, int plan_cout) {
+  L->nbr = nbr;
   L->plan = nullptr;
-  // (the kernel also takes Cout 8 / 12, but on the 5 %-occupancy encoder levels its per-tile overhead loses to the FFMA kernel:
-  // 87-95 us against 68-72 us for 420 k rows, measured)
-  if (!c.tc32 || cout != 16 || !L->nbr || L->n < c.ur_min_rows) return SGNN_OK;
-  const size_t pb = sgnn_tile_plan_bytes(L->n);
-  void* plan = c.ar.get(pb);
-  if (!plan) return SGNN_E_NOMEM;
-  L->plan = plan;
-  return sgnn_tile_plan_build(L->nbr, L->n, L->n, plan, pb, c.stream);
+  if (L->n > 0 && wants_plan(c, L->n, plan_cout)) {
+    const size_t pb = sgnn_tile_plan_bytes(L->n);
+    void* plan = c.ar.get(pb);
+    if (!plan) return SGNN_E_NOMEM;
+    L->plan = plan;
+    return sgnn_rulebook_submanifold_plan(&L->g, L->coords, L->n, nbr, plan, pb, c.stream);
+  }
+  return sgnn_rulebook_submanifold(&L->g, L->coords, L->n, nbr, c.stream);
 }
 
 // a1 + a2: site set from explicit coordinates, with its 27-neighbour table
 static int build_level(Ctx& c, const void* coords, int is64, int64_t n, int nb, const int dims[3], int32_t* status,
-                       Level* L, bool compact = false) {
+                       Level* L, bool compact = false, int plan_cout = 0) {
   grid_shape(&L->g, nb, dims);
   for (int i = 0; i < 3; ++i) L->dims[i] = dims[i];
   L->n = n;
@@ -143,8 +148,7 @@ static int build_level(Ctx& c, const void* coords, int is64, int64_t n, int nb, 
     L->nbr = nullptr; L->slots = nbr; L->cnt = cnt;
     return sgnn_rulebook_submanifold_compact(&L->g, ci32, n, nbr, cnt, c.stream);
   }
-  L->nbr = nbr;
-  return sgnn_rulebook_submanifold(&L->g, ci32, n, nbr, c.stream);
+  return rulebook_and_plan(c, L, nbr, plan_cout);
 }
 
 // a4: stride-2 coarse set of `f` (raster rows) + strided rulebook (+ its own 27-neighbour table), in two phases so
@@ -189,7 +193,8 @@ static int counts_wait(Ctx& c, Level** lv, int n) {
   return SGNN_OK;
 }
 
-static int coarsen_finish(Ctx& c, const Level& f, Level* L, int32_t** parent, int32_t** children, bool want_nbr) {
+static int coarsen_finish(Ctx& c, const Level& f, Level* L, int32_t** parent, int32_t** children, bool want_nbr,
+                          int plan_cout = 0) {
   const int64_t cnt = L->n;
   ALLOC(cc, int32_t, cnt * 4);
   L->coords = cc;
@@ -201,8 +206,7 @@ static int coarsen_finish(Ctx& c, const Level& f, Level* L, int32_t** parent, in
   L->nbr = nullptr;
   if (want_nbr) {
     ALLOC(nbr, int32_t, cnt * 27);
-    L->nbr = nbr;
-    RC(sgnn_rulebook_submanifold(&L->g, cc, cnt, nbr, c.stream));
+    RC(rulebook_and_plan(c, L, nbr, plan_cout));
   }
   return SGNN_OK;
 }
@@ -333,10 +337,8 @@ static int fcn(Ctx& c, const Level& lv0, const SgnnFcnW& f, const float* x_raw, 
   ALLOC(y0_bn, float, lv0.n * ch);
   RC(res_block(c, lv0, f.blk[0], ch, x_raw, x_bn, epi_bn(J0, 3 * ch, f.bn_join), epi_bn(y0_bn, ch, f.bn_down[0])));
   RC(counts_wait(c, pend, 2));
-  RC(coarsen_finish(c, lv0, &lv1, &par01, &chi01, true));
-  RC(coarsen_finish(c, lv1, &lv2, &par12, &chi12, true));
-  RC(build_plan(c, &lv1, ch));
-  RC(build_plan(c, &lv2, ch));
+  RC(coarsen_finish(c, lv0, &lv1, &par01, &chi01, true, ch));
+  RC(coarsen_finish(c, lv1, &lv2, &par12, &chi12, true, ch));
   rows[1] = lv1.n;
   rows[2] = lv2.n;
   ALLOC(J1, float, lv1.n * 2 * ch);
@@ -459,11 +461,9 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
         // coordinates were masked out of the site set by sgnn_grid_build, so that work was safe; it is discarded here)
         GEN(counts_wait(c, enc_pend, 3));
         if (pinb[8]) { rc = SGNN_E_INVALID; break; }   // a coordinate outside [0, dims) x [0, nb): scn raises here too
-        GEN(coarsen_finish(c, enc_lv[0], &enc_lv[1], &enc_par[0], &enc_chi[0], true));
-        GEN(coarsen_finish(c, enc_lv[1], &enc_lv[2], &enc_par[1], &enc_chi[1], true));
+        GEN(coarsen_finish(c, enc_lv[0], &enc_lv[1], &enc_par[0], &enc_chi[0], true, w->enc[1].c));
+        GEN(coarsen_finish(c, enc_lv[1], &enc_lv[2], &enc_par[1], &enc_chi[1], true, w->enc[2].c));
         GEN(coarsen_finish(c, enc_lv[2], &enc_lv[3], &enc_par[2], &enc_chi[2], false));
-        GEN(build_plan(c, &enc_lv[1], w->enc[1].c));
-        GEN(build_plan(c, &enc_lv[2], w->enc[2].c));
       }
       Level cl = enc_lv[l + 1];
       int32_t* chi = enc_chi[l];
@@ -549,19 +549,19 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
     // ------------------------------------------------------------ refinement levels (model.py:387-396)
     int rdims[3] = {dd[0], dd[1], dd[2]};
     bool ref_ok = true;
+    bool joined = false;     // the skip columns of `fts` were written with the rows (sgnn_heads_write_join)
     for (int h = 0; h < 3 && ref_ok; ++h) {
       const SgnnRefineW& R = w->ref[h];
       ref_ok = false;
       if (m == 0) { ref_ok = true; continue; }
       const Skip& sk = skips[3 - h];
-      if (sk.n) { GEN(sgnn_concat_skip(&sk.g, sk.f, sk.c, sk.c, locs, m, fts, ld_f, live_c, stream)); }
+      if (sk.n && !joined) { GEN(sgnn_concat_skip(&sk.g, sk.f, sk.c, sk.c, locs, m, fts, ld_f, live_c, stream)); }
       // (rows of an empty skip set keep the zeros written with the row)
       live_c += sk.c;
       if (live_c != R.cin) { rc = SGNN_E_INVALID; break; }
       Level rl;
-      GEN(build_level(c, locs, 0, m, nb, rdims, nullptr, &rl));
       const int ch = R.c;
-      GEN(build_plan(c, &rl, ch));
+      GEN(build_level(c, locs, 0, m, nb, rdims, nullptr, &rl, false, ch));
       GALLOC(a_raw, float, m * ch);
       GALLOC(a_bn, float, m * ch);
       GEN(conv(c, fts, ld_f, R.cin, rl.nbr, m, 27, 0, R.w_in, ch, m, nullptr, 0, epi(a_raw, ch),
@@ -592,7 +592,13 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       const int ld_n = pad8(ch + 2 + next_skip);
       GALLOC(nl, int32_t, (int64_t)cnt * 4);
       GALLOC(nf, float, (int64_t)cnt * ld_n);
-      GEN(sgnn_heads_write(xc, ch, ch, cand, locs, ncand, flg, offs, nl, nf, ld_n, stream));
+      const Skip& nsk = h < 2 ? skips[2 - h] : skips[0];
+      joined = nsk.n > 0;
+      if (joined) {
+        GEN(sgnn_heads_write_join(xc, ch, ch, cand, locs, ncand, flg, offs, nl, nf, ld_n, &nsk.g, nsk.f, nsk.c, nsk.c, stream));
+      } else {
+        GEN(sgnn_heads_write(xc, ch, ch, cand, locs, ncand, flg, offs, nl, nf, ld_n, stream));
+      }
       locs = nl; fts = nf; ld_f = ld_n; live_c = ch + 2; m = cnt;
       for (int i = 0; i < 3; ++i) rdims[i] *= 2;
       ref_ok = true;
@@ -604,13 +610,12 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
     if (m > 0) {
       const SgnnSurfaceW& S = w->surf;
       const Skip& sk = skips[0];
-      if (sk.n) { GEN(sgnn_concat_skip(&sk.g, sk.f, sk.c, sk.c, locs, m, fts, ld_f, live_c, stream)); }
+      if (sk.n && !joined) { GEN(sgnn_concat_skip(&sk.g, sk.f, sk.c, sk.c, locs, m, fts, ld_f, live_c, stream)); }
       live_c += sk.c;
       if (live_c != S.cin) { rc = SGNN_E_INVALID; break; }
       Level sl;
-      GEN(build_level(c, locs, 0, m, nb, rdims, nullptr, &sl));
       const int ch = S.c;
-      GEN(build_plan(c, &sl, ch));
+      GEN(build_level(c, locs, 0, m, nb, rdims, nullptr, &sl, false, ch));
       GALLOC(a_raw, float, m * ch);
       GALLOC(a_bn, float, m * ch);
       GEN(conv(c, fts, ld_f, S.cin, sl.nbr, m, 27, 0, S.w_in, ch, m, nullptr, 0, epi(a_raw, ch),

@@ -213,53 +213,16 @@ rulebook_submanifold_kernel(GridView g, const int* __restrict__ coords, long lon
                             int* __restrict__ nbr, unsigned char* __restrict__ cnt) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
-    int4 c = __ldg(reinterpret_cast<const int4*>(coords) + i);
-    const int z = c.x, y = c.y, x = c.z, b = c.w;
-    const bool inb = (unsigned)z < (unsigned)g.d0 && (unsigned)y < (unsigned)g.d1 &&
-                     (unsigned)x < (unsigned)g.d2 && (unsigned)b < (unsigned)g.nb;
-    const bool edge = ((x & 63) == 0) || ((x & 63) == 63);
+    const int4 c = __ldg(reinterpret_cast<const int4*>(coords) + i);
+    int idx[27];
+    rulebook_probe27(g, c, idx);
     int filled = 0;
 #pragma unroll
-    for (int dz = -1; dz <= 1; ++dz) {
-#pragma unroll
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int zz = z + dz, yy = y + dy;
-        const int k0 = (dz + 1) * 9 + (dy + 1) * 3;
-        int r0 = -1, r1 = -1, r2 = -1;
-        if (inb && (unsigned)zz < (unsigned)g.d0 && (unsigned)yy < (unsigned)g.d1) {
-          if (!edge) {
-            long long w = grid_word(g, b, zz, yy, x);
-            unsigned long long m = __ldg(g.mask + w);
-            unsigned sh = (x & 63) - 1;
-            unsigned bits = (unsigned)(m >> sh) & 7u;
-            if (bits) {
-              int base = __ldg(g.prefix + w) + __popcll(m & ((1ull << sh) - 1));
-              int rk0 = base, rk1 = base + (bits & 1), rk2 = rk1 + ((bits >> 1) & 1);
-              if (g.row_of_rank) {
-                if (bits & 1) r0 = __ldg(g.row_of_rank + rk0);
-                if (bits & 2) r1 = __ldg(g.row_of_rank + rk1);
-                if (bits & 4) r2 = __ldg(g.row_of_rank + rk2);
-              } else {
-                if (bits & 1) r0 = rk0;
-                if (bits & 2) r1 = rk1;
-                if (bits & 4) r2 = rk2;
-              }
-            }
-          } else {
-            if (x - 1 >= 0) r0 = grid_row(g, b, zz, yy, x - 1);
-            r1 = grid_row(g, b, zz, yy, x);
-            if (x + 1 < g.d2) r2 = grid_row(g, b, zz, yy, x + 1);
-          }
-        }
-        if (COMPACT) {
-          if (r0 >= 0) { nbr[(long long)filled * n + i] = (int)(((unsigned)(k0 + 0) << 27) | (unsigned)r0); ++filled; }
-          if (r1 >= 0) { nbr[(long long)filled * n + i] = (int)(((unsigned)(k0 + 1) << 27) | (unsigned)r1); ++filled; }
-          if (r2 >= 0) { nbr[(long long)filled * n + i] = (int)(((unsigned)(k0 + 2) << 27) | (unsigned)r2); ++filled; }
-        } else {
-          nbr[(long long)(k0 + 0) * n + i] = r0;
-          nbr[(long long)(k0 + 1) * n + i] = r1;
-          nbr[(long long)(k0 + 2) * n + i] = r2;
-        }
+    for (int k = 0; k < 27; ++k) {
+      if (COMPACT) {
+        if (idx[k] >= 0) { nbr[(long long)filled * n + i] = (int)(((unsigned)k << 27) | (unsigned)idx[k]); ++filled; }
+      } else {
+        nbr[(long long)k * n + i] = idx[k];
       }
     }
     if (COMPACT) cnt[i] = (unsigned char)filled;

@@ -241,6 +241,18 @@ def tile_plan(nbr, n_rows):
     return plan
 
 
+def rulebook_submanifold_plan(grid):
+    """a2 + tile plan in one kernel (sgnn_rulebook_submanifold_plan): (nbr int32 [27, n], plan) -- the same table and the same
+    plan as rulebook_submanifold followed by tile_plan."""
+    nbr = torch.empty((27, grid.n), dtype=torch.int32, device=grid.device)
+    nb = lib.sgnn_tile_plan_bytes(int(grid.n))
+    plan = torch.empty(nb, dtype=torch.uint8, device=grid.device)
+    assert plan.data_ptr() % 256 == 0
+    check(lib.sgnn_rulebook_submanifold_plan(grid.ref(), _ptr(grid.coords), grid.n, _ptr(nbr), _ptr(plan), nb, _stream()),
+          'sgnn_rulebook_submanifold_plan')
+    return nbr, plan
+
+
 def deconv(x, parent, weight, out, scale=None, shift=None, relu=False):
     _need_cuda(x, parent, weight, out)
     K, cin, cout = weight.shape

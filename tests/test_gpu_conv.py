@@ -352,7 +352,7 @@ def test_generator_same_bits_with_compact_and_dense_rules():
 
 
 @pytest.mark.parametrize('cin,cout,K', [(1, 8, 27), (8, 8, 27), (8, 12, 27), (12, 12, 27),
-                                        (12, 16, 27), (16, 16, 27), (26, 16, 27), (30, 16, 27), (34, 16, 27)])
+                                        (12, 16, 27), (16, 16, 27)])
 def test_rowlane_kernel_same_bits_as_row_owner_kernel(cin, cout, K):
     """sgnn_conv_forward's two kernels for dense tables (conv.cu row-owner, conv_sp.cu lane = (row, channel group)) forced
     one after the other on a launch larger than the automatic threshold: identical bits, equal to oracle O3."""

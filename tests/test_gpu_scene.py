@@ -90,5 +90,7 @@ def test_run_scene_writes_the_reference_meshes(tmp_path):
         V, F = mcubes.marching_cubes(dense, 0.0, 2.9, 10.0)
         want = str(tmp_path / ('want-' + fname))
         mesh.save_to_ply(want, V, np.full((V.shape[0], 3), 220, dtype=np.uint8), F)
-        assert V.shape[0] > 1000 and open(os.path.join(out_dir, fname), 'rb').read() == open(want, 'rb').read()
+        # (the prediction of a randomly initialised generator is not a distance field: its mesh may be small or empty)
+        assert V.shape[0] > 1000 or fname.startswith('roompred')
+        assert open(os.path.join(out_dir, fname), 'rb').read() == open(want, 'rb').read()
     assert set(timings) == {'forward_ms', 'pad_removal_ms', 'meshes_ms'}

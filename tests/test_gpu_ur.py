@@ -351,3 +351,29 @@ def test_urc_multi_pass_and_direct():
     plan, n = _child_case(E, rng, c)
     ucount, _, _ = _parse_plan(plan, n)
     assert (ucount > 256).any() and (ucount == -1).any() and ((ucount >= 0) & (ucount <= 256)).any()
+
+
+def test_fused_rulebook_and_plan_equals_the_two_calls():
+    """sgnn_rulebook_submanifold_plan: the same neighbour table, and a plan that drives the unique-row convolution to the same
+    bits as the plan built from the table by sgnn_tile_plan_build (caller-ordered rows, ragged last tile, x on word edges)."""
+    import sgnn_b200.engine as E
+    from helpers import random_coords
+    rng = np.random.default_rng(9)
+    for nb, dims, occ in [(2, (20, 24, 130), 0.3), (1, (33, 17, 64), 0.7)]:
+        c = random_coords(rng, nb, dims, occ)
+        c = c[rng.permutation(c.shape[0])]
+        g = E.build_grid(torch.from_numpy(c).cuda(), nb, dims)
+        n = g.n
+        nbr = E.rulebook_submanifold(g)
+        nbr2, plan2 = E.rulebook_submanifold_plan(g)
+        assert torch.equal(nbr, nbr2)
+        plan = E.tile_plan(nbr, n).clone()
+        x = torch.randn((n, 16), device='cuda')
+        w = torch.randn((27, 16, 16), device='cuda') * 0.1
+        a = torch.empty((n, 16), device='cuda')
+        b = torch.empty((n, 16), device='cuda')
+        E.conv(x, nbr, w, n, a, plan=plan)
+        E.conv(x, nbr2, w, n, b, plan=plan2)
+        assert torch.equal(a, b)
+        tiles = (n + 127) // 128
+        assert torch.equal(plan[:tiles * 4], plan2[:tiles * 4])                 # distinct-row counts per tile
