@@ -108,67 +108,6 @@ dense_conv3d_fast_kernel(DenseArgs a) {
   }
 }
 
-// The two strided encoder layers of the coarse U-Net (nn.Conv3d k4 s2 p1: 16 -> 24 on 8^3, 24 -> 32 on 4^3 per block).  The
-// per-thread kernel above issues two scalar global loads per fmaf (62 us per layer for 50 M fmaf: load-issue bound).  Here a
-// CTA owns one block (sample) and COG output channels: the block's whole input (<= 32 KB) is staged in shared memory once,
-// the filters of the CTA's channels stream through shared memory in chunks of CC input channels ([cc][tap][co], read as
-// warp-uniform broadcasts), and a thread owns ONE output element -- one LDS + one broadcast LDS per fmaf, no global loads in
-// the loop.  Per output element the order is unchanged: ci ascending, then the in-range taps in kz,ky,kx order, one fmaf
-// chain from +0.
-__global__ void __launch_bounds__(512)
-dense_conv3d_k4s2p1_tile_kernel(DenseArgs a, int cog, int cc) {
-  extern __shared__ __align__(16) float dcs[];
-  const int ivol = a.d0 * a.d1 * a.d2, ovol = a.o0 * a.o1 * a.o2, cin = a.c0 + a.c1;
-  float* xin = dcs;                         // [cin][ivol]
-  float* wsm = dcs + cin * ivol;            // [cc][64][cog]
-  const int b = blockIdx.x, co0 = blockIdx.y * cog, tid = threadIdx.x, nthr = blockDim.x;
-  for (int i = tid; i < cin * ivol; i += nthr) {
-    const int ci = i / ivol;
-    xin[i] = __ldg(dense_chan(a, b, ci, ivol) + (i - ci * ivol));
-  }
-  const int col = tid / ovol, pos = tid - col * ovol;       // blockDim = cog * ovol
-  const int x = pos % a.o2, y = (pos / a.o2) % a.o1, z = pos / (a.o1 * a.o2);
-  const int z0 = 2 * z - 1, y0 = 2 * y - 1, x0 = 2 * x - 1;
-  int rowoff[16];
-  unsigned okrow = 0, okx = 0;
-#pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    const int iz = z0 + (r >> 2), iy = y0 + (r & 3);
-    if ((unsigned)iz < (unsigned)a.d0 && (unsigned)iy < (unsigned)a.d1) okrow |= 1u << r;
-    rowoff[r] = (iz * a.d1 + iy) * a.d2 + x0;
-  }
-#pragma unroll
-  for (int kx = 0; kx < 4; ++kx)
-    if ((unsigned)(x0 + kx) < (unsigned)a.d2) okx |= 1u << kx;
-  float acc = 0.f;
-  for (int c0 = 0; c0 < cin; c0 += cc) {
-    const int nc = min(cc, cin - c0);
-    __syncthreads();                         // previous chunk consumed (and, the first time, the input staged)
-    for (int i = tid; i < nc * 64 * cog; i += nthr) {
-      const int t = i & 63, cl = (i >> 6) % nc, j = (i >> 6) / nc;
-      wsm[(cl * 64 + t) * cog + j] = __ldg(a.w + ((long long)(co0 + j) * cin + c0 + cl) * 64 + t);
-    }
-    __syncthreads();
-    for (int cl = 0; cl < nc; ++cl) {
-      const float* xs = xin + (c0 + cl) * ivol;
-      const float* ws = wsm + cl * 64 * cog + col;
-#pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        if (!((okrow >> r) & 1u)) continue;
-        const float* row = xs + rowoff[r];
-#pragma unroll
-        for (int kx = 0; kx < 4; ++kx)
-          if ((okx >> kx) & 1u) acc = fmaf(row[kx], ws[(r * 4 + kx) * cog], acc);
-      }
-    }
-  }
-  const int co = co0 + col;
-  float v = acc;
-  if (a.scale) v = fmaf(v, __ldg(a.scale + co), __ldg(a.shift + co));
-  if (a.relu) v = fmaxf(v, 0.f);
-  a.out[((long long)b * a.cout + co) * ovol + pos] = v;
-}
-
 // Transposed convolution: per axis only the taps k == (o + pad) (mod stride) reach an input cell; they are
 // enumerated once per output element (at most 4 per axis), so the channel loop runs over live taps only.
 // Order of the live taps is kz, ky, kx ascending -- the order of the full loop with the dead taps removed.
@@ -347,17 +286,7 @@ static int dense_launch(bool transposed, const float* in0, int c0, const float* 
   const long long total = (long long)nb * cout * a.o0 * a.o1 * a.o2;
   if (total == 0) return SGNN_OK;
   const int blocks = sgnn_blocks(total, 128, (int64_t)148 * 32);
-  const int ovol_i = a.o0 * a.o1 * a.o2, ivol_i = d0 * d1 * d2;
-  int cog = 0;
-  if (!transposed && ks == 4 && stride == 2 && pad == 1 && ovol_i <= 256 && nb <= 65535)
-    for (int g = 256 / ovol_i > cout ? cout : 256 / ovol_i; g >= 1; --g)
-      if (cout % g == 0) { cog = g; break; }
-  const int dcc = cog ? (64 / cog > 0 ? 64 / cog : 1) : 0;              // 16 KB of filters per chunk
-  const size_t dsm = cog ? ((size_t)(c0 + c1) * ivol_i + (size_t)dcc * 64 * cog) * 4 : 0;
-  if (cog && dsm <= 48 * 1024) {
-    dim3 grid((unsigned)nb, (unsigned)(cout / cog));
-    dense_conv3d_k4s2p1_tile_kernel<<<grid, cog * ovol_i, dsm, (cudaStream_t)stream>>>(a, cog, dcc);
-  } else if (!transposed && (ks == 4 || ks == 1)) {
+  if (!transposed && (ks == 4 || ks == 1)) {
     const int fb = sgnn_blocks(total, 64, (int64_t)148 * 64);
     if (ks == 4) dense_conv3d_fast_kernel<4><<<fb, 64, 0, (cudaStream_t)stream>>>(a);
     else dense_conv3d_fast_kernel<1><<<fb, 64, 0, (cudaStream_t)stream>>>(a);

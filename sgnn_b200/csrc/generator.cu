@@ -136,11 +136,9 @@ static int build_level(Ctx& c, const void* coords, int is64, int64_t n, int nb, 
   ALLOC(ror, int32_t, n);
   ALLOC(ci32, int32_t, n * 4);
   L->g.mask = mask; L->g.prefix = prefix; L->g.row_of_rank = ror; L->coords = ci32;
-  const size_t mark = c.ar.off;
   const size_t sb = sgnn_scan_scratch_bytes(L->g.n_words);
   ALLOC(scr, char, sb);
   RC(sgnn_grid_build(&L->g, coords, is64, n, ci32, status, scr, sb, c.stream));
-  c.ar.off = mark;
   ALLOC(nbr, int32_t, 27 * n);
   L->plan = nullptr; L->slots = nullptr; L->cnt = nullptr;
   if (compact && n < (1LL << 27)) {
@@ -164,11 +162,9 @@ static int coarsen_begin(Ctx& c, const Level& f, Level* L) {
   ALLOC(prefix, int32_t, L->g.n_words + 1);
   L->g.mask = mask; L->g.prefix = prefix; L->g.row_of_rank = nullptr;
   L->n = -1; L->coords = nullptr; L->nbr = nullptr; L->plan = nullptr; L->slots = nullptr; L->cnt = nullptr;
-  const size_t mark = c.ar.off;
   const size_t sb = sgnn_scan_scratch_bytes(L->g.n_words);
   ALLOC(scr, char, sb);
   RC(sgnn_grid_coarsen(&f.g, &L->g, scr, sb, c.stream));
-  c.ar.off = mark;
   return SGNN_OK;
 }
 
@@ -319,21 +315,33 @@ static int res_block(Ctx& c, const Level& lv, const SgnnResBlockW& rb, int ch, c
 }
 
 // FullyConvolutionalNet(reps 1, [c,c,c], residual) + BatchNormReLU(3c): J0 [n, 3c]   (model.py:180-181,255-256)
-static int fcn(Ctx& c, const Level& lv0, const SgnnFcnW& f, const float* x_raw, const float* x_bn, float** out,
+// The two coarse site sets of a level's FullyConvolutionalNet, first half: masks + rank scans + the count copies, enqueued as
+// soon as the level's own grid exists -- BEFORE its first convolution, so that the counts have long arrived when the host asks
+// for them (counts_wait, after it has enqueued that convolution and the first residual block) and the host never stalls there.
+// (Measured and removed: building these sets on a second stream under the convolutions.  Same bits, but the small grid
+// kernels then share SMs with the persistent one-CTA-per-SM tensor-core convolutions and delay their CTAs: 4.44 ms per step
+// single-stream against 4.64 / 4.71 ms with the levels of >= 100 k / >= 300 k rows overlapped, profiles/r02_ab_runs.txt.)
+struct FcnSets { Level lv1, lv2; };
+static int fcn_begin(Ctx& c, const Level& lv0, FcnSets* s) {
+  if (lv0.n == 0) return SGNN_OK;
+  RC(coarsen_begin(c, lv0, &s->lv1));
+  RC(coarsen_begin(c, s->lv1, &s->lv2));
+  Level* pend[2] = {&s->lv1, &s->lv2};
+  return counts_post(c, pend, 2);
+}
+
+static int fcn(Ctx& c, const Level& lv0, FcnSets& sets, const SgnnFcnW& f, const float* x_raw, const float* x_bn, float** out,
                int64_t rows[3]) {
   const int ch = f.c;
   ALLOC(J0, float, lv0.n * 3 * ch);
   *out = J0;
   rows[0] = lv0.n; rows[1] = rows[2] = 0;
   if (lv0.n == 0) return SGNN_OK;
-  // both coarse site sets + rulebooks of the U first (one host read), then the convolutions back to back
-  Level lv1, lv2;
+  Level& lv1 = sets.lv1;
+  Level& lv2 = sets.lv2;
   int32_t *par01, *chi01, *par12 = nullptr, *chi12 = nullptr;
-  RC(coarsen_begin(c, lv0, &lv1));
-  RC(coarsen_begin(c, lv1, &lv2));
   Level* pend[2] = {&lv1, &lv2};
-  RC(counts_post(c, pend, 2));
-  // the finest residual block does not depend on the coarse counts: it runs while the host reads them
+  // the finest residual block does not depend on the coarse sets: it is enqueued before the host asks for their counts
   ALLOC(y0_bn, float, lv0.n * ch);
   RC(res_block(c, lv0, f.blk[0], ch, x_raw, x_bn, epi_bn(J0, 3 * ch, f.bn_join), epi_bn(y0_bn, ch, f.bn_down[0])));
   RC(counts_wait(c, pend, 2));
@@ -529,11 +537,9 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
     {
       GALLOC(dflags, uint8_t, ncell);
       GALLOC(offs, int32_t, ncell + 1);
-      const size_t mark = c.ar.off;
       const size_t sb = sgnn_scan_scratch_bytes(ncell);
       GALLOC(scr, char, sb);
       GEN(sgnn_dense_flags(occsdf, nb, dvol, cand0, dflags, offs, scr, sb, stream));
-      c.ar.off = mark;
       int32_t cnt = 0;
       GEN(read_i32(c, offs + ncell, &cnt));
       m = cnt;
@@ -562,12 +568,14 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       Level rl;
       const int ch = R.c;
       GEN(build_level(c, locs, 0, m, nb, rdims, nullptr, &rl, false, ch));
+      FcnSets rsets;
+      GEN(fcn_begin(c, rl, &rsets));
       GALLOC(a_raw, float, m * ch);
       GALLOC(a_bn, float, m * ch);
       GEN(conv(c, fts, ld_f, R.cin, rl.nbr, m, 27, 0, R.w_in, ch, m, nullptr, 0, epi(a_raw, ch),
                epi_bn(a_bn, ch, R.fcn.blk[0].bn0), 0, rl.plan));
       float* J0 = nullptr;
-      GEN(fcn(c, rl, R.fcn, a_raw, a_bn, &J0, &out->rows[4 + 3 * h]));
+      GEN(fcn(c, rl, rsets, R.fcn, a_raw, a_bn, &J0, &out->rows[4 + 3 * h]));
       // a9: 8 children per site, never materialised: n1 in child mode + n2, heads, mask, compaction
       const int64_t ncand = 8 * m;
       GALLOC(xc, float, ncand * ch);
@@ -575,11 +583,9 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       GALLOC(cand, float, ncand * 2);
       GALLOC(flg, uint8_t, ncand);
       GALLOC(offs, int32_t, ncand + 1);
-      const size_t mark = c.ar.off;
       const size_t sb = sgnn_scan_scratch_bytes(ncand);
       GALLOC(scr, char, sb);
       GEN(sgnn_heads_flags(xc, ch, ch, R.w_occ, R.b_occ, R.w_sdf, R.b_sdf, ncand, cand, flg, offs, scr, sb, stream));
-      c.ar.off = mark;
       int32_t cnt = 0;
       GEN(read_i32(c, offs + ncand, &cnt));
       out->n_cand[h + 1] = ncand; out->cand[h + 1] = cand;
@@ -616,12 +622,14 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       Level sl;
       const int ch = S.c;
       GEN(build_level(c, locs, 0, m, nb, rdims, nullptr, &sl, false, ch));
+      FcnSets ssets;
+      GEN(fcn_begin(c, sl, &ssets));
       GALLOC(a_raw, float, m * ch);
       GALLOC(a_bn, float, m * ch);
       GEN(conv(c, fts, ld_f, S.cin, sl.nbr, m, 27, 0, S.w_in, ch, m, nullptr, 0, epi(a_raw, ch),
                epi_bn(a_bn, ch, S.fcn.blk[0].bn0), 0, sl.plan));
       float* J0 = nullptr;
-      GEN(fcn(c, sl, S.fcn, a_raw, a_bn, &J0, &out->rows[13]));
+      GEN(fcn(c, sl, ssets, S.fcn, a_raw, a_bn, &J0, &out->rows[13]));
       GALLOC(sdf, float, m);
       GEN(sgnn_linear(J0, 3 * ch, S.w_lin, S.b_lin, sdf, 1, m, 3 * ch, 1, stream));
       out->out_sdf = sdf;

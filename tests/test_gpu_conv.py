@@ -349,54 +349,4 @@ def test_generator_same_bits_with_compact_and_dense_rules():
         assert torch.equal(la, lb) and torch.equal(sa, sb)
         for x, y in zip(lva, lvb):
             assert torch.equal(x[0], y[0]) and torch.equal(x[1], y[1])
-
-
-@pytest.mark.parametrize('cin,cout,K', [(1, 8, 27), (8, 8, 27), (8, 12, 27), (12, 12, 27),
-                                        (12, 16, 27), (16, 16, 27)])
-def test_rowlane_kernel_same_bits_as_row_owner_kernel(cin, cout, K):
-    """sgnn_conv_forward's two kernels for dense tables (conv.cu row-owner, conv_sp.cu lane = (row, channel group)) forced
-    one after the other on a launch larger than the automatic threshold: identical bits, equal to oracle O3."""
-    E = _E()
-    rng = np.random.default_rng(cin * 13 + cout + K)
-    nb, dims = 2, (16, 14, 40)
-    c = random_coords(rng, nb, dims, 0.6)
-    n_in = c.shape[0]
-    ld = (cin + 7) // 8 * 8
-    xbuf = torch.full((n_in, ld), float('nan'))
-    xbuf[:, :cin] = torch.from_numpy(rng.standard_normal((n_in, cin)).astype(np.float32))
-    w = torch.from_numpy((rng.standard_normal((K, cin, cout)) * 0.1).astype(np.float32))
-    if K == 27:
-        tbl = torch.from_numpy(nbr_table(c))
-        n_out = n_in
-    else:
-        cc, parent, children, cd = coarse_sets(c, dims)
-        tbl = torch.from_numpy(children)
-        n_out = cc.shape[0]
-    assert n_out > 4096
-    r = torch.from_numpy(rng.standard_normal((n_out, cout)).astype(np.float32))
-    sa, ta = torch.rand(cout) + 0.5, torch.rand(cout) - 0.5
-    want = o3.conv(xbuf[:, :cin], tbl, w, n_out, residual=r, scale=sa, shift=ta, relu=True)
-    outs = []
-    for flags in (2, 4):                                     # SGNN_CONV_ROWLANE, SGNN_CONV_NO_ROWLANE
-        o = torch.empty((n_out, cout), device='cuda')
-        raw = torch.empty((n_out, cout), device='cuda')
-        E.conv(xbuf.cuda()[:, :cin], tbl.cuda(), w.cuda(), n_out, o, residual=r.cuda(), scale_a=sa.cuda(), shift_a=ta.cuda(),
-               relu_a=True, out_b=raw, flags=flags)
-        outs.append((o.cpu(), raw.cpu()))
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
-    assert torch.equal(outs[0][0], want)
-
-
-def test_rowlane_small_and_ragged_launches():
-    """The automatic route (K = 27, <= 4096 rows): 1 row, 63/64/65 rows (tile edges), absent-only rows."""
-    E = _E()
-    rng = np.random.default_rng(3)
-    for n in (1, 63, 64, 65, 700):
-        x = torch.from_numpy(rng.standard_normal((n, 16)).astype(np.float32))
-        w = torch.from_numpy((rng.standard_normal((27, 16, 16)) * 0.1).astype(np.float32))
-        nbr = torch.from_numpy(rng.integers(-1, n, (27, n)).astype(np.int32))
-        nbr[:, 0] = -1                                        # a row with no neighbour at all -> zeros (+ epilogue)
-        out = torch.empty((n, 16), device='cuda')
-        E.conv(x.cuda(), nbr.cuda(), w.cuda(), n, out)
-        assert torch.equal(out.cpu(), o3.conv(x, nbr, w, n))
-        assert (out[0] == 0).all()
+        m.dense_rules = False
