@@ -48,6 +48,7 @@ def parse():
     ap.add_argument('--conv-mode', default='tc32', choices=['exact', 'tc32'],
                     help="exact: fixed-order FFMA convolutions; tc32: Cout=16 convolutions on tcgen05 (3-way bf16 split)")
     ap.add_argument('--tc32-min-rows', type=int, default=0, help='GenModel.tc32_min_rows (A/B runs; 0 = default)')
+    ap.add_argument('--overlap-max-rows', type=int, default=0, help='A/B: GenModel.overlap_max_rows (0 default, -1 never)')
     ap.add_argument('--dense-rules', action='store_true', help='A/B: dense neighbour table on the encoder input level')
     ap.add_argument('--ur-min-rows', type=int, default=0, help='GenModel.ur_min_rows (A/B runs; 0 = default)')
     return ap.parse_args()
@@ -270,6 +271,7 @@ def run_b200(args):
     model.conv_mode = args.conv_mode
     model.tc32_min_rows, model.ur_min_rows = args.tc32_min_rows, args.ur_min_rows
     model.dense_rules = bool(args.dense_rules)
+    model.overlap_max_rows = int(args.overlap_max_rows)
 
     if args.blocks <= 0:
         args.blocks = 512 if args.config == 3 else 32

@@ -112,6 +112,12 @@ int sgnn_rulebook_submanifold_compact(const SgnnGrid* g, const int32_t* coords, 
  *   children dev [8][n_coarse]   fine row at offset k of coarse row, or -1                       */
 int sgnn_rulebook_strided(const SgnnGrid* coarse, const int32_t* fine_coords, int64_t n_fine,
                           int32_t* parent, int32_t* children, int64_t n_coarse, void* stream);
+/* sgnn_grid_enumerate(coarse) + sgnn_rulebook_strided(coarse, fine) in one kernel, from the coarse side (no memset of the
+ * children table; `parent` is preset to -1 only when an odd fine extent leaves fine sites without a parent).  Requires a
+ * raster-ordered coarse set (sgnn_grid_coarsen) and a fine set without duplicate coordinates (duplicate rows of a mode-0 input
+ * keep the parent of the row that owns the cell only -- use the two calls there).  Same outputs otherwise. */
+int sgnn_grid_coarse_build(const SgnnGrid* fine, const SgnnGrid* coarse, int64_t n_fine, int64_t n_coarse,
+                           int32_t* coarse_coords, int32_t* parent, int32_t* children, void* stream);
 
 /* Epilogue slot of a convolution: y = acc (+ residual); if scale: y = y*scale[c] + shift[c]
  * (one fused multiply-add); if relu: y = max(y, 0).  out == NULL disables the slot. */
@@ -341,6 +347,9 @@ typedef struct SgnnGeneratorW {
   /* SGNN_GEN_TC32 row thresholds, 0 = default: site sets with >= ur_min_rows rows (1000) get a unique-row tile plan; other
    * Cout = 16 convolutions with >= tc32_min_rows output rows (60000) use sgnn_conv_forward_tc32, the rest sgnn_conv_forward */
   int64_t tc32_min_rows, ur_min_rows;
+  /* levels of at most overlap_max_rows rows build the coarse site sets of their FullyConvolutionalNet on a second stream under
+   * their first convolutions (generator.cu fork_side); 0 = default (200000), < 0 = never */
+  int64_t overlap_max_rows;
 } SgnnGeneratorW;
 typedef struct SgnnGeneratorOut {
   int64_t n_out;        int32_t* out_locs;  float* out_sdf;        /* [n_out,4], [n_out,1] */
@@ -353,6 +362,8 @@ typedef struct SgnnGeneratorOut {
 #define SGNN_GEN_CAND_LOCS 1        /* materialise the candidate coordinates of every level (model.py:247,336) */
 #define SGNN_GEN_PROFILE 2          /* time every convolution launch with CUDA events (adds one sync at the end) */
 #define SGNN_GEN_TC32 4             /* run the Cout = 16 convolutions through sgnn_conv_forward_tc32 (tensor cores) */
+#define SGNN_GEN_PHASES 16          /* one CUDA event per phase boundary of the pass: in-situ time of every phase, launch gaps and
+                                     * host reads included (sgnn_generator_phase_entry; adds one sync at the end) */
 #define SGNN_GEN_DENSE_RULES 8      /* A/B: dense neighbour table + sgnn_conv_forward on the encoder's input level instead of the
                                      * compact rulebook + sgnn_conv_forward_compact (same bits either way) */
 /* Prepared tensor-core filter banks of every Cout = 16 convolution of the generator, built once per weight set: with
@@ -366,6 +377,9 @@ int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coords, int coor
 /* Per-convolution record of the calling thread's last SGNN_GEN_PROFILE pass (i = 0 .. n_conv-1, launch order):
  * rec6 = {n_out, cin, cout, K, child_mode, ran on tensor cores}, *ms = CUDA-event duration.  SGNN_E_INVALID past the end. */
 int sgnn_generator_profile_entry(int32_t i, int64_t* rec6, float* ms);
+/* Phase i of the calling thread's last SGNN_GEN_PHASES pass (i = 1 .. n-1): name48 = label (<= 47 chars + NUL), *ms = CUDA-event
+ * time since the previous phase boundary.  SGNN_E_INVALID past the end. */
+int sgnn_generator_phase_entry(int32_t i, char* name48, float* ms);
 
 /* ---- marching cubes on the predicted dense TSDF, the step after the forward pass
  * (reference torch/marching_cubes/marching_cubes.cpp:459-517 run_marching_cubes, called from data_util.py:270-284).

@@ -73,7 +73,7 @@ class SgnnGeneratorW(C.Structure):
     _fields_ = [('enc', SgnnEncLevelW * 3), ('dense', SgnnDenseLayerW * 6), ('w_heads', C.c_void_p),
                 ('nf_coarse', C.c_int32), ('reserved', C.c_int32), ('ref', SgnnRefineW * 3), ('surf', SgnnSurfaceW),
                 ('prepared', C.c_void_p), ('prepared_bytes', C.c_size_t), ('tc32_min_rows', C.c_int64),
-                ('ur_min_rows', C.c_int64)]
+                ('ur_min_rows', C.c_int64), ('overlap_max_rows', C.c_int64)]
 
 
 class SgnnGeneratorOut(C.Structure):
@@ -87,6 +87,7 @@ GEN_CAND_LOCS = 1
 GEN_PROFILE = 2
 GEN_TC32 = 4
 GEN_DENSE_RULES = 8
+GEN_PHASES = 16
 
 _P, _I, _L, _Z = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
 _G, _E = C.POINTER(SgnnGrid), C.POINTER(SgnnEpilogue)
@@ -101,6 +102,7 @@ SIGNATURES = {
     'sgnn_grid_lookup': (_I, [_G, _P, _L, _I, _P, _P]),
     'sgnn_rulebook_submanifold': (_I, [_G, _P, _L, _P, _P]),
     'sgnn_rulebook_strided': (_I, [_G, _P, _L, _P, _P, _L, _P]),
+    'sgnn_grid_coarse_build': (_I, [_G, _G, _L, _L, _P, _P, _P, _P]),
     'sgnn_conv_forward': (_I, [C.POINTER(SgnnConvArgs), _P]),
     'sgnn_conv_forward_compact': (_I, [C.POINTER(SgnnConvArgs), _P, _P, _P]),
     'sgnn_rulebook_submanifold_plan': (_I, [_G, _P, _L, _P, _P, _Z, _P]),
@@ -134,6 +136,7 @@ SIGNATURES = {
     'sgnn_generator_forward': (_I, [C.POINTER(SgnnGeneratorW), _P, _I, _P, _L, _I, C.POINTER(C.c_int32), _P, _Z, _I,
                                     C.POINTER(SgnnGeneratorOut), _P]),
     'sgnn_generator_profile_entry': (_I, [_I, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
+    'sgnn_generator_phase_entry': (_I, [_I, C.c_char_p, C.POINTER(C.c_float)]),
     'sgnn_mc_scratch_bytes': (_Z, [_I, _I, _I]),
     'sgnn_mc_count': (_I, [_P, _I, _I, _I, C.c_float, C.c_float, C.c_float, _P, _P, _Z, _P]),
     'sgnn_mc_emit': (_I, [_P, _I, _I, _I, C.c_float, C.c_float, C.c_float, _P, _P, _P]),

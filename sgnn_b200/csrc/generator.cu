@@ -5,6 +5,7 @@
 // Memory comes from a caller-provided bump arena (no cudaMalloc on the path); temporaries are released in
 // stream order.  The arithmetic is the fused composition of sgnn_b200/fused.py -- bit-identical to the
 // module-by-module path.
+#include <stdio.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -15,6 +16,8 @@
 //    that a launch cannot fill the chip with 128-row tiles and the FFMA kernel's shorter per-tile latency wins.
 #define SGNN_DEFAULT_TC32_MIN_ROWS 60000
 #define SGNN_DEFAULT_UR_MIN_ROWS 1000
+// levels of at most this many rows build their coarse site sets on the side stream (SgnnGeneratorW::overlap_max_rows)
+#define SGNN_DEFAULT_OVERLAP_MAX_ROWS 200000
 
 namespace {
 
@@ -34,11 +37,16 @@ struct Arena {
 
 struct Ctx {
   Arena ar;
-  cudaStream_t st;
+  cudaStream_t st;        // the stream helper calls enqueue on: main_st, or side_st between use_side() and use_main()
   void* stream;
+  cudaStream_t main_st, side_st;   // side_st == nullptr: no overlap, everything on main_st
+  bool side_on;                    // between fork_side() and join_side() of a level small enough to overlap
+  long long overlap_max_rows;
   bool profile;
   bool tc32;
   bool compact;    // compact rulebook + conv_sp.cu on the encoder's input level
+  bool phases;
+  int n_ph;
   int n_ev;
   const SgnnGeneratorW* w;
   long long tc32_min_rows, ur_min_rows;
@@ -51,6 +59,14 @@ static thread_local int g_ev_made = 0;
 struct ConvRec { int64_t n_out; int cin, cout, K, child, tc; float ms; };
 static thread_local ConvRec g_rec[256];
 static thread_local int g_nrec = 0;
+
+// SGNN_GEN_PHASES: one CUDA event at every phase boundary of the pass (~45 marks); the time between consecutive marks is what
+// the phase really costs in situ -- kernels, launch gaps, memsets and host-read stalls included (sgnn_generator_phase_entry).
+struct PhaseRec { char name[48]; float ms; };
+static thread_local cudaEvent_t g_ph_ev[96];
+static thread_local int g_ph_made = 0;
+static thread_local PhaseRec g_ph[96];
+static thread_local int g_nph = 0;
 
 struct Epi {
   float* out; int ld; const float* scale; const float* shift; int relu;
@@ -70,6 +86,7 @@ struct Level {
   void* plan;      // unique-row tile plan of nbr (conv_ur.cu) or nullptr
   int32_t* slots;  // compact rulebook (grid.cu COMPACT / conv_sp.cu) instead of nbr, or nullptr
   uint8_t* cnt;
+  bool unique;     // no two rows share a coordinate (every set except the caller's input)
   int64_t n;
   int dims[3];
 };
@@ -97,6 +114,63 @@ static int read_i32(Ctx& c, const int32_t* dev, int32_t* host) {
   SGNN_CUDA(cudaMemcpyAsync(pin, dev, 4, cudaMemcpyDeviceToHost, c.st));
   SGNN_CUDA(cudaStreamSynchronize(c.st));
   *host = pin[0];
+  return SGNN_OK;
+}
+
+// ---- side stream for the SMALL levels.  The coarse site sets of a level (masks, ranks, coordinates, strided rulebooks,
+// neighbour tables, plans: ~20 tiny launches) depend only on the level's own grid, not on its features.  On levels of a few
+// thousand rows every launch is pure latency (~5 us each, profiles/r02_phases_*.txt), so there they are built on a second stream
+// while the level's first convolutions run on the caller's stream.  Only there: on the large levels the small grid kernels would
+// share SMs with the persistent one-CTA-per-SM tensor-core convolutions and delay their CTAs (measured: 4.44 ms per step
+// single-stream, 4.64 / 4.71 ms with the levels of >= 100 k / >= 300 k rows overlapped, profiles/r02_ab_runs.txt).
+// fork: side waits for main's tail; join: main waits for side's tail.  Scratch handed out by the arena is never recycled within
+// a pass (the bump pointer only grows), so memory used on one stream is never re-issued to the other.
+static thread_local cudaStream_t g_side_stream[64] = {};
+static thread_local cudaEvent_t g_fj_ev[16] = {};
+static thread_local int g_fj_next = 0;
+static cudaStream_t side_stream() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!g_side_stream[dev] && cudaStreamCreateWithFlags(&g_side_stream[dev], cudaStreamNonBlocking) != cudaSuccess) {
+    g_side_stream[dev] = nullptr;
+    cudaGetLastError();
+  }
+  return g_side_stream[dev];
+}
+static int order_after(cudaStream_t waiter, cudaStream_t signaller) {
+  cudaEvent_t& e = g_fj_ev[g_fj_next];
+  g_fj_next = (g_fj_next + 1) & 15;
+  if (!e) SGNN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  SGNN_CUDA(cudaEventRecord(e, signaller));
+  SGNN_CUDA(cudaStreamWaitEvent(waiter, e, 0));
+  return SGNN_OK;
+}
+static void use_main(Ctx& c) { c.st = c.main_st; c.stream = (void*)c.main_st; }
+static void use_side(Ctx& c) { if (c.side_on) { c.st = c.side_st; c.stream = (void*)c.side_st; } }
+static int fork_side(Ctx& c, int64_t level_rows) {     // side work from here on sees everything enqueued on main so far
+  c.side_on = c.side_st && level_rows <= c.overlap_max_rows;
+  if (!c.side_on) return SGNN_OK;
+  RC(order_after(c.side_st, c.main_st));
+  use_side(c);
+  return SGNN_OK;
+}
+static int join_side(Ctx& c) {     // main work from here on sees everything enqueued on side so far
+  use_main(c);
+  if (!c.side_on) return SGNN_OK;
+  c.side_on = false;
+  return order_after(c.main_st, c.side_st);
+}
+
+// phase boundary: everything enqueued since the previous mark is accounted to `name`
+static int mark(Ctx& c, const char* name, int level = -1) {
+  if (!c.phases || c.n_ph >= 96) return SGNN_OK;
+  while (g_ph_made <= c.n_ph) SGNN_CUDA(cudaEventCreate(&g_ph_ev[g_ph_made++]));
+  SGNN_CUDA(cudaEventRecord(g_ph_ev[c.n_ph], c.st));
+  PhaseRec& r = g_ph[c.n_ph];
+  if (level >= 0) snprintf(r.name, sizeof(r.name), "L%d %s", level, name);
+  else snprintf(r.name, sizeof(r.name), "%s", name);
+  r.ms = 0.f;
+  ++c.n_ph;
   return SGNN_OK;
 }
 
@@ -131,6 +205,7 @@ static int build_level(Ctx& c, const void* coords, int is64, int64_t n, int nb, 
   grid_shape(&L->g, nb, dims);
   for (int i = 0; i < 3; ++i) L->dims[i] = dims[i];
   L->n = n;
+  L->unique = status == nullptr;   // internal levels (children of distinct kept sites); the caller's input is checked, not trusted
   ALLOC(mask, uint64_t, L->g.n_words);
   ALLOC(prefix, int32_t, L->g.n_words + 1);
   ALLOC(ror, int32_t, n);
@@ -162,6 +237,7 @@ static int coarsen_begin(Ctx& c, const Level& f, Level* L) {
   ALLOC(prefix, int32_t, L->g.n_words + 1);
   L->g.mask = mask; L->g.prefix = prefix; L->g.row_of_rank = nullptr;
   L->n = -1; L->coords = nullptr; L->nbr = nullptr; L->plan = nullptr; L->slots = nullptr; L->cnt = nullptr;
+  L->unique = true;   // one row per set bit
   const size_t sb = sgnn_scan_scratch_bytes(L->g.n_words);
   ALLOC(scr, char, sb);
   RC(sgnn_grid_coarsen(&f.g, &L->g, scr, sb, c.stream));
@@ -194,11 +270,15 @@ static int coarsen_finish(Ctx& c, const Level& f, Level* L, int32_t** parent, in
   const int64_t cnt = L->n;
   ALLOC(cc, int32_t, cnt * 4);
   L->coords = cc;
-  if (cnt) RC(sgnn_grid_enumerate(&L->g, cc, c.stream));
   ALLOC(par, int32_t, f.n);
   ALLOC(chi, int32_t, cnt * 8);
   *parent = par; *children = chi;
-  RC(sgnn_rulebook_strided(&L->g, f.coords, f.n, par, chi, cnt, c.stream));
+  if (f.unique) {   // coordinates + strided rulebook in one kernel, from the coarse side
+    RC(sgnn_grid_coarse_build(&f.g, &L->g, f.n, cnt, cc, par, chi, c.stream));
+  } else {          // the caller's input set may hold duplicate coordinates: every duplicate row gets its parent
+    if (cnt) RC(sgnn_grid_enumerate(&L->g, cc, c.stream));
+    RC(sgnn_rulebook_strided(&L->g, f.coords, f.n, par, chi, cnt, c.stream));
+  }
   L->nbr = nullptr;
   if (want_nbr) {
     ALLOC(nbr, int32_t, cnt * 27);
@@ -318,20 +398,21 @@ static int res_block(Ctx& c, const Level& lv, const SgnnResBlockW& rb, int ch, c
 // The two coarse site sets of a level's FullyConvolutionalNet, first half: masks + rank scans + the count copies, enqueued as
 // soon as the level's own grid exists -- BEFORE its first convolution, so that the counts have long arrived when the host asks
 // for them (counts_wait, after it has enqueued that convolution and the first residual block) and the host never stalls there.
-// (Measured and removed: building these sets on a second stream under the convolutions.  Same bits, but the small grid
-// kernels then share SMs with the persistent one-CTA-per-SM tensor-core convolutions and delay their CTAs: 4.44 ms per step
-// single-stream against 4.64 / 4.71 ms with the levels of >= 100 k / >= 300 k rows overlapped, profiles/r02_ab_runs.txt.)
+// On small levels the rest of the construction runs on the side stream (fork_side above).
 struct FcnSets { Level lv1, lv2; };
 static int fcn_begin(Ctx& c, const Level& lv0, FcnSets* s) {
   if (lv0.n == 0) return SGNN_OK;
+  RC(fork_side(c, lv0.n));
   RC(coarsen_begin(c, lv0, &s->lv1));
   RC(coarsen_begin(c, s->lv1, &s->lv2));
   Level* pend[2] = {&s->lv1, &s->lv2};
-  return counts_post(c, pend, 2);
+  RC(counts_post(c, pend, 2));
+  use_main(c);
+  return SGNN_OK;
 }
 
 static int fcn(Ctx& c, const Level& lv0, FcnSets& sets, const SgnnFcnW& f, const float* x_raw, const float* x_bn, float** out,
-               int64_t rows[3]) {
+               int64_t rows[3], int lvl) {
   const int ch = f.c;
   ALLOC(J0, float, lv0.n * 3 * ch);
   *out = J0;
@@ -344,9 +425,13 @@ static int fcn(Ctx& c, const Level& lv0, FcnSets& sets, const SgnnFcnW& f, const
   // the finest residual block does not depend on the coarse sets: it is enqueued before the host asks for their counts
   ALLOC(y0_bn, float, lv0.n * ch);
   RC(res_block(c, lv0, f.blk[0], ch, x_raw, x_bn, epi_bn(J0, 3 * ch, f.bn_join), epi_bn(y0_bn, ch, f.bn_down[0])));
+  RC(mark(c, "FCN residual block, finest", lvl));
   RC(counts_wait(c, pend, 2));
+  use_side(c);
   RC(coarsen_finish(c, lv0, &lv1, &par01, &chi01, true, ch));
   RC(coarsen_finish(c, lv1, &lv2, &par12, &chi12, true, ch));
+  RC(join_side(c));
+  RC(mark(c, "FCN coarse coords + rulebooks + plans", lvl));
   rows[1] = lv1.n;
   rows[2] = lv2.n;
   ALLOC(J1, float, lv1.n * 2 * ch);
@@ -369,9 +454,11 @@ static int fcn(Ctx& c, const Level& lv0, FcnSets& sets, const SgnnFcnW& f, const
     e1.out = J1 + ch; e1.ld = 2 * ch; e1.relu = 0; e1.scale = nullptr; e1.shift = nullptr;
     RC(sgnn_unpool(y2, ch, par12, ch, lv1.n, &e1, c.stream));
   }
+  RC(mark(c, "FCN coarse convolutions + inner unpool", lvl));
   SgnnEpilogue e0;
   e0.out = J0 + ch; e0.ld = 3 * ch; e0.relu = 1; e0.scale = f.bn_join.scale + ch; e0.shift = f.bn_join.shift + ch;
-  return sgnn_unpool(J1, 2 * ch, par01, 2 * ch, lv0.n, &e0, c.stream);
+  RC(sgnn_unpool(J1, 2 * ch, par01, 2 * ch, lv0.n, &e0, c.stream));
+  return mark(c, "FCN outer unpool", lvl);
 }
 
 // leading dimension of the joined feature rows: a multiple of 8 floats keeps every row 32-byte aligned (256-bit gathers)
@@ -415,9 +502,14 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
   Ctx c;
   c.ar.base = (char*)arena; c.ar.cap = arena_bytes; c.ar.off = 0; c.ar.high = 0; c.ar.oom = false;
   c.st = (cudaStream_t)stream; c.stream = stream;
+  c.main_st = c.st;
+  c.side_on = false;
+  c.overlap_max_rows = w->overlap_max_rows > 0 ? w->overlap_max_rows : (w->overlap_max_rows < 0 ? 0 : SGNN_DEFAULT_OVERLAP_MAX_ROWS);
+  c.side_st = c.overlap_max_rows > 0 ? side_stream() : nullptr;
   c.profile = (flags & SGNN_GEN_PROFILE) != 0; c.n_ev = 0;
   c.tc32 = (flags & SGNN_GEN_TC32) != 0;
   c.compact = (flags & SGNN_GEN_DENSE_RULES) == 0;
+  c.phases = (flags & SGNN_GEN_PHASES) != 0; c.n_ph = 0;
   c.w = w;
   c.tc32_min_rows = w->tc32_min_rows > 0 ? w->tc32_min_rows : SGNN_DEFAULT_TC32_MIN_ROWS;
   c.ur_min_rows = w->ur_min_rows > 0 ? w->ur_min_rows : SGNN_DEFAULT_UR_MIN_ROWS;
@@ -433,7 +525,9 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
     Level lv;
     GALLOC(status, int32_t, 1);
     if ((rc = (cudaMemsetAsync(status, 0, 4, c.st) == cudaSuccess ? SGNN_OK : SGNN_E_CUDA)) != SGNN_OK) break;
+    GEN(mark(c, "start"));
     GEN(build_level(c, coords, coords_i64, n, nb, dims, status, &lv, c.compact));
+    GEN(mark(c, "encoder: input grid + rulebook"));
     out->rows[0] = n;
     Skip skips[4];
     const float* x = feats;
@@ -452,6 +546,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       break;
     Level* enc_pend[3] = {&enc_lv[1], &enc_lv[2], &enc_lv[3]};
     GEN(counts_post(c, enc_pend, 3));
+    GEN(mark(c, "encoder: pyramid masks + scans"));
     bool enc_ok = true;
     for (int l = 0; l < 3 && enc_ok; ++l) {
       const SgnnEncLevelW& e = w->enc[l];
@@ -471,7 +566,9 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
         if (pinb[8]) { rc = SGNN_E_INVALID; break; }   // a coordinate outside [0, dims) x [0, nb): scn raises here too
         GEN(coarsen_finish(c, enc_lv[0], &enc_lv[1], &enc_par[0], &enc_chi[0], true, w->enc[1].c));
         GEN(coarsen_finish(c, enc_lv[1], &enc_lv[2], &enc_par[1], &enc_chi[1], true, w->enc[2].c));
+        GEN(mark(c, "encoder: input-level convolutions"));
         GEN(coarsen_finish(c, enc_lv[2], &enc_lv[3], &enc_par[2], &enc_chi[2], false));
+        GEN(mark(c, "encoder: pyramid coords + rulebooks + plans"));
       }
       Level cl = enc_lv[l + 1];
       int32_t* chi = enc_chi[l];
@@ -486,6 +583,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       enc_ok = true;
     }
     if (rc || !enc_ok) { if (!rc) rc = SGNN_E_NOMEM; break; }
+    GEN(mark(c, "encoder: remaining convolutions"));
     skips[3].g = lv.g; skips[3].f = x; skips[3].c = ld_x; skips[3].n = lv.n;   // ft3 (model.py:64)
     int dd[3] = {lv.dims[0], lv.dims[1], lv.dims[2]};
     // ------------------------------------------------------------ dense U-Net (model.py:152-166)
@@ -527,6 +625,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
     GALLOC(occsdf, float, (int64_t)nb * 2 * dvol);
     GEN(sgnn_dense_conv3d(cur, cur_c, nullptr, 0, nb, dd[0], dd[1], dd[2], w->w_heads, 2, 1, 1, 0, nullptr, nullptr, 0,
                           occsdf, stream));
+    GEN(mark(c, "dense U-Net (8 launches)"));
     // ------------------------------------------------------------ a8: dense -> sparse (model.py:315-336)
     const int64_t ncell = (int64_t)nb * dvol;
     GALLOC(cand0, float, ncell * 2);
@@ -550,6 +649,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       locs = l0; fts = f0;
       GEN(sgnn_dense_write(cur, occsdf, nb, w->nf_coarse, dd[0], dd[1], dd[2], dflags, offs, locs, fts, ld_f, stream));
     }
+    GEN(mark(c, "dense -> sparse (flags, scan, host read, write)"));
     out->n_cand[0] = ncell; out->cand[0] = cand0;
     out->cand_locs[0] = nullptr;   // level 0 candidates are ALL cells in batch-major raster order: implicit
     // ------------------------------------------------------------ refinement levels (model.py:387-396)
@@ -565,21 +665,26 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       // (rows of an empty skip set keep the zeros written with the row)
       live_c += sk.c;
       if (live_c != R.cin) { rc = SGNN_E_INVALID; break; }
+      GEN(mark(c, "skip join (level 0 only)", h));
       Level rl;
       const int ch = R.c;
       GEN(build_level(c, locs, 0, m, nb, rdims, nullptr, &rl, false, ch));
+      GEN(mark(c, "grid + rulebook + plan", h));
       FcnSets rsets;
       GEN(fcn_begin(c, rl, &rsets));
+      GEN(mark(c, "coarse masks + scans", h));
       GALLOC(a_raw, float, m * ch);
       GALLOC(a_bn, float, m * ch);
       GEN(conv(c, fts, ld_f, R.cin, rl.nbr, m, 27, 0, R.w_in, ch, m, nullptr, 0, epi(a_raw, ch),
                epi_bn(a_bn, ch, R.fcn.blk[0].bn0), 0, rl.plan));
       float* J0 = nullptr;
-      GEN(fcn(c, rl, rsets, R.fcn, a_raw, a_bn, &J0, &out->rows[4 + 3 * h]));
+      GEN(mark(c, "first convolution", h));
+      GEN(fcn(c, rl, rsets, R.fcn, a_raw, a_bn, &J0, &out->rows[4 + 3 * h], h));
       // a9: 8 children per site, never materialised: n1 in child mode + n2, heads, mask, compaction
       const int64_t ncand = 8 * m;
       GALLOC(xc, float, ncand * ch);
       GEN(conv(c, J0, 3 * ch, 3 * ch, rl.nbr, m, 27, 1, R.w_up, ch, ncand, nullptr, 0, epi_bn(xc, ch, R.bn_up), kNoEpi, m, rl.plan));
+      GEN(mark(c, "child-mode convolution", h));
       GALLOC(cand, float, ncand * 2);
       GALLOC(flg, uint8_t, ncand);
       GALLOC(offs, int32_t, ncand + 1);
@@ -588,6 +693,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       GEN(sgnn_heads_flags(xc, ch, ch, R.w_occ, R.b_occ, R.w_sdf, R.b_sdf, ncand, cand, flg, offs, scr, sb, stream));
       int32_t cnt = 0;
       GEN(read_i32(c, offs + ncand, &cnt));
+      GEN(mark(c, "heads + scan + host read", h));
       out->n_cand[h + 1] = ncand; out->cand[h + 1] = cand;
       if (flags & SGNN_GEN_CAND_LOCS) {
         GALLOC(cl, int32_t, ncand * 4);
@@ -605,6 +711,7 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       } else {
         GEN(sgnn_heads_write(xc, ch, ch, cand, locs, ncand, flg, offs, nl, nf, ld_n, stream));
       }
+      GEN(mark(c, "candidate coords + kept rows (+ skip join)", h));
       locs = nl; fts = nf; ld_f = ld_n; live_c = ch + 2; m = cnt;
       for (int i = 0; i < 3; ++i) rdims[i] *= 2;
       ref_ok = true;
@@ -622,17 +729,21 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       Level sl;
       const int ch = S.c;
       GEN(build_level(c, locs, 0, m, nb, rdims, nullptr, &sl, false, ch));
+      GEN(mark(c, "grid + rulebook + plan", 3));
       FcnSets ssets;
       GEN(fcn_begin(c, sl, &ssets));
+      GEN(mark(c, "coarse masks + scans", 3));
       GALLOC(a_raw, float, m * ch);
       GALLOC(a_bn, float, m * ch);
       GEN(conv(c, fts, ld_f, S.cin, sl.nbr, m, 27, 0, S.w_in, ch, m, nullptr, 0, epi(a_raw, ch),
                epi_bn(a_bn, ch, S.fcn.blk[0].bn0), 0, sl.plan));
       float* J0 = nullptr;
-      GEN(fcn(c, sl, ssets, S.fcn, a_raw, a_bn, &J0, &out->rows[13]));
+      GEN(mark(c, "first convolution", 3));
+      GEN(fcn(c, sl, ssets, S.fcn, a_raw, a_bn, &J0, &out->rows[13], 3));
       GALLOC(sdf, float, m);
       GEN(sgnn_linear(J0, 3 * ch, S.w_lin, S.b_lin, sdf, 1, m, 3 * ch, 1, stream));
       out->out_sdf = sdf;
+      GEN(mark(c, "TSDF head", 3));
     }
   } while (0);
   if (c.profile && c.n_ev > 0 && rc == SGNN_OK) {
@@ -648,6 +759,21 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
     out->conv_ms = ms;
     out->n_conv = c.n_ev / 2;
   }
+  // whatever happened above, nothing stays in flight on the side stream that the caller's stream does not wait for
+  if (c.side_st) {
+    use_main(c);
+    if (order_after(c.main_st, c.side_st) != SGNN_OK && rc == SGNN_OK) rc = SGNN_E_CUDA;
+  }
+  g_nph = 0;
+  if (c.phases && c.n_ph > 1 && rc == SGNN_OK) {
+    SGNN_CUDA(cudaStreamSynchronize(c.st));
+    for (int i = 1; i < c.n_ph; ++i) {
+      float t = 0.f;
+      SGNN_CUDA(cudaEventElapsedTime(&t, g_ph_ev[i - 1], g_ph_ev[i]));
+      g_ph[i].ms = t;
+    }
+    g_nph = c.n_ph;
+  }
   out->arena_used = c.ar.off;
   out->arena_needed = c.ar.high > arena_bytes ? 2 * c.ar.high : c.ar.high;
   if (c.ar.oom && rc == SGNN_OK) rc = SGNN_E_NOMEM;
@@ -661,5 +787,14 @@ extern "C" int sgnn_generator_profile_entry(int32_t i, int64_t* rec6, float* ms)
   const ConvRec& r = g_rec[i];
   rec6[0] = r.n_out; rec6[1] = r.cin; rec6[2] = r.cout; rec6[3] = r.K; rec6[4] = r.child; rec6[5] = r.tc;
   *ms = r.ms;
+  return SGNN_OK;
+}
+
+// i-th phase of the calling thread's last SGNN_GEN_PHASES pass (i = 1 .. n-1; entry 0 is the start mark): name (<= 47 chars) and
+// the CUDA-event time since the previous mark.  SGNN_E_INVALID past the end.
+extern "C" int sgnn_generator_phase_entry(int32_t i, char* name48, float* ms) {
+  if (i < 0 || i >= g_nph || !name48 || !ms) return SGNN_E_INVALID;
+  memcpy(name48, g_ph[i].name, sizeof(g_ph[i].name));
+  *ms = g_ph[i].ms;
   return SGNN_OK;
 }

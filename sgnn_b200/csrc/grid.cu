@@ -174,6 +174,84 @@ extern "C" int sgnn_grid_enumerate(const SgnnGrid* g, int32_t* coords_out, void*
   return SGNN_OK;
 }
 
+// ------------------------------------------- coarse set, second half, in one kernel
+// Coordinates of a raster-ordered coarse set (grid_enumerate) AND its filter-2 stride-2 rulebook against the fine set
+// (rulebook_strided + the memset of its children table), from the coarse side: a thread walks the set bits of one byte of a
+// coarse mask word; for each coarse site it writes the coordinates, probes its 8 fine cells (two x-neighbours share a fine mask word),
+// writes children[k][row] for all 8 (-1 = absent: no memset needed) and parent[fine_row] = row * 8 + k for the present ones.
+// Every fine site whose coordinates halve into the coarse extent is visited exactly once (fine rows are unique cells), so
+// `parent` is fully written when the fine extents are even; otherwise the caller presets it to -1.
+__global__ void __launch_bounds__(128)
+grid_coarse_build_kernel(GridView c, GridView f, int* __restrict__ ccoords, int* __restrict__ parent,
+                         int* __restrict__ children, long long n_coarse) {
+  // a thread takes one BYTE of a coarse mask word (8 threads per word: the large levels have ~1 site per word, the dense
+  // small ones up to 64 -- a whole word per thread left most of the chip idle there)
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < c.n_words * 8;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long w = t >> 3;
+    const int g8 = (int)(t & 7) * 8;
+    const unsigned long long mw = __ldg(c.mask + w);
+    unsigned m = (unsigned)(mw >> g8) & 0xffu;
+    if (!m) continue;
+    const int wc = (int)(w % c.wx);
+    long long r = w / c.wx;
+    const int y = (int)(r % c.d1); r /= c.d1;
+    const int z = (int)(r % c.d0);
+    const int b = (int)(r / c.d0);
+    int row = __ldg(c.prefix + w) + __popcll(mw & ((1ull << g8) - 1));
+    while (m) {
+      const int bit = g8 + __ffs((int)m) - 1;
+      m &= m - 1;
+      const int x = wc * 64 + bit;
+      reinterpret_cast<int4*>(ccoords)[row] = make_int4(z, y, x, b);
+#pragma unroll
+      for (int kz = 0; kz < 2; ++kz)
+#pragma unroll
+        for (int ky = 0; ky < 2; ++ky) {
+          const int fz = 2 * z + kz, fy = 2 * y + ky, fx = 2 * x;
+          int r0 = -1, r1 = -1;
+          if (fz < f.d0 && fy < f.d1 && fx < f.d2) {
+            const long long fw = grid_word(f, b, fz, fy, fx);            // fx even: fx and fx + 1 sit in the same word
+            const unsigned long long fm = __ldg(f.mask + fw);
+            const unsigned two = (unsigned)(fm >> (fx & 63)) & 3u;
+            if (two) {
+              const int base = __ldg(f.prefix + fw) + __popcll(fm & ((1ull << (fx & 63)) - 1));
+              if (two & 1) r0 = f.row_of_rank ? __ldg(f.row_of_rank + base) : base;
+              if ((two & 2) && fx + 1 < f.d2) {
+                const int rk = base + (two & 1);
+                r1 = f.row_of_rank ? __ldg(f.row_of_rank + rk) : rk;
+              }
+            }
+          }
+          const int k = (kz << 2) | (ky << 1);
+          children[(long long)k * n_coarse + row] = r0;
+          children[(long long)(k + 1) * n_coarse + row] = r1;
+          if (r0 >= 0) parent[r0] = row * 8 + k;
+          if (r1 >= 0) parent[r1] = row * 8 + k + 1;
+        }
+      ++row;
+    }
+  }
+}
+
+extern "C" int sgnn_grid_coarse_build(const SgnnGrid* fine, const SgnnGrid* coarse, int64_t n_fine, int64_t n_coarse,
+                                      int32_t* coarse_coords, int32_t* parent, int32_t* children, void* stream) {
+  if (!fine || !coarse || !fine->mask || !fine->prefix || !coarse->mask || !coarse->prefix || n_fine < 0 || n_coarse < 0 ||
+      coarse->row_of_rank || (n_fine > 0 && !parent) || (n_coarse > 0 && (!coarse_coords || !children)))
+    return SGNN_E_INVALID;
+  if (n_coarse > 0x0fffffffLL) return SGNN_E_TOO_LARGE;
+  cudaStream_t st = (cudaStream_t)stream;
+  // fine sites outside the coarse extent (odd fine extents: scn drops parents >= (S-2)/2+1) keep parent -1
+  const bool covered = coarse->d0 * 2 >= fine->d0 && coarse->d1 * 2 >= fine->d1 && coarse->d2 * 2 >= fine->d2;
+  if (n_fine > 0 && (!covered || n_coarse == 0)) SGNN_CUDA(cudaMemsetAsync(parent, 0xff, (size_t)n_fine * 4, st));
+  if (n_coarse > 0) {
+    grid_coarse_build_kernel<<<sgnn_blocks(coarse->n_words * 8, 128), 128, 0, st>>>(make_view(coarse), make_view(fine),
+                                                                              coarse_coords, parent, children, (long long)n_coarse);
+    SGNN_CHECK_LAUNCH();
+  }
+  return SGNN_OK;
+}
+
 // ----------------------------------------------------------------- lookup
 __global__ void grid_lookup_kernel(GridView g, const int* __restrict__ coords, long long n,
                                    int shift, int* __restrict__ rows) {

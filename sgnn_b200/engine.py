@@ -152,6 +152,17 @@ def rulebook_strided(fine, coarse):
     return parent, children
 
 
+def coarse_build(fine, coarse):
+    """sgnn_grid_coarse_build: coordinates of a raster-ordered coarse set + the strided rulebook against `fine`, one kernel.
+    -> (coords int32 [n_coarse, 4], parent int32 [n_fine], children int32 [8, n_coarse])"""
+    coords = torch.empty((coarse.n, 4), dtype=torch.int32, device=fine.device)
+    parent = torch.empty(fine.n, dtype=torch.int32, device=fine.device)
+    children = torch.empty((8, coarse.n), dtype=torch.int32, device=fine.device)
+    check(lib.sgnn_grid_coarse_build(fine.ref(), coarse.ref(), fine.n, coarse.n, _ptr(coords), _ptr(parent), _ptr(children),
+                                     _stream()), 'sgnn_grid_coarse_build')
+    return coords, parent, children
+
+
 def _epilogue(out, scale=None, shift=None, relu=False):
     e = SgnnEpilogue()
     if out is None:

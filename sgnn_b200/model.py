@@ -226,6 +226,7 @@ class GenModel(nn.Module):
         self.conv_mode = 'tc32'
         self.tc32_min_rows = 0       # row thresholds of the tensor-core paths (0 = library defaults, SgnnGeneratorW)
         self.ur_min_rows = 0
+        self.overlap_max_rows = 0    # levels up to this many rows build their coarse site sets on a side stream (0: default, -1: never)
         self.dense_rules = False     # A/B: dense neighbour table on the encoder's input level (default: compact rulebook; same bits)
 
     # model.py:357-369.  The sizes are upper bounds of mode-0 InputLayers; the reference doubles

@@ -126,6 +126,7 @@ class NativeGenerator(object):
         self.arena_bytes = int(arena_bytes)
         self.last = None
         self.profile = False
+        self.phases = False          # SGNN_GEN_PHASES: per-phase CUDA-event times of the next passes (phase_table())
 
     def _prepare(self, dev):
         m = self.model
@@ -158,6 +159,7 @@ class NativeGenerator(object):
         out = _lib.SgnnGeneratorOut()
         self.weights.w.tc32_min_rows = int(getattr(m, 'tc32_min_rows', 0))
         self.weights.w.ur_min_rows = int(getattr(m, 'ur_min_rows', 0))
+        self.weights.w.overlap_max_rows = int(getattr(m, 'overlap_max_rows', 0))
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         for _ in range(8):
             rc = lib.sgnn_generator_forward(C.byref(self.weights.w), C.c_void_p(locs.data_ptr()),
@@ -165,6 +167,7 @@ class NativeGenerator(object):
                                             locs.shape[0], nb, dims, C.c_void_p(self.arena.data_ptr()),
                                             self.arena.numel(), (_lib.GEN_CAND_LOCS if want_cand_locs else 0) |
                                             (_lib.GEN_PROFILE if self.profile else 0) |
+                                            (_lib.GEN_PHASES if self.phases else 0) |
                                             (_lib.GEN_TC32 if getattr(m, 'conv_mode', 'tc32') == 'tc32' else 0) |
                                             (_lib.GEN_DENSE_RULES if getattr(m, 'dense_rules', False) else 0),
                                             C.byref(out), stream)
@@ -175,6 +178,15 @@ class NativeGenerator(object):
         check(rc, 'sgnn_generator_forward')
         self.last = out
         return out, nb
+
+    def phase_table(self):
+        """[(label, ms)] of the last pass run with self.phases = True."""
+        out, name, ms = [], C.create_string_buffer(48), C.c_float(0)
+        i = 1
+        while lib.sgnn_generator_phase_entry(i, name, C.byref(ms)) == 0:
+            out.append((name.value.decode(), float(ms.value)))
+            i += 1
+        return out
 
     def view(self, ptr, shape, dtype):
         """Tensor view into the arena (valid until the next forward)."""

@@ -350,3 +350,28 @@ def test_generator_same_bits_with_compact_and_dense_rules():
         for x, y in zip(lva, lvb):
             assert torch.equal(x[0], y[0]) and torch.equal(x[1], y[1])
         m.dense_rules = False
+
+
+def test_generator_same_bits_with_and_without_the_side_stream():
+    """Small levels build their coarse site sets on a side stream under the level's first convolutions (generator.cu fork_side /
+    join_side; GenModel.overlap_max_rows, -1 = never).  Same bits as the single-stream order, repeatedly (a missing
+    cross-stream dependency would show as a difference on some repetition)."""
+    import sgnn_b200
+    from sgnn_b200.synth import fill_parameters, synthetic_batch
+    m = sgnn_b200.GenModel(8, 64, 1, 16, 16, 4, True, True, 1, 1)
+    fill_parameters(m, 0)
+    m = m.cuda().eval()
+    ones = np.ones(5, dtype=np.float32)
+    batches = [synthetic_batch(8, 64, 0.05, first=8 * i) for i in range(3)]
+    for mode in ('tc32', 'exact'):
+        m.conv_mode = mode
+        m.overlap_max_rows = -1
+        want = [m([l.cuda(), f.cuda(), 8], ones) for l, f in batches]
+        for setting in (0, 1 << 40):                      # default threshold; every level
+            m.overlap_max_rows = setting
+            for rep in range(3):
+                for (l, f), ((wl, ws), wlv) in zip(batches, want):
+                    (gl, gs), glv = m([l.cuda(), f.cuda(), 8], ones)
+                    assert torch.equal(wl, gl) and torch.equal(ws, gs), (mode, setting, rep)
+                    for x, y in zip(wlv, glv):
+                        assert torch.equal(x[0], y[0]) and torch.equal(x[1], y[1]), (mode, setting, rep)

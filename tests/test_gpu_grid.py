@@ -63,6 +63,10 @@ def test_coarsen_and_strided_rulebook(nb, dims, occ, empty, shuffle):
     p, ch = E.rulebook_strided(g, cg)
     assert np.array_equal(p.cpu().numpy(), parent)
     assert np.array_equal(ch.cpu().numpy(), children)
+    # the same three tables from the one-kernel form (sgnn_grid_coarse_build: coordinates + strided rulebook, coarse side)
+    fc, fp, fch = E.coarse_build(g, cg)
+    assert np.array_equal(fc.cpu().numpy(), cc) and np.array_equal(fp.cpu().numpy(), parent)
+    assert np.array_equal(fch.cpu().numpy(), children)
     # shifted lookup = parent row
     rows = E.grid_lookup(cg, g.coords, shift=1).cpu().numpy()
     assert np.array_equal(rows, np.where(parent >= 0, parent >> 3, -1))
