@@ -40,7 +40,7 @@ namespace {
 // (the table the direct mode, the child-mode kernel and the FFMA fallbacks read) and goes straight on to the plan: the table
 // is written once and not read back (27 x 4 B per row less traffic and one launch less per site set).
 template <bool PROBE>
-__global__ void __launch_bounds__(128, PROBE ? 6 : 8)
+__global__ void __launch_bounds__(128, 8)
 tile_plan_kernel(const int* __restrict__ nbr, long long nbr_stride, long long n_rows, long long n_tiles,
                  int* __restrict__ ucount, int* __restrict__ urows, unsigned short* __restrict__ lidx,
                  GridView g, const int* __restrict__ coords, int* __restrict__ nbr_out) {
@@ -571,7 +571,7 @@ extern "C" int sgnn_rulebook_submanifold_plan(const SgnnGrid* g, const int32_t* 
   if (!al(plan, 256)) return SGNN_E_ALIGN;
   const long long tiles = (n + 127) / 128;
   PlanView v = plan_view(plan, tiles);
-  long long grid = tiles < 148 * 6 ? tiles : 148 * 6;
+  long long grid = tiles < 148 * 8 ? tiles : 148 * 8;
   tile_plan_kernel<true><<<(int)grid, 128, 0, (cudaStream_t)stream>>>(nullptr, n, n, tiles, (int*)v.ucount, (int*)v.urows,
                                                                        (unsigned short*)v.lidx, make_view(g), coords, nbr);
   SGNN_CHECK_LAUNCH();

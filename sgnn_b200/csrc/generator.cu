@@ -183,6 +183,7 @@ static void grid_shape(SgnnGrid* g, int nb, const int dims[3]) {
 
 // does a site set of n rows feeding Cout = cout convolutions get a unique-row tile plan?  (The kernel also takes Cout 8 / 12,
 // but on the sparse encoder levels its per-tile overhead loses to the FFMA kernels: 87-95 us against 68-72 us for 420 k rows.)
+// (Measured again in round 2 for the 352 k-row Cout = 12 encoder level: no difference, 4.19-4.27 against 4.22-4.24 ms per step.)
 static bool wants_plan(const Ctx& c, int64_t n, int cout) { return c.tc32 && cout == 16 && n >= c.ur_min_rows; }
 
 // neighbour table of a site set and, when it qualifies, its tile plan -- in one kernel (sgnn_rulebook_submanifold_plan)
