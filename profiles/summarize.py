@@ -2,7 +2,7 @@
 """Summarise ncu artefacts brought back in gpurun_out/ into small text files under profiles/.
   python profiles/summarize.py rep <file.ncu-rep> <out.txt>       key metrics per captured kernel
   python profiles/summarize.py launches <launches.csv> <out.txt> [forwards-per-run kernel-name count]
-  python profiles/summarize.py dram <metrics.csv> <out.json>      DRAM bytes + duration per captured launch (bench.py's
+  python profiles/summarize.py dram <metrics.csv> <out.json> [last-n]  DRAM bytes + duration per captured launch (bench.py's
                                                                   roofline.traffic reads profiles/conv_dram_traffic.json)
 """
 import collections
@@ -73,7 +73,7 @@ def launches(path, out, per=None):
         f.write('%-72s %9s %14.1f\n' % ('TOTAL', '', tot / 1e3 / nf))
 
 
-def dram(path, out):
+def dram(path, out, last=0):
     import json
     lines = [l for l in open(path) if not l.startswith('==')]
     by = collections.OrderedDict()
@@ -84,9 +84,19 @@ def dram(path, out):
     launches_ = [{'kernel': d['kernel'], 'dram_read_bytes': d.get('dram__bytes_read.sum', 0.0),
                   'dram_write_bytes': d.get('dram__bytes_write.sum', 0.0), 'us': d.get('gpu__time_duration.sum', 0.0)}
                  for d in by.values()]
+    if last:            # a first pass that outgrew the arena is re-run by the host mirror: keep the complete pass only
+        launches_ = launches_[-last:]
     tot = sum(l['dram_read_bytes'] + l['dram_write_bytes'] for l in launches_)
+    # stamp: sha256 over the CUDA sources the capture was made with (bench.py quotes the file only for the same sources)
+    import glob
+    import hashlib
+    import os
+    h = hashlib.sha256()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for fn in sorted(glob.glob(os.path.join(root, 'sgnn_b200', 'csrc', '*.cu*'))):
+        h.update(open(fn, 'rb').read())
     with open(out, 'w') as f:
-        json.dump({'source': 'ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control '
+        json.dump({'kernel_source_sha256': h.hexdigest(), 'source': 'ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control '
                              'none over the %d convolution launches of one generator pass (cold cache: ncu flushes L2 '
                              'before every launch)' % len(launches_),
                    'n_launches': len(launches_), 'dram_bytes_total': tot,
@@ -97,6 +107,6 @@ if __name__ == '__main__':
     if sys.argv[1] == 'rep':
         rep(sys.argv[2], sys.argv[3])
     elif sys.argv[1] == 'dram':
-        dram(sys.argv[2], sys.argv[3])
+        dram(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 0)
     else:
         launches(sys.argv[2], sys.argv[3], sys.argv[4:6] if len(sys.argv) > 5 else None)
