@@ -360,6 +360,7 @@ typedef struct SgnnGeneratorOut {
   int64_t n_conv;
 } SgnnGeneratorOut;
 #define SGNN_GEN_CAND_LOCS 1        /* materialise the candidate coordinates of every level (model.py:247,336) */
+#define SGNN_GEN_CAND_PARENTS 32    /* instead: cand_locs[h] = the level's PARENT coordinates [n_cand/8, 4] (for SGNN_EXPORT_CHILDREN) */
 #define SGNN_GEN_PROFILE 2          /* time every convolution launch with CUDA events (adds one sync at the end) */
 #define SGNN_GEN_TC32 4             /* run the Cout = 16 convolutions through sgnn_conv_forward_tc32 (tensor cores) */
 #define SGNN_GEN_PHASES 16          /* one CUDA event per phase boundary of the pass: in-situ time of every phase, launch gaps and
@@ -410,6 +411,26 @@ int sgnn_mc_merge_host_src(const float* tris, int64_t n_tri, float* verts, int32
 int sgnn_mc_tri_cells(const int32_t* offs, int64_t n_cells, int32_t* tri_cell, void* stream);
 /* The packed triangulation table the kernels use: 256 words, 4 bits per triangle-vertex edge id, 0xF terminates. */
 int sgnn_mc_table(uint64_t* out256);
+
+/* ---- result export: every output tensor of a pass in ONE launch.  The generator's results live in its arena; the reference
+ * returns fresh tensors with int64 coordinates (model.py:247,336,380,416).  A segment = n units of one kind:
+ *   COPY32       n 4-byte elements src -> dst
+ *   COORDS       n rows int32 [n,4] -> int32 / int64 (to_i64) [n,4]
+ *   CHILDREN     n = 8 * parents: row i = child (i & 7) of parent row i >> 3 of src int32 [n/8,4] (model.py:192-207)
+ *   DENSE_CELLS  n = nb*d0*d1*d2 cells of a dense grid, batch-major raster order (model.py:319-321); aux = {nb, d0, d1, d2}, no src */
+#define SGNN_EXPORT_COPY32 0
+#define SGNN_EXPORT_COORDS 1
+#define SGNN_EXPORT_CHILDREN 2
+#define SGNN_EXPORT_DENSE_CELLS 3
+#define SGNN_EXPORT_MAX_SEGS 16
+typedef struct SgnnExportSeg {
+  const void* src;
+  void* dst;
+  int64_t n;
+  int32_t kind, to_i64;
+  int32_t aux[4];
+} SgnnExportSeg;
+int sgnn_export(const SgnnExportSeg* segs, int32_t n_segs, void* stream);
 
 /* Candidate coordinates of model.py:192-207: out dev [8*n_parent,4]. */
 int sgnn_children_coords(const int32_t* parent_coords, int64_t n_parent, int32_t* out, void* stream);

@@ -83,7 +83,14 @@ class SgnnGeneratorOut(C.Structure):
                 ('conv_ms', C.c_double), ('n_conv', C.c_int64)]
 
 
+class SgnnExportSeg(C.Structure):
+    _fields_ = [('src', C.c_void_p), ('dst', C.c_void_p), ('n', C.c_int64), ('kind', C.c_int32), ('to_i64', C.c_int32),
+                ('aux', C.c_int32 * 4)]
+
+
+EXPORT_COPY32, EXPORT_COORDS, EXPORT_CHILDREN, EXPORT_DENSE_CELLS = 0, 1, 2, 3
 GEN_CAND_LOCS = 1
+GEN_CAND_PARENTS = 32
 GEN_PROFILE = 2
 GEN_TC32 = 4
 GEN_DENSE_RULES = 8
@@ -145,6 +152,7 @@ SIGNATURES = {
     'sgnn_mc_tri_cells': (_I, [_P, _L, _P, _P]),
     'sgnn_mc_table': (_I, [_P]),
     'sgnn_children_coords': (_I, [_P, _L, _P, _P]),
+    'sgnn_export': (_I, [C.POINTER(SgnnExportSeg), _I, _P]),
     'sgnn_concat_skip': (_I, [_G, _P, _I, _I, _P, _L, _P, _I, _I, _P]),
     'sgnn_coords_to_i64': (_I, [_P, _L, _P, _P]),
     'sgnn_debug_ur_diag': (_I, [_P]),

@@ -303,3 +303,75 @@ extern "C" const char* sgnn_error_string(int code) {
     default: return "unknown sgnn error code";
   }
 }
+
+
+// ------------------------------------------------------------ output export (one launch for every result tensor)
+// The generator's results live in its arena (valid until the next pass); the reference returns fresh tensors and int64
+// coordinates (model.py:247,336,380,416).  Formatting them tensor by tensor from the host mirror cost ~50 framework calls
+// and ~0.9 ms of host time per pass -- more than the GPU had queued, so the device idled.  One kernel walks a list of
+// segments instead.
+struct ExportSegs { SgnnExportSeg s[SGNN_EXPORT_MAX_SEGS]; long long start[SGNN_EXPORT_MAX_SEGS + 1]; int n; };
+
+__device__ __forceinline__ void export_store4(void* dst, long long row, int to64, int z, int y, int x, int b) {
+  if (to64) {
+    longlong2* d = reinterpret_cast<longlong2*>(dst) + 2 * row;
+    d[0] = make_longlong2(z, y);
+    d[1] = make_longlong2(x, b);
+  } else {
+    reinterpret_cast<int4*>(dst)[row] = make_int4(z, y, x, b);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+export_kernel(ExportSegs e) {
+  const long long total = e.start[e.n];
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    int k = 0;
+    while (k + 1 < e.n && t >= e.start[k + 1]) ++k;
+    const SgnnExportSeg& g = e.s[k];
+    const long long i = t - e.start[k];
+    switch (g.kind) {
+      case SGNN_EXPORT_COPY32:
+        reinterpret_cast<int*>(g.dst)[i] = reinterpret_cast<const int*>(g.src)[i];
+        break;
+      case SGNN_EXPORT_COORDS: {          // [n,4] int32 rows -> int32 / int64 rows
+        const int4 c = __ldg(reinterpret_cast<const int4*>(g.src) + i);
+        export_store4(g.dst, i, g.to_i64, c.x, c.y, c.z, c.w);
+        break;
+      }
+      case SGNN_EXPORT_CHILDREN: {        // row i = child (i & 7) of parent row i >> 3 (model.py:192-207)
+        const int4 p = __ldg(reinterpret_cast<const int4*>(g.src) + (i >> 3));
+        const int c = (int)(i & 7);
+        export_store4(g.dst, i, g.to_i64, 2 * p.x + ((c >> 2) & 1), 2 * p.y + ((c >> 1) & 1), 2 * p.z + (c & 1), p.w);
+        break;
+      }
+      default: {                          // SGNN_EXPORT_DENSE_CELLS: all cells of [nb, d0, d1, d2], batch-major raster (model.py:319-321)
+        const int d0 = g.aux[1], d1 = g.aux[2], d2 = g.aux[3];
+        const int x = (int)(i % d2), y = (int)((i / d2) % d1), z = (int)((i / ((long long)d1 * d2)) % d0);
+        const int b = (int)(i / ((long long)d0 * d1 * d2));
+        export_store4(g.dst, i, g.to_i64, z, y, x, b);
+      }
+    }
+  }
+}
+
+extern "C" int sgnn_export(const SgnnExportSeg* segs, int32_t n_segs, void* stream) {
+  if (n_segs < 0 || n_segs > SGNN_EXPORT_MAX_SEGS || (n_segs > 0 && !segs)) return SGNN_E_INVALID;
+  ExportSegs e;
+  e.n = 0;
+  e.start[0] = 0;
+  for (int i = 0; i < n_segs; ++i) {
+    const SgnnExportSeg& g = segs[i];
+    if (g.n < 0 || g.kind < 0 || g.kind > SGNN_EXPORT_DENSE_CELLS) return SGNN_E_INVALID;
+    if (g.n == 0) continue;
+    if (!g.dst || (g.kind != SGNN_EXPORT_DENSE_CELLS && !g.src)) return SGNN_E_INVALID;
+    if (g.kind == SGNN_EXPORT_DENSE_CELLS && (g.aux[1] <= 0 || g.aux[2] <= 0 || g.aux[3] <= 0)) return SGNN_E_INVALID;
+    e.s[e.n] = g;
+    e.start[e.n + 1] = e.start[e.n] + g.n;
+    ++e.n;
+  }
+  if (e.n == 0) return SGNN_OK;
+  export_kernel<<<sgnn_blocks(e.start[e.n], 256), 256, 0, (cudaStream_t)stream>>>(e);
+  SGNN_CHECK_LAUNCH();
+  return SGNN_OK;
+}

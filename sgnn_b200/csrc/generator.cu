@@ -696,7 +696,9 @@ extern "C" int sgnn_generator_forward(const SgnnGeneratorW* w, const void* coord
       GEN(read_i32(c, offs + ncand, &cnt));
       GEN(mark(c, "heads + scan + host read", h));
       out->n_cand[h + 1] = ncand; out->cand[h + 1] = cand;
-      if (flags & SGNN_GEN_CAND_LOCS) {
+      if (flags & SGNN_GEN_CAND_PARENTS) {
+        out->cand_locs[h + 1] = locs;          // the parents: their 8 children each are the candidates, in this order
+      } else if (flags & SGNN_GEN_CAND_LOCS) {
         GALLOC(cl, int32_t, ncand * 4);
         GEN(sgnn_children_coords(locs, m, cl, stream));
         out->cand_locs[h + 1] = cl;

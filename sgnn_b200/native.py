@@ -136,7 +136,7 @@ class NativeGenerator(object):
             self.arena = None
             self.arena = torch.empty(self.arena_bytes, dtype=torch.uint8, device=dev)
 
-    def forward(self, locs, feats, want_cand_locs=True, nb=None):
+    def forward(self, locs, feats, want_cand_locs=True, nb=None, cand_parents=False):
         """locs int64/int32 [n,4] CUDA, feats fp32 [n,cin] CUDA -> raw SgnnGeneratorOut-backed tensors (clones)."""
         dev = feats.device
         m = self.model
@@ -148,9 +148,9 @@ class NativeGenerator(object):
         if next(m.parameters()).device != dev:
             raise RuntimeError('sgnn_b200: model parameters on %s, features on %s' % (next(m.parameters()).device, dev))
         with torch.cuda.device(dev):
-            return self._forward(locs, feats, want_cand_locs, nb, dev)
+            return self._forward(locs, feats, want_cand_locs, nb, dev, cand_parents)
 
-    def _forward(self, locs, feats, want_cand_locs, nb, dev):
+    def _forward(self, locs, feats, want_cand_locs, nb, dev, cand_parents=False):
         self._prepare(dev)
         m = self.model
         dims = (C.c_int32 * 3)(*[int(v) for v in m.encoder.process_sparse[0].p0.spatial_size])
@@ -165,7 +165,8 @@ class NativeGenerator(object):
             rc = lib.sgnn_generator_forward(C.byref(self.weights.w), C.c_void_p(locs.data_ptr()),
                                             1 if locs.dtype == torch.int64 else 0, C.c_void_p(feats.data_ptr()),
                                             locs.shape[0], nb, dims, C.c_void_p(self.arena.data_ptr()),
-                                            self.arena.numel(), (_lib.GEN_CAND_LOCS if want_cand_locs else 0) |
+                                            self.arena.numel(),
+                                            (_lib.GEN_CAND_PARENTS if cand_parents else (_lib.GEN_CAND_LOCS if want_cand_locs else 0)) |
                                             (_lib.GEN_PROFILE if self.profile else 0) |
                                             (_lib.GEN_PHASES if self.phases else 0) |
                                             (_lib.GEN_TC32 if getattr(m, 'conv_mode', 'tc32') == 'tc32' else 0) |
@@ -219,22 +220,48 @@ def forward_native(model, x, loss_weights):
     feats = feats.float().contiguous()
     ssz = [int(v) for v in model.encoder.process_sparse[0].p0.spatial_size]
     with torch.no_grad(), torch.cuda.device(dev):
-        out, nb = g.forward(locs, feats, want_cand_locs=True, nb=int(x[2]) if len(x) > 2 else None)
-        def to64(v):
-            return E.coords_to_i64(v) if model.return_long else v.clone()
-        outputs = []
+        out, nb = g.forward(locs, feats, nb=int(x[2]) if len(x) > 2 else None, cand_parents=True)
+        # Every result tensor is written by ONE kernel (sgnn_export): fresh tensors as the reference returns them (the arena is
+        # recycled by the next pass), int64 coordinates when model.return_long, the candidate coordinates expanded from the
+        # parents on the way.  (Tensor-by-tensor formatting was ~50 framework calls and ~0.9 ms of host time per pass.)
+        to64 = 1 if model.return_long else 0
+        cdt = torch.int64 if to64 else torch.int32
         dd = list(ssz)
         for _ in range(3):
             dd = [(d - 2) // 2 + 1 for d in dd]
-        outputs.append([to64(_dense_cell_coords(nb, dd, dev)), g.view(out.cand[0], (out.n_cand[0], 2), torch.float32).clone()])
+        segs = (_lib.SgnnExportSeg * 16)()
+        ns = 0
+
+        def seg(src, dst, n, kind, aux=None):
+            nonlocal ns
+            sg = segs[ns]
+            sg.src, sg.dst, sg.n, sg.kind, sg.to_i64 = src, dst.data_ptr(), n, kind, to64
+            if aux is not None:
+                sg.aux[0], sg.aux[1], sg.aux[2], sg.aux[3] = aux
+            ns += 1
+        outputs = []
+        n0 = int(out.n_cand[0])
+        l0 = torch.empty((n0, 4), dtype=cdt, device=dev)
+        c0 = torch.empty((n0, 2), dtype=torch.float32, device=dev)
+        seg(None, l0, n0, _lib.EXPORT_DENSE_CELLS, (nb, dd[0], dd[1], dd[2]))
+        seg(out.cand[0], c0, 2 * n0, _lib.EXPORT_COPY32)
+        outputs.append([l0, c0])
         for h in range(1, 4):
-            n = out.n_cand[h]
+            n = int(out.n_cand[h])
             if n == 0:
                 outputs.append([[], []])
                 continue
-            outputs.append([to64(g.view(out.cand_locs[h], (n, 4), torch.int32)),
-                            g.view(out.cand[h], (n, 2), torch.float32).clone()])
-        if out.n_out == 0:
-            return [[], []], outputs
-        ol = to64(g.view(out.out_locs, (out.n_out, 4), torch.int32))
-        return [ol, g.view(out.out_sdf, (out.n_out, 1), torch.float32).clone()], outputs
+            lh = torch.empty((n, 4), dtype=cdt, device=dev)
+            ch = torch.empty((n, 2), dtype=torch.float32, device=dev)
+            seg(out.cand_locs[h], lh, n, _lib.EXPORT_CHILDREN)
+            seg(out.cand[h], ch, 2 * n, _lib.EXPORT_COPY32)
+            outputs.append([lh, ch])
+        result = [[], []]
+        if out.n_out:
+            ol = torch.empty((out.n_out, 4), dtype=cdt, device=dev)
+            os_ = torch.empty((out.n_out, 1), dtype=torch.float32, device=dev)
+            seg(out.out_locs, ol, int(out.n_out), _lib.EXPORT_COORDS)
+            seg(out.out_sdf, os_, int(out.n_out), _lib.EXPORT_COPY32)
+            result = [ol, os_]
+        check(lib.sgnn_export(segs, ns, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), 'sgnn_export')
+        return result, outputs
