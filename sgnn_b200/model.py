@@ -219,6 +219,7 @@ class GenModel(nn.Module):
         self.surfacepred = SurfacePrediction(nf_in, nf, 1, self.refine_sizes[-1])
         self.return_long = True      # LongTensor coordinates at the boundary, like the reference
         self._native = None
+        self._native_ok = None       # cached native.supported(self); re-evaluated when the parameters change or move
         # 'tc32' (default): the wide (Cout = 16) convolutions of the native generator with >= 60000 output rows run on
         # the tensor cores (tcgen05, exact 3-way bf16 split of fp32 features and filters: fp32 accuracy, but not the
         # fmaf order of the FFMA kernels);  'exact': every convolution on the fixed-order FFMA kernels -- bit-reproducible,
@@ -301,9 +302,17 @@ class GenModel(nn.Module):
         """Fast path: the native generator (one C-ABI call, csrc/generator.cu) when the model has the default
         SG-NN structure and every level is requested; otherwise the Python-orchestrated fused path."""
         from . import native
-        if native.supported(self) and all(float(v) > 0 for v in loss_weights):
+        ok = self._native_ok
+        if ok is None or self._native is None or self._native.stale():     # first call, or the parameters changed / moved
+            ok = self._native_ok = native.supported(self)
+        if ok and all(float(v) > 0 for v in loss_weights):
             return native.forward_native(self, x, loss_weights)
         return self.forward_fused(x, loss_weights)
+
+    def invalidate_native(self):
+        """Forget the native generator's cached weight struct and structure check (after replacing sub-modules)."""
+        self._native = None
+        self._native_ok = None
 
     def forward_fused(self, x, loss_weights):
         from .fused import forward_fused

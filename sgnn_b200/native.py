@@ -3,6 +3,7 @@ SgnnGeneratorW struct of device pointers (cached until a parameter changes), own
 ONE C-ABI call per forward and wraps the results.  Same results, bit for bit, as fused.forward_fused /
 GenModel.forward_modules; only the default SG-NN structure (test_scene.py:29-39) is supported natively."""
 import ctypes as C
+import itertools
 
 import torch
 
@@ -29,7 +30,8 @@ class _Weights(object):
 
     def __init__(self, model):
         self.keep = []
-        self.key = self.version_key(model)
+        self.tensors = list(itertools.chain(model.parameters(), model.buffers()))
+        self.key = self.version_key(model, self.tensors)
         self.w = _lib.SgnnGeneratorW()
         self.dev = next(model.parameters()).device
         w = self.w
@@ -79,8 +81,15 @@ class _Weights(object):
                   'sgnn_generator_prepare')
 
     @staticmethod
-    def version_key(model):
-        return tuple((t._version, t.data_ptr()) for t in model.state_dict().values())
+    def version_key(model, tensors=None):
+        """(version counter, address) of every parameter and buffer.  `tensors`: the list cached by NativeGenerator -- walking the
+        module tree (857 us) or building a state_dict (1.5 ms) on EVERY forward made the host, not the GPU, the bottleneck of
+        the pass; over a cached list the key costs ~60 us.  In-place updates (optimizer steps, load_state_dict) bump the
+        version, .to()/.cuda()/.half() change the address; replacing sub-MODULES after the first forward is not seen -- call
+        GenModel.invalidate_native() after that kind of surgery."""
+        if tensors is None:
+            tensors = list(itertools.chain(model.parameters(), model.buffers()))
+        return tuple((t._version, t.data_ptr()) for t in tensors)
 
     def t(self, x):
         x = x.detach().float().contiguous()
@@ -126,11 +135,21 @@ class NativeGenerator(object):
         self.arena_bytes = int(arena_bytes)
         self.last = None
         self.profile = False
+        self._stale = None
         self.phases = False          # SGNN_GEN_PHASES: per-phase CUDA-event times of the next passes (phase_table())
+
+    def stale(self):
+        """True when the parameters changed since the weight struct was built (cheap: cached tensor list)."""
+        self._stale = self.weights is None or self.weights.key != _Weights.version_key(self.model, self.weights.tensors)
+        return self._stale
 
     def _prepare(self, dev):
         m = self.model
-        if self.weights is None or self.weights.dev != dev or self.weights.key != _Weights.version_key(m):
+        stale, self._stale = self._stale, None           # GenModel.forward has just asked: do not compute the key twice
+        if stale is None:
+            stale = self.stale()
+            self._stale = None
+        if self.weights is None or self.weights.dev != dev or stale:
             self.weights = _Weights(m)
         if self.arena is None or self.arena.device != dev or self.arena.numel() < self.arena_bytes:
             self.arena = None
@@ -145,8 +164,9 @@ class NativeGenerator(object):
             raise ValueError('sgnn_b200: expected locs [n,4] and feats [n,%d], got %s and %s' % (cin, tuple(locs.shape), tuple(feats.shape)))
         if feats.shape[1] != cin:
             raise ValueError('sgnn_b200: the model takes %d input feature channel(s), got %d' % (cin, feats.shape[1]))
-        if next(m.parameters()).device != dev:
-            raise RuntimeError('sgnn_b200: model parameters on %s, features on %s' % (next(m.parameters()).device, dev))
+        pdev = self.weights.tensors[0].device if self.weights is not None else next(m.parameters()).device
+        if pdev != dev:
+            raise RuntimeError('sgnn_b200: model parameters on %s, features on %s' % (pdev, dev))
         with torch.cuda.device(dev):
             return self._forward(locs, feats, want_cand_locs, nb, dev, cand_parents)
 
