@@ -9,8 +9,9 @@
   mesh        SURVEY 8(f4): marching cubes on a scene-sized dense TSDF (96 x 320 x 256): triangle-soup kernels + host merge,
               next to the REAL reference's run_marching_cubes (oracle/_ref, compiled from its own source) on the host cores
   tc32        one 16->16 3^3 submanifold convolution and one child-mode 48->16 convolution on a surface-like site set
-              (32 blocks of 64^3, a 3-voxel shell, rows in Morton order like the generator's hierarchical order), every
-              kernel generation: the A/B tool behind DESIGN.md section 5 (hooks 0/23/24/27, 28 with SGNN_EXPERIMENTAL=1)
+              (32 blocks of 64^3, a 3-voxel shell, rows in Morton order like the generator's hierarchical order): exact FFMA
+              kernel, round-1 tcgen05 kernel, unique-row tcgen05 kernel (+ its tile plan) -- the A/B tool behind DESIGN.md section 5
+  scene       SURVEY 8(f1): sgnn_b200.scene.run_scene on a synthetic 1.29 M-site room (forward, pad removal, meshes)
 
 The headline metric lives in bench.py; this file feeds DESIGN.md §5 and the ncu captures under profiles/.
 """

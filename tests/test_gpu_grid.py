@@ -146,7 +146,8 @@ def test_rulebook_microbench_size_properties():
 
 def test_config2_block_128_conv_deconv_pair():
     """BASELINE.json configs[2] geometry: one 128^3 block @3 %, C=16 stride-2 Convolution then Deconvolution back to
-    the fine set (fp32 here; the bf16 tensor-core variant is round-2 work).  Checked against the dense identities."""
+    the fine set, fp32 on the exact kernels (the bf16 tcgen05 pair of the same geometry is tests/test_gpu_tc.py).  Checked against
+    the dense identities."""
     import dense_equiv as o1
     E = _E()
     rng = np.random.default_rng(1234)
