@@ -1,6 +1,6 @@
 // generator.cu -- native (C++) orchestration of the whole SG-NN generator forward (reference torch/model.py:371-416)
 // on top of the kernels of this library.  The reference drives ~130 scn ops + Python glue per pass from Python
-// with CPU-side metadata; here one C-ABI call enqueues the ~145 kernels of a pass (two streams on the small levels) and touches the
+// with CPU-side metadata; here one C-ABI call enqueues the ~190 kernels of a pass on one stream and touches the
 // host only to read the data-dependent row counts (4 bytes each: coarse site counts, kept-candidate counts).
 // Memory comes from a caller-provided bump arena (no cudaMalloc on the path); temporaries are released in
 // stream order.  The arithmetic is the fused composition of sgnn_b200/fused.py -- bit-identical to the
