@@ -331,6 +331,7 @@ def run_b200(args):
     # the dominant kernel's live duration.  Kept out of the bracket above because it adds one sync per step.
     conv_ms, n_conv, prof_ms = 0.0, 0, 0.0
     conv_table = []
+    phase_table = []
     if rank == 0 and getattr(model, '_native', None) is not None:
         model._native.profile = True
         torch.cuda.synchronize()
@@ -352,6 +353,13 @@ def run_b200(args):
         torch.cuda.synchronize()
         prof_ms = p0.elapsed_time(p1)
         model._native.profile = False
+        # ---- and one pass with a CUDA event at every phase boundary (SGNN_GEN_PHASES): where the step goes, in situ
+        model._native.phases = True
+        flush.fill_(1)
+        step(0)
+        torch.cuda.synchronize()
+        phase_table = [[name, round(ms * 1e3, 1)] for name, ms in model._native.phase_table()]
+        model._native.phases = False
     ms = shard.max_over_ranks(dev_ms, dev)
     vox_timed = sum(vox[i % args.sets] for i in range(args.steps))
     total_vox = shard.sum_over_ranks(vox_timed, dev)
@@ -461,6 +469,7 @@ def run_b200(args):
         'avg_launch_us': 1e3 * conv_ms / n_conv,
         'share_of_step': conv_ms / prof_ms if prof_ms > 0 else None,
         'profiled_pass_ms_per_step': prof_ms / max(args.steps, 1),
+        'phases_us_one_pass': phase_table,
         'gflops_per_step': per_set_flops / 1e9,
         'achieved_tflops_fp32': per_set_flops * args.steps / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0,
         'fp32_ffma_peak_tflops': 148 * 128 * 2 * 1.965e9 / 1e12,
