@@ -88,6 +88,23 @@ dense_conv3d_fast_kernel(DenseArgs a) {
       off[t] = (iz * a.d1 + iy) * a.d2 + ix;
     }
     float acc = 0.f;
+    if (KS == 1) {
+      // 1^3 layers (bottleneck, final, heads): one load pair per channel -- taken 8 channels at a time so that 16 loads are in
+      // flight instead of a dependent round trip per channel (26 us for the 28 -> 16 layer on 8^3 x 32 before)
+      for (int c0 = 0; c0 < cin; c0 += 8) {
+        float xv[8], wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int ci = c0 + u;
+          const bool in = ci < cin && ok[0];
+          xv[u] = in ? __ldg(dense_chan(a, b, in ? ci : 0, ivol) + off[0]) : 0.f;
+          wv[u] = ci < cin ? __ldg(a.w + (long long)co * cin + ci) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (c0 + u < cin && ok[0]) acc = fmaf(xv[u], wv[u], acc);
+      }
+    } else {
     for (int ci = 0; ci < cin; ++ci) {
       const float* src = dense_chan(a, b, ci, ivol);
       const float* wk = a.w + ((long long)co * cin + ci) * K3;
@@ -101,11 +118,121 @@ dense_conv3d_fast_kernel(DenseArgs a) {
       for (int t = 0; t < K3; ++t)
         if (ok[t]) acc = fmaf(xv[t], wv[t], acc);
     }
+    }
     float v = acc;
     if (a.scale) v = fmaf(v, __ldg(a.scale + co), __ldg(a.shift + co));
     if (a.relu) v = fmaxf(v, 0.f);
     a.out[idx] = v;
   }
+}
+
+// The two strided encoder layers (nn.Conv3d k4 s2 p1: 16 -> 24 on 8^3, 24 -> 32 on 4^3 per sample) with both operands in
+// shared memory.  One thread per output element as above (the fmaf chain of an output is sequential by definition: ci
+// ascending, then kz,ky,kx over the in-range taps), a CTA = one sample x COG output channels:
+//  * the sample's whole input is staged once, de-interleaved into the 8 PARITY PLANES of (z,y,x): output (z,y,x) reads input
+//    2z+kz-1, so for a fixed tap every thread reads the same plane at its own (z,y,x) + a constant -- consecutive positions
+//    are consecutive words: conflict-free, where the stride-2 reads of a plain layout collide 4-way;
+//  * the filters of the CTA's channels stream through in chunks of CC input channels, laid out [ci][tap][co]: a warp reads
+//    one word (same channel) or 4 consecutive words -- a broadcast;
+//  * out-of-range taps are selected to +0 instead of branched around (fmaf(+0, w, acc) == acc), so the 64 taps of a channel
+//    are 128 independent shared-memory loads followed by the chain.
+// (A first shared-memory version without the parity planes and with a branch per tap was 2x SLOWER than the global-load
+// kernel above: profiles/r02_ab_runs.txt.)
+__global__ void __launch_bounds__(256, 2)
+dense_conv3d_k4s2p1_pp_kernel(DenseArgs a, int cog, int cc, int spc) {
+  extern __shared__ __align__(16) float dcs[];
+  const int o0 = a.o0, o1 = a.o1, o2 = a.o2;
+  const int ovol = o0 * o1 * o2, ivol = 8 * ovol, cin = a.c0 + a.c1;
+  float* xin = dcs;                         // [spc samples][cin][8 planes][ovol]
+  float* wsm = dcs + spc * cin * ivol;      // [cc][64][cog]
+  // a CTA = spc samples x cog output channels (small volumes: several samples share one copy of the filters)
+  const int b0 = blockIdx.x * spc, co0 = blockIdx.y * cog, tid = threadIdx.x, nthr = blockDim.x;
+  const int ns = min(spc, a.nb - b0);
+  // staging loops: 8 independent loads in flight per thread (one load -> one dependent shared-memory store per iteration
+  // serialises a full memory round trip per element: measured 41 / 107 us per layer, most of it here)
+  const int per_s = cin * ivol;
+  for (int i0 = tid; i0 < ns * per_s; i0 += 8 * nthr) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * nthr;
+      const int sl = i / per_s, q = i - sl * per_s;
+      const int ci = q / ivol;
+      v[u] = i < ns * per_s ? __ldg(dense_chan(a, b0 + sl, ci, ivol) + (q - ci * ivol)) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * nthr;
+      if (i >= ns * per_s) break;
+      const int sl = i / per_s, q = i - sl * per_s;
+      const int ci = q / ivol, r = q - ci * ivol;
+      const int ix = r % a.d2, iy = (r / a.d2) % a.d1, iz = r / (a.d1 * a.d2);
+      const int plane = ((iz & 1) << 2) | ((iy & 1) << 1) | (ix & 1);
+      xin[sl * per_s + ci * ivol + plane * ovol + ((iz >> 1) * o1 + (iy >> 1)) * o2 + (ix >> 1)] = v[u];
+    }
+  }
+  const int sl = tid / (cog * ovol), rem = tid - sl * (cog * ovol);   // blockDim = spc * cog * ovol
+  const int col = rem / ovol, pos = rem - col * ovol;
+  const bool live = sl < ns;
+  const int x = pos % o2, y = (pos / o2) % o1, z = pos / (o1 * o2);
+  // tap k of an axis: input 2o + k - 1 = plane parity (k + 1) & 1, half-coordinate o + dk with dk = -1, 0, 0, +1
+  bool vz[4], vy[4], vx[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int dk = k == 0 ? -1 : (k == 3 ? 1 : 0);
+    vz[k] = (unsigned)(z + dk) < (unsigned)o0;
+    vy[k] = (unsigned)(y + dk) < (unsigned)o1;
+    vx[k] = (unsigned)(x + dk) < (unsigned)o2;
+  }
+  float acc = 0.f;
+  for (int c0 = 0; c0 < cin; c0 += cc) {
+    const int nc = min(cc, cin - c0);
+    __syncthreads();                         // previous chunk consumed (and, the first time, the input staged)
+    for (int i0 = tid; i0 < nc * 64 * cog; i0 += 8 * nthr) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * nthr;
+        const int t = i & 63, cl = (i >> 6) % nc, j = (i >> 6) / nc;
+        v[u] = i < nc * 64 * cog ? __ldg(a.w + ((long long)(co0 + j) * cin + c0 + cl) * 64 + t) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * nthr;
+        if (i >= nc * 64 * cog) break;
+        const int t = i & 63, cl = (i >> 6) % nc, j = (i >> 6) / nc;
+        wsm[(cl * 64 + t) * cog + j] = v[u];
+      }
+    }
+    __syncthreads();
+    for (int cl = 0; cl < nc; ++cl) {
+      const float* xc = xin + (live ? sl : 0) * per_s + (c0 + cl) * ivol + pos;
+      const float* wc = wsm + cl * 64 * cog + col;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {       // 32 taps at a time: 64 loads in flight, <= 128 registers (2 CTAs per SM)
+        float xv[32], wv[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          const int t = half * 32 + u;
+          const int kz = t >> 4, ky = (t >> 2) & 3, kx = t & 3;
+          const int dz = kz == 0 ? -1 : (kz == 3 ? 1 : 0), dy = ky == 0 ? -1 : (ky == 3 ? 1 : 0), dx = kx == 0 ? -1 : (kx == 3 ? 1 : 0);
+          const int plane = (((kz + 1) & 1) << 2) | (((ky + 1) & 1) << 1) | ((kx + 1) & 1);
+          const bool ok = vz[kz] && vy[ky] && vx[kx];
+          const int off = plane * ovol + (dz * o1 + dy) * o2 + dx;
+          xv[u] = ok ? xc[off] : 0.f;
+          wv[u] = wc[t * cog];
+        }
+#pragma unroll
+        for (int u = 0; u < 32; ++u) acc = fmaf(xv[u], wv[u], acc);
+      }
+    }
+  }
+  if (!live) return;
+  const int co = co0 + col;
+  float v = acc;
+  if (a.scale) v = fmaf(v, __ldg(a.scale + co), __ldg(a.shift + co));
+  if (a.relu) v = fmaxf(v, 0.f);
+  a.out[((long long)(b0 + sl) * a.cout + co) * ovol + pos] = v;
 }
 
 // Transposed convolution: per axis only the taps k == (o + pad) (mod stride) reach an input cell; they are
@@ -286,7 +413,20 @@ static int dense_launch(bool transposed, const float* in0, int c0, const float* 
   const long long total = (long long)nb * cout * a.o0 * a.o1 * a.o2;
   if (total == 0) return SGNN_OK;
   const int blocks = sgnn_blocks(total, 128, (int64_t)148 * 32);
-  if (!transposed && (ks == 4 || ks == 1)) {
+  const int ovol_i = a.o0 * a.o1 * a.o2;
+  int cog = 0;
+  if (!transposed && ks == 4 && stride == 2 && pad == 1 && !(d0 & 1) && !(d1 & 1) && !(d2 & 1) && ovol_i <= 256 && nb <= 65535)
+    for (int g = 256 / ovol_i > 8 ? 8 : 256 / ovol_i; g >= 1; --g)          // output channels per CTA (<= 8, <= 256 threads)
+      if (cout % g == 0) { cog = g; break; }
+  int spc = cog ? 256 / (cog * ovol_i) : 0;                              // samples per CTA: fill 256 threads
+  if (spc > nb) spc = nb;
+  if (spc < 1) spc = 1;
+  const int dcc = cog ? (64 / cog > 0 ? 64 / cog : 1) : 0;              // <= 16 KB of filters per chunk
+  const size_t dsm = cog ? ((size_t)spc * (c0 + c1) * 8 * ovol_i + (size_t)dcc * 64 * cog) * 4 : 0;
+  if (cog && dsm <= 48 * 1024) {
+    dim3 grid((unsigned)((nb + spc - 1) / spc), (unsigned)(cout / cog));
+    dense_conv3d_k4s2p1_pp_kernel<<<grid, spc * cog * ovol_i, dsm, (cudaStream_t)stream>>>(a, cog, dcc, spc);
+  } else if (!transposed && (ks == 4 || ks == 1)) {
     const int fb = sgnn_blocks(total, 64, (int64_t)148 * 64);
     if (ks == 4) dense_conv3d_fast_kernel<4><<<fb, 64, 0, (cudaStream_t)stream>>>(a);
     else dense_conv3d_fast_kernel<1><<<fb, 64, 0, (cudaStream_t)stream>>>(a);
