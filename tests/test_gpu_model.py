@@ -311,3 +311,25 @@ def _check_host_result(got, want):
         assert isinstance(got[0], list)
     else:
         assert got[0].dtype == torch.int16 and torch.equal(got[0].long(), want[0]) and torch.equal(got[1], want[1])
+
+
+def test_native_generator_follows_parameter_updates():
+    """Weights changed after the first forward (load_state_dict, in-place update) are picked up by the next one: the cached
+    weight struct is keyed by (version, address) of every parameter and buffer."""
+    import sgnn_b200
+    from sgnn_b200.synth import fill_parameters, synthetic_batch
+    dims = (32, 32, 32)
+    locs, feats = synthetic_batch(2, list(dims), 0.08)
+    a = _model(dims, 0)
+    out_a = a([locs.cuda(), feats.cuda()], ONES)
+    b = _model(dims, 5)
+    out_b = b([locs.cuda(), feats.cuda()], ONES)
+    assert not torch.equal(out_a[1][0][1], out_b[1][0][1])
+    a.load_state_dict(b.state_dict())
+    _same_outputs(a([locs.cuda(), feats.cuda()], ONES), out_b)
+    with torch.no_grad():
+        for p in a.parameters():
+            p.mul_(1.0)                                            # versions move, values do not
+        a.encoder.occpred[0].weight.neg_()
+        b.encoder.occpred[0].weight.neg_()
+    _same_outputs(a([locs.cuda(), feats.cuda()], ONES), b([locs.cuda(), feats.cuda()], ONES))

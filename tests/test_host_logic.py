@@ -96,3 +96,34 @@ def test_gloo_world2_broadcast_and_reductions():
     assert res[0][1] == res[1][1]                 # identical parameters after the one broadcast
     assert res[0][2] == res[1][2] == 11.0         # max over ranks
     assert res[0][3] == res[1][3] == 7.0          # every block owned exactly once
+
+
+def test_native_weight_cache_key_sees_updates_and_moves():
+    """The native generator caches its weight struct and checks a (version, address) key over a CACHED tensor list on every
+    forward (walking the module tree or building a state_dict per call cost more host time than the GPU pass had queued).
+    The key must change on in-place updates, load_state_dict and dtype / device style re-allocation; invalidate_native()
+    forgets everything."""
+    import itertools
+    import sgnn_b200
+    from sgnn_b200 import native
+    from sgnn_b200.synth import fill_parameters
+    m = sgnn_b200.GenModel(8, 32, 1, 16, 16, 4, True, True, 1, 1).eval()
+    fill_parameters(m, 0)
+    tensors = list(itertools.chain(m.parameters(), m.buffers()))
+    k0 = native._Weights.version_key(m, tensors)
+    assert k0 == native._Weights.version_key(m, tensors) == native._Weights.version_key(m)
+    with torch.no_grad():
+        m.surfacepred.linear.weight.mul_(2.0)                     # optimizer-style in-place update
+    k1 = native._Weights.version_key(m, tensors)
+    assert k1 != k0
+    other = sgnn_b200.GenModel(8, 32, 1, 16, 16, 4, True, True, 1, 1)
+    fill_parameters(other, 7)
+    m.load_state_dict(other.state_dict())                         # copies in place: versions move
+    k2 = native._Weights.version_key(m, tensors)
+    assert k2 != k1
+    m.double()                                                    # re-allocates: addresses move (same Parameter objects)
+    assert native._Weights.version_key(m, tensors) != k2
+    m._native_ok = True
+    m.invalidate_native()
+    assert m._native is None and m._native_ok is None
+    assert native.supported(m) is False                           # CPU / fp64 parameters: not a native-generator model
