@@ -97,14 +97,25 @@ __global__ void heads_flag_kernel(const float* __restrict__ x, int ld_x, int c, 
                                   const float* __restrict__ b_occ, const float* __restrict__ w_sdf,
                                   const float* __restrict__ b_sdf, long long n_cand,
                                   unsigned char* __restrict__ flags, float* __restrict__ cand_out) {
+  const bool vec4 = (c & 3) == 0 && (ld_x & 3) == 0 && ((size_t)x & 15) == 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_cand;
        i += (long long)gridDim.x * blockDim.x) {
     const float* xr = x + i * ld_x;
     float occ = 0.f, sdf = 0.f;
-    for (int ch = 0; ch < c; ++ch) {
-      const float v = xr[ch];
-      occ = fmaf(v, __ldg(w_occ + ch), occ);
-      sdf = fmaf(v, __ldg(w_sdf + ch), sdf);
+    if (vec4) {                       // 16-byte row loads (c, ld_x multiples of 4, x 16-byte aligned); same fmaf order
+      for (int ch = 0; ch < c; ch += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + ch);
+        occ = fmaf(v.x, __ldg(w_occ + ch), occ);         sdf = fmaf(v.x, __ldg(w_sdf + ch), sdf);
+        occ = fmaf(v.y, __ldg(w_occ + ch + 1), occ);     sdf = fmaf(v.y, __ldg(w_sdf + ch + 1), sdf);
+        occ = fmaf(v.z, __ldg(w_occ + ch + 2), occ);     sdf = fmaf(v.z, __ldg(w_sdf + ch + 2), sdf);
+        occ = fmaf(v.w, __ldg(w_occ + ch + 3), occ);     sdf = fmaf(v.w, __ldg(w_sdf + ch + 3), sdf);
+      }
+    } else {
+      for (int ch = 0; ch < c; ++ch) {
+        const float v = xr[ch];
+        occ = fmaf(v, __ldg(w_occ + ch), occ);
+        sdf = fmaf(v, __ldg(w_sdf + ch), sdf);
+      }
     }
     occ += __ldg(b_occ);
     sdf += __ldg(b_sdf);
@@ -127,6 +138,7 @@ __global__ void heads_write_kernel(const float* __restrict__ x, int ld_x, int c,
                                    int* __restrict__ count, SkipJoin sk) {
   if (count && blockIdx.x == 0 && threadIdx.x == 0) *count = offs[n_cand];
   const int sub = threadIdx.x & 7;
+  const bool st4 = (ld & 3) == 0 && ((size_t)feats & 15) == 0;
   for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3; i < n_cand;
        i += ((long long)gridDim.x * blockDim.x) >> 3) {
     if (!flags[i]) continue;
@@ -142,13 +154,18 @@ __global__ void heads_write_kernel(const float* __restrict__ x, int ld_x, int c,
     }
     float* f = feats + (long long)pos * ld;
     const float* xr = x + i * ld_x;
-    for (int ch = sub; ch < ld; ch += 8) {
-      float v = 0.f;                                         // spare columns (skip join of the next level / padding)
-      if (ch < c) v = xr[ch];
-      else if (ch == c) v = cand_out[2 * i];
-      else if (ch == c + 1) v = cand_out[2 * i + 1];
-      else if (JOIN && srow && ch < c + 2 + sk.c) v = __ldg(srow + (ch - c - 2));
-      f[ch] = v;
+    auto value = [&](int ch) -> float {
+      if (ch < c) return xr[ch];
+      if (ch == c) return cand_out[2 * i];
+      if (ch == c + 1) return cand_out[2 * i + 1];
+      if (JOIN && srow && ch < c + 2 + sk.c) return __ldg(srow + (ch - c - 2));
+      return 0.f;                                            // spare columns (skip join of the next level / padding)
+    };
+    if (st4) {                                               // rows of ld % 4 == 0 floats, 16-byte aligned: one float4 per lane
+      for (int q = sub * 4; q < ld; q += 32)
+        *reinterpret_cast<float4*>(f + q) = make_float4(value(q), value(q + 1), value(q + 2), value(q + 3));
+    } else {
+      for (int ch = sub; ch < ld; ch += 8) f[ch] = value(ch);
     }
   }
 }

@@ -98,14 +98,24 @@ __global__ void linear1_kernel(const float* __restrict__ x, int ld_x, const floa
                                const float* __restrict__ b, float* __restrict__ y, int ld_y, long long n, int cin) {
   const int q = threadIdx.x & 3;
   const int per = cin >> 2;
+  const bool vec4 = (per & 3) == 0 && (ld_x & 3) == 0 && ((size_t)x & 15) == 0;
   for (long long i0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 2; ; i0 += ((long long)gridDim.x * blockDim.x) >> 2) {
     const long long base = i0 - (i0 & 7);   // rows handled by this warp iteration: keep the warp converged for shuffles
     if (base >= n) break;
     const bool live = i0 < n;
     const float* xr = x + (live ? i0 : 0) * ld_x + q * per;
     float v[16];
+    if (vec4) {                       // per, ld_x multiples of 4 and x 16-byte aligned: 16-byte loads of the lane's quarter row
 #pragma unroll
-    for (int c = 0; c < 16; ++c) v[c] = (live && c < per) ? xr[c] : 0.f;
+      for (int c = 0; c < 16; c += 4) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live && c < per) t = *reinterpret_cast<const float4*>(xr + c);
+        v[c] = t.x; v[c + 1] = t.y; v[c + 2] = t.z; v[c + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] = (live && c < per) ? xr[c] : 0.f;
+    }
     float acc = 0.f;
 #pragma unroll
     for (int step = 0; step < 4; ++step) {
