@@ -42,3 +42,19 @@ def test_library_is_sm100a_and_uses_no_cpu_fallback():
     import pytest
     with pytest.raises(RuntimeError):
         E.coords_to_i64(torch.zeros((4, 4), dtype=torch.int32))      # CPU tensor -> loud failure
+
+
+def test_export_argument_validation_without_a_launch():
+    """sgnn_export rejects malformed segment lists on the host (no kernel is launched for these)."""
+    import ctypes as C
+    from sgnn_b200 import _lib
+    segs = (_lib.SgnnExportSeg * 17)()
+    assert _lib.lib.sgnn_export(segs, 0, None) == 0                      # nothing to do
+    assert _lib.lib.sgnn_export(segs, 17, None) != 0                     # more than SGNN_EXPORT_MAX_SEGS
+    assert _lib.lib.sgnn_export(None, 1, None) != 0
+    segs[0].n, segs[0].kind = 5, 7                                       # unknown kind
+    assert _lib.lib.sgnn_export(segs, 1, None) != 0
+    segs[0].kind, segs[0].dst = _lib.EXPORT_COPY32, None                 # non-empty segment without a destination
+    assert _lib.lib.sgnn_export(segs, 1, None) != 0
+    segs[0].n = -1
+    assert _lib.lib.sgnn_export(segs, 1, None) != 0
