@@ -197,3 +197,18 @@ def test_scene_pairs_dataset_matches_reference(tmp_path, max_height):
         b_r, b_m = sd.collate([r]), scene_io.collate([m])
         assert all(_same(b_r[k], b_m[k]) for k in b_r)
     assert tuple(my_ds[0]['sdf'].shape[1:]) == ((64 if max_height == 40 else 64), 96, 64)
+
+
+def test_save_predictions_scope_is_the_test_scene_call():
+    """sgnn_b200.scene.save_predictions mirrors the call test_scene.py:98 makes (targets None, per-level occupancy None);
+    the train.py-only forms are refused loudly instead of silently writing something else."""
+    import torch
+    from sgnn_b200 import scene
+    locs = torch.zeros((1, 4), dtype=torch.long)
+    feats = torch.zeros((1, 1))
+    for kw in ({'target_for_sdf': torch.zeros(1, 1, 2, 2, 2)}, {'target_for_occs': [None]}, {'output_occs': [None]}):
+        args = dict(target_for_sdf=None, target_for_occs=None, output_occs=None)
+        args.update(kw)
+        with pytest.raises(ValueError):
+            scene.save_predictions('/tmp/unused', ['x'], [locs, feats], args['target_for_sdf'], args['target_for_occs'], [None],
+                                   args['output_occs'], None, 3.0)
