@@ -11,7 +11,9 @@
  *   - every pointer marked "dev" is a CUDA device pointer owned by the caller;
  *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it
  *     (no host synchronisation, no allocation, no mutable global state: tuning lives in argument structs) and is re-entrant for
- *     distinct (buffers, stream) pairs;
+ *     distinct (buffers, stream) pairs.  The one exception is sgnn_generator_forward, which orchestrates a whole pass: it reads
+ *     nine data-dependent row counts back (4 bytes each, pinned), keeps per-thread caches (pinned slots, events, a side stream
+ *     per device) and, for small levels, forks work to that side stream and joins it back before it returns;
  *   - return value: SGNN_OK or a negative SGNN_E_* code; nothing throws across the ABI;
  *   - features are row-major [n_rows, ld] with `ld` (elements) >= channels;
  *   - coordinates are int32 [n,4] = (z, y, x, batch)  (model.py:321, scene_dataloader.py:17,30);
