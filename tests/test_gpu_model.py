@@ -333,3 +333,23 @@ def test_native_generator_follows_parameter_updates():
         a.encoder.occpred[0].weight.neg_()
         b.encoder.occpred[0].weight.neg_()
     _same_outputs(a([locs.cuda(), feats.cuda()], ONES), b([locs.cuda(), feats.cuda()], ONES))
+
+
+@pytest.mark.parametrize('mode', ['exact', 'tc32'])
+def test_baseline_config_teacher_forced_all_blocks(mode):
+    """configs[1] at full size once more, with NOTHING excluded: the oracle runs with the device pass's keep decisions
+    (helpers.compare_teacher_forced), so all 32 blocks are compared at every level to the end -- coordinates equal, logits within
+    1e-4, the oracle's own decisions equal to the device's except within 1e-5 of the threshold (counted), TSDF <= 1e-3."""
+    from genmodel import OracleGenModel
+    from helpers import compare_teacher_forced
+    from sgnn_b200.synth import fill_parameters, synthetic_batch
+    locs, feats = synthetic_batch(32, 64, 0.05)
+    ora = OracleGenModel()
+    fill_parameters(ora, 0)
+    ora.eval()
+    m = _model((64, 64, 64), 0)
+    m.conv_mode = mode
+    got = m([locs.cuda(), feats.cuda(), 32], ONES)
+    flips = compare_teacher_forced(ora, locs, feats, got, margin=1e-5, tol_logit=TOL_LOGIT, rtol_logit=0.0, tol_sdf=TOL_SDF,
+                                   max_flips=4, tag='configs[1] teacher-forced ' + mode)
+    assert sum(flips) <= 4
